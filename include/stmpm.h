@@ -1,0 +1,128 @@
+/* stmpm.h — C ABI of libstmpm.so: the B200-native (sm_100a) Monte Carlo trial loop of StarTrackerMPM.
+ *
+ * The reference has no FFI: its hot path is the pure-Python `simObjects` package (absent from the mount).
+ * Each entry point below cites the reference interface it replaces (file:line in /root/reference) — the call sites that
+ * pin the behaviour.  Trial semantics are frozen in docs/MODEL.md.
+ *
+ * Conventions: every function returns 0 on success, non-zero on failure (a cudaError_t value, or STMPM_E_* below) and
+ * stmpm_last_error() then holds a message.  `stream` is a cudaStream_t passed as void* (NULL = default stream); calls
+ * are stream-ordered.  Pointers named *_dev are device pointers (e.g. torch.Tensor.data_ptr()), *_host host pointers.
+ * No torch / C++ types cross this boundary.  There is no CPU fallback anywhere behind it.
+ */
+#ifndef STMPM_H
+#define STMPM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STMPM_E_ARG      10001   /* bad argument */
+#define STMPM_E_STATE    10002   /* catalog / sensor not set */
+#define STMPM_E_NOGPU    10003   /* no CUDA device */
+
+#define STMPM_NCOLS      13      /* pre-sampled input columns, order below */
+#define STMPM_NNORMAL    11      /* normal-distributed parameters in native-RNG mode */
+#define STMPM_STATS_HEAD 8       /* [n_ok, n_fail, sum_x, sum_x2, sum_ndet, x_max, under, over] then the histogram */
+#define STMPM_HIST_OCTAVES 34    /* x in [2^-14, 2^20) arcsec */
+#define STMPM_HIST_MIN_EXP (-14)
+
+/* Column order of pre-sampled inputs == DataFrame columns the reference builds in MonteCarlo.create_data
+ * (monte_carlo.py:85-105) from StarTracker.randomize / Software.randomize (monte_carlo.py:93-94); names pinned by
+ * run.sh:11-17:  RIGHT_ASCENSION, DECLINATION, ROLL [rad], FOCAL_LENGTH [px], F_ARR_EPS_X/Y/Z [px],
+ * F_ARR_PHI/THETA/PSI [deg], BASE_DEV_X/Y [px], MAX_MAGNITUDE. */
+enum { STMPM_COL_RA = 0, STMPM_COL_DEC, STMPM_COL_ROLL, STMPM_COL_F, STMPM_COL_EPS_X, STMPM_COL_EPS_Y, STMPM_COL_EPS_Z,
+       STMPM_COL_PHI, STMPM_COL_THETA, STMPM_COL_PSI, STMPM_COL_DEV_X, STMPM_COL_DEV_Y, STMPM_COL_MAX_MAG };
+
+typedef struct stmpm_handle stmpm_t;
+
+/* Software-side camera knowledge + detection rule.  Replaces the attributes quest_objective reads from
+ * Simulation.camera (StarTracker.f_len.ideal: sensitivity.py:118; SENSOR_WIDTH/HEIGHT: constants.py:97-98). */
+typedef struct {
+    double  f_ideal;      /* px; back-projection focal length (MODEL.md §4) */
+    double  half_u;       /* SENSOR_WIDTH / 2  = 512 */
+    double  half_v;       /* SENSOR_HEIGHT / 2 = 512 */
+    int32_t n_min;        /* minimum detected stars for a solve (3) */
+    int32_t hist_log2_sub;/* histogram sub-bins per octave = 2^k, 4 <= k <= 8 (8 -> 8704 bins) */
+} stmpm_sensor_cfg;
+
+/* Parameter distributions for native-RNG mode (MODEL.md §6): normal(mean, sigma) in the order
+ * FOCAL_LENGTH, F_ARR_EPS_X, _Y, _Z, F_ARR_PHI, _THETA, _PSI, BASE_DEV_X, _Y, MAX_MAGNITUDE, D_TEMP.
+ * Replaces Parameter(.ideal,.stddev) sampling in StarTracker/Software/Orbit.randomize (monte_carlo.py:93-95;
+ * sensitivity.py:43-44) and the thermal focal update (sensitivity.py:115-118). */
+typedef struct {
+    double mean[STMPM_NNORMAL];
+    double sigma[STMPM_NNORMAL];
+    double thermal_coef;  /* FOCAL_THERMAL_COEFFICIENT */
+} stmpm_dist;
+
+/* Final reductions: driver.py:321-324 (failure rate, half-normal sigma/mean), toolplot.py:82 (RMS). */
+typedef struct {
+    double n_ok, n_fail, fail_rate;
+    double mean, std, rms;
+    double sigma_halfnormal, mean_halfnormal;
+    double p50, p90, p99, p999, x_max;
+    double mean_ndet;
+} stmpm_summary;
+
+const char* stmpm_last_error(void);
+int stmpm_version(void);
+
+int stmpm_create(stmpm_t** h, int device);
+int stmpm_destroy(stmpm_t* h);
+/* sm_count, max dynamic shared memory per block, SM clock kHz, memory clock kHz */
+int stmpm_device_info(stmpm_t* h, int32_t* sm_count, int64_t* smem_per_block, int32_t* sm_khz, int32_t* mem_khz);
+
+/* Catalog sorted by sky-grid cell (host pointers; uploaded once).  xyz is S x 3 row-major float64 unit vectors,
+ * star_id the Philox key of each row (MODEL.md §5).  Band b (n_bands equal declination bands from -pi/2) has n_ra[b]
+ * equal RA cells; cell_start has sum(n_ra)+1 entries.  Replaces the BSC5 catalog the reference loads from
+ * utils/BSC5PKL.pkl (constants.py:32-33). */
+int stmpm_set_catalog(stmpm_t* h, const double* xyz_host, const float* mag_host, const int32_t* star_id_host,
+                      int32_t n_stars, int32_t n_bands, const int32_t* n_ra_host, const int32_t* cell_start_host);
+int stmpm_set_sensor(stmpm_t* h, const stmpm_sensor_cfg* cfg);
+
+int stmpm_stats_len(const stmpm_t* h, int64_t* n_doubles);
+int stmpm_stats_finalize(const stmpm_t* h, const double* packed_host, stmpm_summary* out);
+
+/* (1) Pre-sampled mode == Simulation.run_sim(params, obj_func=quest_objective[, trueData]) over n DataFrame rows
+ * (monte_carlo.py:52; sensitivity.py:77).  cols_dev: STMPM_NCOLS device pointers to n float64 each.
+ * err_arcsec_dev[n] = QUATERNION_ERROR_[arcsec] (toolplot.py:71), -1 = failed trial; n_det_dev[n] = detected stars.
+ * stats_dev (optional) is accumulated into (+=), not cleared.  precision = 64 or 32. */
+int stmpm_trials_presampled(stmpm_t* h, int precision, int64_t n, uint64_t seed, int64_t trial0,
+                            const double* const* cols_dev, double* err_arcsec_dev, int32_t* n_det_dev,
+                            double* stats_dev, void* stream);
+
+/* (2) Native-RNG mode == MonteCarlo.create_data + Simulation.run_sim fused (monte_carlo.py:48-58): parameters are drawn
+ * on the device from Philox streams keyed by (seed, global trial index).  n_segments independent parameter sets (a
+ * sensitivity grid point / an orbit step: sensitivity.py:39-55) of trials_per_segment trials each; segment s uses
+ * dists_host[s], global trial indices trial0 + s*trials_per_segment + i, and accumulates into
+ * stats_dev[s*stats_len ...].  Records (optional, may be NULL) are n_segments*trials_per_segment long. */
+int stmpm_trials_rng(stmpm_t* h, int precision, int64_t n_segments, int64_t trials_per_segment, uint64_t seed,
+                     int64_t trial0, const stmpm_dist* dists_host, double* err_arcsec_dev, int32_t* n_det_dev,
+                     double* stats_dev, void* stream);
+
+/* The seeded generator of config 2: fills STMPM_NCOLS device columns with exactly the parameters native-RNG mode draws
+ * for trials trial0 .. trial0+n-1 (so presampled(fill(...)) == rng(...) trial for trial). */
+int stmpm_fill_presampled(stmpm_t* h, int64_t n, uint64_t seed, int64_t trial0, const stmpm_dist* dist_host,
+                          double* const* cols_dev, void* stream);
+
+/* Host-buffer entry points (the call Simulation.run_sim makes): chunked, double-buffered H2D -> kernel -> D2H on
+ * internal streams; returns after the results are in the host buffers.  Host buffers should be pinned for full PCIe
+ * rate (pageable works, slower).  stats_host (optional) receives the packed statistics of this call. */
+int stmpm_run_presampled_host(stmpm_t* h, int precision, int64_t n, uint64_t seed, int64_t trial0,
+                              const double* const* cols_host, double* err_arcsec_host, int32_t* n_det_host,
+                              double* stats_host);
+int stmpm_run_rng_host(stmpm_t* h, int precision, int64_t n_segments, int64_t trials_per_segment, uint64_t seed,
+                       int64_t trial0, const stmpm_dist* dists_host, double* err_arcsec_host, int32_t* n_det_host,
+                       double* stats_host);
+
+/* FMA-chain microbenchmark: measured FP64 / FP32 FMA peak of this GPU in TFLOP/s (roofline denominator). */
+int stmpm_fma_peak(stmpm_t* h, int precision, double* tflops);
+/* Number of kernels this library has launched on this handle (bench.py's gpu_launches claim). */
+int stmpm_launch_count(const stmpm_t* h, int64_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STMPM_H */

@@ -1,0 +1,89 @@
+"""ctypes binding of libstmpm.so — one-to-one with include/stmpm.h.  No compute happens in Python; there is no fallback:
+a missing library or GPU raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import LIB_PATH
+
+NCOLS = 13
+NNORMAL = 11
+STATS_HEAD = 8
+HIST_OCTAVES = 34
+HIST_MIN_EXP = -14
+
+COLUMNS = ("RIGHT_ASCENSION", "DECLINATION", "ROLL", "FOCAL_LENGTH",
+           "F_ARR_EPS_X", "F_ARR_EPS_Y", "F_ARR_EPS_Z",
+           "F_ARR_PHI", "F_ARR_THETA", "F_ARR_PSI",
+           "BASE_DEV_X", "BASE_DEV_Y", "MAX_MAGNITUDE")
+NORMAL_PARAMS = ("FOCAL_LENGTH", "F_ARR_EPS_X", "F_ARR_EPS_Y", "F_ARR_EPS_Z", "F_ARR_PHI", "F_ARR_THETA",
+                 "F_ARR_PSI", "BASE_DEV_X", "BASE_DEV_Y", "MAX_MAGNITUDE", "D_TEMP")
+
+# every symbol include/stmpm.h declares (tests check that the library exports each one)
+EXPORTS = ("stmpm_last_error", "stmpm_version", "stmpm_create", "stmpm_destroy", "stmpm_device_info",
+           "stmpm_set_catalog", "stmpm_set_sensor", "stmpm_stats_len", "stmpm_stats_finalize",
+           "stmpm_trials_presampled", "stmpm_trials_rng", "stmpm_fill_presampled", "stmpm_run_presampled_host",
+           "stmpm_run_rng_host", "stmpm_fma_peak", "stmpm_launch_count")
+
+
+class SensorCfg(C.Structure):
+    _fields_ = [("f_ideal", C.c_double), ("half_u", C.c_double), ("half_v", C.c_double),
+                ("n_min", C.c_int32), ("hist_log2_sub", C.c_int32)]
+
+
+class Dist(C.Structure):
+    _fields_ = [("mean", C.c_double * NNORMAL), ("sigma", C.c_double * NNORMAL), ("thermal_coef", C.c_double)]
+
+
+class Summary(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("n_ok", "n_fail", "fail_rate", "mean", "std", "rms", "sigma_halfnormal",
+                                          "mean_halfnormal", "p50", "p90", "p99", "p999", "x_max", "mean_ndet")]
+
+
+class StmpmError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libstmpm.so (built in-tree by startrackermpm_b200.build). Raises if it is missing: no fallback exists."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise StmpmError(f"{LIB_PATH} not found: build it with `python -m startrackermpm_b200.build` "
+                         "(there is no CPU fallback for the trial loop)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, u64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double
+    P = C.POINTER
+    lib.stmpm_last_error.restype = C.c_char_p
+    lib.stmpm_last_error.argtypes = []
+    lib.stmpm_version.restype = C.c_int
+    lib.stmpm_create.argtypes = [P(vp), C.c_int]
+    lib.stmpm_destroy.argtypes = [vp]
+    lib.stmpm_device_info.argtypes = [vp, P(i32), P(i64), P(i32), P(i32)]
+    lib.stmpm_set_catalog.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
+    lib.stmpm_set_sensor.argtypes = [vp, P(SensorCfg)]
+    lib.stmpm_stats_len.argtypes = [vp, P(i64)]
+    lib.stmpm_stats_finalize.argtypes = [vp, vp, P(Summary)]
+    lib.stmpm_trials_presampled.argtypes = [vp, C.c_int, i64, u64, i64, P(vp), vp, vp, vp, vp]
+    lib.stmpm_trials_rng.argtypes = [vp, C.c_int, i64, i64, u64, i64, P(Dist), vp, vp, vp, vp]
+    lib.stmpm_fill_presampled.argtypes = [vp, i64, u64, i64, P(Dist), P(vp), vp]
+    lib.stmpm_run_presampled_host.argtypes = [vp, C.c_int, i64, u64, i64, P(vp), vp, vp, vp]
+    lib.stmpm_run_rng_host.argtypes = [vp, C.c_int, i64, i64, u64, i64, P(Dist), vp, vp, vp]
+    lib.stmpm_fma_peak.argtypes = [vp, C.c_int, P(dbl)]
+    lib.stmpm_launch_count.argtypes = [vp, P(i64)]
+    for name in EXPORTS:
+        if name not in ("stmpm_last_error",):
+            getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().stmpm_last_error()
+        raise StmpmError(f"libstmpm error {rc}: {msg.decode() if msg else '?'}")

@@ -1,0 +1,718 @@
+// stmpm.cu — kernels + C ABI (include/stmpm.h) of the B200-native StarTrackerMPM Monte Carlo trial loop.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC  (see build.py)
+//
+// Kernel design: persistent CTAs, one per SM, 512 threads, one trial per thread.  The fp32 copy of the
+// sky-grid-sorted catalog (16 B/star), the cell index and a log-linear error histogram live in shared memory; the
+// exact fp64 star records (one 32 B sector each) are gathered from L1/L2 only for pre-filter survivors.
+#include "../../include/stmpm.h"
+#include "stmpm_device.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace stmpm;
+
+// ------------------------------------------------------------------------------------------------ kernel arguments
+struct KArgs {
+    const float4* cat32;
+    const StarRec* cat64;
+    const uint16_t* cell_start;   // n_cells + 1 (padded)
+    const int2* band_tab;         // (cell_base, n_ra) per band
+    int n_stars, n_cells_pad, n_bands;
+    float inv_band_h;
+    double f_ideal, half_u, half_v;
+    int n_min, hist_shift, n_bins;   // hist_shift = 52 - log2(sub-bins per octave)
+    long long n_segments, trials_per_segment, trial0, part_len;
+    int parts_per_segment;
+    uint32_t k0, k1;
+    const double* cols[STMPM_NCOLS];
+    const DistDev* dists;         // per-segment distributions (n_segments > 1)
+    DistDev dist0;                // the single segment's distribution (n_segments == 1): no device buffer to race on
+    double* err;
+    int* ndet;
+    double* stats;
+    long long stats_len;
+};
+
+struct SmemLayout {
+    size_t cat32, cell_start, band_tab, hist, list, red, total;
+};
+static SmemLayout smem_layout(int n_stars, int n_cells_pad, int n_bands, int n_bins) {
+    SmemLayout L;
+    size_t o = 0;
+    L.cat32 = o;      o += (size_t)n_stars * 16;
+    L.cell_start = o; o += (((size_t)n_cells_pad * 2) + 15) / 16 * 16;
+    L.band_tab = o;   o += (((size_t)n_bands * 8) + 15) / 16 * 16;
+    L.hist = o;       o += (size_t)n_bins * 4;
+    L.list = o;       o += (size_t)LIST_CAP * TPB * 2;
+    L.red = o;        o += (size_t)(TPB / 32) * 8 * 8;
+    L.total = o;
+    return L;
+}
+
+// ------------------------------------------------------------------------------------------------ the trial kernel
+// MODE 0: pre-sampled columns.  MODE 1: native RNG.  PREC 64 / 32: per-star arithmetic.
+template <int MODE, int PREC>
+__global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const SmemLayout L) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float4* s_cat = reinterpret_cast<float4*>(smem + L.cat32);
+    uint16_t* s_cell = reinterpret_cast<uint16_t*>(smem + L.cell_start);
+    int2* s_band = reinterpret_cast<int2*>(smem + L.band_tab);
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem + L.hist);
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(smem + L.list) + threadIdx.x;   // entry j at s_list[j * TPB]
+    double* s_red = reinterpret_cast<double*>(smem + L.red);
+
+    // ---- stage the catalog + grid into shared memory (once per CTA; the CTA is persistent)
+    {
+        const uint4* g = reinterpret_cast<const uint4*>(a.cat32);
+        uint4* s = reinterpret_cast<uint4*>(s_cat);
+        for (int i = threadIdx.x; i < a.n_stars; i += TPB) s[i] = __ldg(g + i);
+        for (int i = threadIdx.x; i < a.n_cells_pad; i += TPB) s_cell[i] = __ldg(a.cell_start + i);
+        for (int i = threadIdx.x; i < a.n_bands; i += TPB) s_band[i] = __ldg(a.band_tab + i);
+        for (int i = threadIdx.x; i < a.n_bins + 2; i += TPB) s_hist[i] = 0u;
+    }
+    __syncthreads();
+
+    const long long n_units = a.n_segments * (long long)a.parts_per_segment;
+    for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const long long seg = unit / a.parts_per_segment;
+        const long long part = unit - seg * a.parts_per_segment;
+        const long long t_begin = part * a.part_len;
+        const long long t_end = min(t_begin + a.part_len, a.trials_per_segment);
+        const bool want_stats = a.stats != nullptr;
+
+        DistDev dist;
+        if (MODE == 1) dist = (a.n_segments == 1) ? a.dist0 : a.dists[seg];
+
+        // per-thread streaming accumulators (MODEL.md §9)
+        unsigned int acc_ok = 0, acc_fail = 0;
+        unsigned long long acc_ndet = 0;
+        double acc_x = 0.0, acc_xx = 0.0, acc_max = 0.0;
+
+        for (long long tb = t_begin; tb < t_end; tb += TPB) {   // warp-uniform trip count
+            const long long t = tb + threadIdx.x;
+            const bool valid = t < t_end;
+            const long long rec = seg * a.trials_per_segment + t;          // record / global trial offset
+            const unsigned long long gidx = (unsigned long long)(a.trial0 + rec);
+            const uint32_t t_lo = (uint32_t)gidx, t_hi = (uint32_t)(gidx >> 32);
+
+            TrialParams p;
+            if (MODE == 0) {
+                if (valid) {
+                    p.ra = __ldcs(a.cols[0] + rec);     p.dec = __ldcs(a.cols[1] + rec);
+                    p.roll = __ldcs(a.cols[2] + rec);   p.f = __ldcs(a.cols[3] + rec);
+                    p.ex = __ldcs(a.cols[4] + rec);     p.ey = __ldcs(a.cols[5] + rec);
+                    p.ez = __ldcs(a.cols[6] + rec);     p.phi = __ldcs(a.cols[7] + rec);
+                    p.theta = __ldcs(a.cols[8] + rec);  p.psi = __ldcs(a.cols[9] + rec);
+                    p.devx = __ldcs(a.cols[10] + rec);  p.devy = __ldcs(a.cols[11] + rec);
+                    p.maxmag = __ldcs(a.cols[12] + rec);
+                } else {
+                    p.ra = p.dec = p.roll = 0.0; p.f = 1000.0; p.ex = p.ey = p.ez = p.phi = p.theta = p.psi = 0.0;
+                    p.devx = p.devy = 0.0; p.maxmag = -100.0;
+                }
+            } else {
+                sample_params(dist, t_lo, t_hi, a.k0, a.k1, p);
+            }
+
+            TrialCtx c;
+            trial_setup(p, a.half_u, a.half_v, c);
+
+            // ---- sky-grid scan state (fp32, conservative)
+            int b = max(0, (int)floorf((c.dec0 - c.cone + 1.57079633f) * a.inv_band_h));
+            const int b_hi = min(a.n_bands - 1, (int)floorf((c.dec0 + c.cone + 1.57079633f) * a.inv_band_h));
+            int i = 0, i_end = 0, pi = 0, p_end = 0;
+            bool scanning = valid;
+            int cnt = 0, n_det = 0;
+            double B[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            float Bf[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+
+            do {
+                // ---- phase A: scan cells, push pre-filter survivors onto the per-thread list
+                while (scanning && cnt < LIST_CAP) {
+                    if (i >= i_end) {
+                        if (pi < p_end) { i = pi; i_end = p_end; pi = p_end = 0; continue; }
+                        if (b > b_hi) { scanning = false; break; }
+                        const int2 bt = s_band[b];
+                        ++b;
+                        const int base = bt.x, n = bt.y;
+                        if (c.dalpha < 0.0f) { i = s_cell[base]; i_end = s_cell[base + n]; continue; }
+                        const float inv_w = (float)n * 0.159154943f;
+                        const int c_lo = (int)floorf((c.ra0 - c.dalpha) * inv_w);
+                        const int c_hi = (int)floorf((c.ra0 + c.dalpha) * inv_w);
+                        const int count = c_hi - c_lo + 1;
+                        if (count >= n) { i = s_cell[base]; i_end = s_cell[base + n]; continue; }
+                        int lo = c_lo % n;
+                        if (lo < 0) lo += n;
+                        if (lo + count <= n) { i = s_cell[base + lo]; i_end = s_cell[base + lo + count]; }
+                        else {
+                            i = s_cell[base + lo]; i_end = s_cell[base + n];
+                            pi = s_cell[base]; p_end = s_cell[base + lo + count - n];
+                        }
+                        continue;
+                    }
+                    if (prefilter(c, s_cat[i])) { s_list[cnt * TPB] = (uint16_t)i; ++cnt; }
+                    ++i;
+                }
+                __syncwarp();
+                // ---- phase B: exact evaluation of the listed stars (lanes in lock-step)
+                for (int j = 0; j < cnt; ++j) {
+                    const int idx = s_list[j * TPB];
+                    StarRec s;
+                    {
+                        const double2* g = reinterpret_cast<const double2*>(a.cat64 + idx);
+                        const double2 lo = __ldg(g), hi = __ldg(g + 1);
+                        s.x = lo.x; s.y = lo.y; s.z = hi.x;
+                        s.star_id = (uint32_t)(__double_as_longlong(hi.y) & 0xffffffffll);
+                    }
+                    bool det;
+                    if (PREC == 64) det = star_exact(c, s, t_lo, t_hi, a.k0, a.k1, a.f_ideal, a.half_u, a.half_v, B);
+                    else det = star_f32(c, s, t_lo, t_hi, a.k0, a.k1, a.f_ideal, a.half_u, a.half_v, Bf, B);
+                    n_det += det ? 1 : 0;
+                }
+                cnt = 0;
+            } while (__any_sync(0xffffffffu, scanning));
+
+            // ---- solve + record
+            double err = -1.0;
+            if (PREC == 32) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) B[k] += (double)Bf[k];
+            }
+            if (n_det >= a.n_min) err = quest_error_arcsec(B, c.C, n_det);
+            if (valid) {
+                if (a.err) __stcs(a.err + rec, err);
+                if (a.ndet) __stcs(a.ndet + rec, n_det);
+                if (want_stats) {
+                    acc_ndet += (unsigned long long)n_det;
+                    if (err >= 0.0) {
+                        ++acc_ok;
+                        acc_x += err;
+                        acc_xx = fma(err, err, acc_xx);
+                        acc_max = fmax(acc_max, err);
+                        const long long e = (__double_as_longlong(err) >> a.hist_shift)
+                                            - ((long long)(1023 + STMPM_HIST_MIN_EXP) << (52 - a.hist_shift));
+                        int bin = e < 0 ? -1 : (e >= a.n_bins ? a.n_bins : (int)e);
+                        if (bin >= 0 && bin < a.n_bins) atomicAdd(&s_hist[bin], 1u);
+                        else if (bin < 0) atomicAdd(&s_hist[a.n_bins], 1u);       // under
+                        else atomicAdd(&s_hist[a.n_bins + 1], 1u);                 // over
+                    } else {
+                        ++acc_fail;
+                    }
+                }
+            }
+        }
+
+        // ---- unit epilogue: block reduction of the moments, one atomic per CTA per quantity; histogram flush
+        if (want_stats) {
+            double v[5] = {(double)acc_ok, (double)acc_fail, acc_x, acc_xx, (double)acc_ndet};
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+                acc_max = fmax(acc_max, __shfl_xor_sync(0xffffffffu, acc_max, off));
+            }
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) s_red[warp * 8 + k] = v[k];
+                s_red[warp * 8 + 5] = acc_max;
+            }
+            __syncthreads();
+            double* st = a.stats + seg * a.stats_len;
+            if (threadIdx.x < 6) {
+                double r = 0.0;
+                for (int w = 0; w < TPB / 32; ++w)
+                    r = (threadIdx.x == 5) ? fmax(r, s_red[w * 8 + 5]) : r + s_red[w * 8 + threadIdx.x];
+                if (threadIdx.x == 5)
+                    atomicMax(reinterpret_cast<unsigned long long*>(st + 5), (unsigned long long)__double_as_longlong(r));
+                else if (r != 0.0) atomicAdd(st + threadIdx.x, r);
+            }
+            for (int k = threadIdx.x; k < a.n_bins + 2; k += TPB) {
+                const uint32_t h = s_hist[k];
+                if (h) {
+                    const int slot = k < a.n_bins ? STMPM_STATS_HEAD + k : (k == a.n_bins ? 6 : 7);
+                    atomicAdd(st + slot, (double)h);
+                    s_hist[k] = 0u;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ generator kernel
+__global__ void __launch_bounds__(256) fill_presampled_kernel(long long n, long long trial0, uint32_t k0, uint32_t k1,
+                                                              DistDev dist, double* c0, double* c1, double* c2,
+                                                              double* c3, double* c4, double* c5, double* c6,
+                                                              double* c7, double* c8, double* c9, double* c10,
+                                                              double* c11, double* c12) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long g = (unsigned long long)(trial0 + t);
+        TrialParams p;
+        sample_params(dist, (uint32_t)g, (uint32_t)(g >> 32), k0, k1, p);
+        c0[t] = p.ra; c1[t] = p.dec; c2[t] = p.roll; c3[t] = p.f; c4[t] = p.ex; c5[t] = p.ey; c6[t] = p.ez;
+        c7[t] = p.phi; c8[t] = p.theta; c9[t] = p.psi; c10[t] = p.devx; c11[t] = p.devy; c12[t] = p.maxmag;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ FMA peak kernels
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T b) {
+    T x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = (T)(threadIdx.x + k);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = x[k] * a + b;   // contracted to FMA
+    }
+    T s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += x[k];
+    if (s == (T)12345.678) out[0] = s;   // keep the chain alive without a store in practice
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail((int)e_, std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+    } while (0)
+
+struct stmpm_handle {
+    int device = 0;
+    cudaDeviceProp prop{};
+    // catalog
+    float4* cat32 = nullptr;
+    StarRec* cat64 = nullptr;
+    uint16_t* cell_start = nullptr;
+    int2* band_tab = nullptr;
+    int n_stars = 0, n_cells_pad = 0, n_bands = 0;
+    bool have_catalog = false, have_sensor = false;
+    stmpm_sensor_cfg cfg{};
+    int n_bins = 0;
+    // rng dists
+    DistDev* dists = nullptr;
+    long long dists_cap = 0;
+    // host pipeline
+    static constexpr int NBUF = 3;
+    cudaStream_t streams[NBUF] = {nullptr, nullptr, nullptr};
+    double* stage_cols[NBUF] = {nullptr, nullptr, nullptr};
+    double* stage_err[NBUF] = {nullptr, nullptr, nullptr};
+    int* stage_ndet[NBUF] = {nullptr, nullptr, nullptr};
+    long long stage_cap = 0;
+    double* stage_stats = nullptr;
+    long long stage_stats_cap = 0;
+    long long launches = 0;
+    size_t smem_attr_set[2][2] = {{0, 0}, {0, 0}};
+};
+
+extern "C" const char* stmpm_last_error(void) { return g_err.c_str(); }
+extern "C" int stmpm_version(void) { return 100; }
+
+extern "C" int stmpm_create(stmpm_t** out, int device) {
+    if (!out) return fail(STMPM_E_ARG, "stmpm_create: null out pointer");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(STMPM_E_NOGPU, std::string("stmpm_create: no CUDA device (") + cudaGetErrorString(e) +
+                                       "); this library has no CPU fallback");
+    if (device < 0 || device >= n) return fail(STMPM_E_ARG, "stmpm_create: bad device index");
+    CK(cudaSetDevice(device));
+    stmpm_handle* h = new stmpm_handle();
+    h->device = device;
+    CK(cudaGetDeviceProperties(&h->prop, device));
+    for (int i = 0; i < stmpm_handle::NBUF; ++i) CK(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
+    *out = h;
+    return 0;
+}
+
+static void free_stage(stmpm_handle* h) {
+    for (int i = 0; i < stmpm_handle::NBUF; ++i) {
+        cudaFree(h->stage_cols[i]); cudaFree(h->stage_err[i]); cudaFree(h->stage_ndet[i]);
+        h->stage_cols[i] = nullptr; h->stage_err[i] = nullptr; h->stage_ndet[i] = nullptr;
+    }
+    h->stage_cap = 0;
+}
+
+extern "C" int stmpm_destroy(stmpm_t* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaFree(h->cat32); cudaFree(h->cat64); cudaFree(h->cell_start); cudaFree(h->band_tab); cudaFree(h->dists);
+    cudaFree(h->stage_stats);
+    free_stage(h);
+    for (int i = 0; i < stmpm_handle::NBUF; ++i) if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
+    delete h;
+    return 0;
+}
+
+extern "C" int stmpm_device_info(stmpm_t* h, int32_t* sm_count, int64_t* smem_per_block, int32_t* sm_khz,
+                                 int32_t* mem_khz) {
+    if (!h) return fail(STMPM_E_ARG, "null handle");
+    if (sm_count) *sm_count = h->prop.multiProcessorCount;
+    if (smem_per_block) *smem_per_block = (int64_t)h->prop.sharedMemPerBlockOptin;
+    int v = 0;
+    if (sm_khz) { cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, h->device); *sm_khz = v; }
+    if (mem_khz) { cudaDeviceGetAttribute(&v, cudaDevAttrMemoryClockRate, h->device); *mem_khz = v; }
+    return 0;
+}
+
+extern "C" int stmpm_set_catalog(stmpm_t* h, const double* xyz, const float* mag, const int32_t* star_id,
+                                 int32_t n_stars, int32_t n_bands, const int32_t* n_ra, const int32_t* cell_start) {
+    if (!h || !xyz || !mag || !star_id || !n_ra || !cell_start) return fail(STMPM_E_ARG, "stmpm_set_catalog: null");
+    if (n_stars <= 0 || n_stars > 65535)
+        return fail(STMPM_E_ARG, "stmpm_set_catalog: n_stars must be in [1, 65535] (16-bit shared-memory cell index)");
+    if (n_bands <= 0 || n_bands > 4096) return fail(STMPM_E_ARG, "stmpm_set_catalog: bad n_bands");
+    CK(cudaSetDevice(h->device));
+    long long n_cells = 0;
+    std::vector<int2> bt(n_bands);
+    for (int b = 0; b < n_bands; ++b) {
+        if (n_ra[b] <= 0) return fail(STMPM_E_ARG, "stmpm_set_catalog: n_ra must be positive");
+        bt[b] = make_int2((int)n_cells, n_ra[b]);
+        n_cells += n_ra[b];
+    }
+    if (cell_start[0] != 0 || cell_start[n_cells] != n_stars)
+        return fail(STMPM_E_ARG, "stmpm_set_catalog: cell_start must run from 0 to n_stars");
+    const int n_pad = (int)((n_cells + 1 + 7) / 8 * 8);
+    std::vector<uint16_t> cs(n_pad, (uint16_t)n_stars);
+    for (long long c = 0; c <= n_cells; ++c) {
+        if (c && cell_start[c] < cell_start[c - 1]) return fail(STMPM_E_ARG, "stmpm_set_catalog: cell_start not sorted");
+        cs[c] = (uint16_t)cell_start[c];
+    }
+    std::vector<float4> c32(n_stars);
+    std::vector<StarRec> c64(n_stars);
+    for (int i = 0; i < n_stars; ++i) {
+        c32[i] = make_float4((float)xyz[3 * i], (float)xyz[3 * i + 1], (float)xyz[3 * i + 2], mag[i]);
+        c64[i].x = xyz[3 * i]; c64[i].y = xyz[3 * i + 1]; c64[i].z = xyz[3 * i + 2];
+        c64[i].star_id = (uint32_t)star_id[i]; c64[i].mag = mag[i];
+    }
+    cudaFree(h->cat32); cudaFree(h->cat64); cudaFree(h->cell_start); cudaFree(h->band_tab);
+    h->cat32 = nullptr; h->cat64 = nullptr; h->cell_start = nullptr; h->band_tab = nullptr;
+    CK(cudaMalloc(&h->cat32, sizeof(float4) * n_stars));
+    CK(cudaMalloc(&h->cat64, sizeof(StarRec) * n_stars));
+    CK(cudaMalloc(&h->cell_start, sizeof(uint16_t) * n_pad));
+    CK(cudaMalloc(&h->band_tab, sizeof(int2) * n_bands));
+    CK(cudaMemcpy(h->cat32, c32.data(), sizeof(float4) * n_stars, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->cat64, c64.data(), sizeof(StarRec) * n_stars, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->cell_start, cs.data(), sizeof(uint16_t) * n_pad, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->band_tab, bt.data(), sizeof(int2) * n_bands, cudaMemcpyHostToDevice));
+    h->n_stars = n_stars; h->n_cells_pad = n_pad; h->n_bands = n_bands;
+    h->have_catalog = true;
+    return 0;
+}
+
+extern "C" int stmpm_set_sensor(stmpm_t* h, const stmpm_sensor_cfg* cfg) {
+    if (!h || !cfg) return fail(STMPM_E_ARG, "stmpm_set_sensor: null");
+    if (!(cfg->f_ideal > 0) || !(cfg->half_u > 0) || !(cfg->half_v > 0) || cfg->n_min < 2)
+        return fail(STMPM_E_ARG, "stmpm_set_sensor: f_ideal, half_u, half_v must be > 0 and n_min >= 2");
+    if (cfg->hist_log2_sub < 4 || cfg->hist_log2_sub > 8)
+        return fail(STMPM_E_ARG, "stmpm_set_sensor: hist_log2_sub must be in [4, 8]");
+    h->cfg = *cfg;
+    h->n_bins = STMPM_HIST_OCTAVES << cfg->hist_log2_sub;
+    h->have_sensor = true;
+    return 0;
+}
+
+extern "C" int stmpm_stats_len(const stmpm_t* h, int64_t* n) {
+    if (!h || !n) return fail(STMPM_E_ARG, "stmpm_stats_len: null");
+    if (!h->have_sensor) return fail(STMPM_E_STATE, "stmpm_stats_len: call stmpm_set_sensor first");
+    *n = STMPM_STATS_HEAD + h->n_bins;
+    return 0;
+}
+
+// percentile from the log-linear histogram: bins are linear inside each octave
+static double hist_percentile(const double* hist, int n_bins, int log2_sub, double under, double n_ok, double q) {
+    const double target = q * n_ok;
+    double cum = under;
+    if (target <= cum) return std::ldexp(1.0, STMPM_HIST_MIN_EXP);
+    for (int b = 0; b < n_bins; ++b) {
+        const double c = hist[b];
+        if (c > 0 && cum + c >= target) {
+            const int oct = b >> log2_sub, sub = b & ((1 << log2_sub) - 1);
+            const double base = std::ldexp(1.0, STMPM_HIST_MIN_EXP + oct);
+            const double w = base / (double)(1 << log2_sub);
+            return base + w * ((double)sub + (target - cum) / c);
+        }
+        cum += c;
+    }
+    return std::ldexp(1.0, STMPM_HIST_MIN_EXP + STMPM_HIST_OCTAVES);
+}
+
+extern "C" int stmpm_stats_finalize(const stmpm_t* h, const double* s, stmpm_summary* o) {
+    if (!h || !s || !o) return fail(STMPM_E_ARG, "stmpm_stats_finalize: null");
+    if (!h->have_sensor) return fail(STMPM_E_STATE, "stmpm_stats_finalize: call stmpm_set_sensor first");
+    std::memset(o, 0, sizeof(*o));
+    const double n = s[0], nf = s[1];
+    o->n_ok = n; o->n_fail = nf;
+    o->fail_rate = (n + nf) > 0 ? nf / (n + nf) : 0.0;          // driver.py:321-322
+    o->mean_ndet = (n + nf) > 0 ? s[4] / (n + nf) : 0.0;
+    o->x_max = s[5];
+    if (n > 0) {
+        o->mean = s[2] / n;
+        o->rms = std::sqrt(s[3] / n);                            // toolplot.py:82
+        const double var = n > 1 ? std::max(0.0, (s[3] - s[2] * s[2] / n) / (n - 1.0)) : 0.0;   // pandas .std(): ddof=1
+        o->std = std::sqrt(var);
+        o->sigma_halfnormal = o->std / std::sqrt(1.0 - 2.0 / M_PI);      // driver.py:290,324
+        o->mean_halfnormal = o->sigma_halfnormal * std::sqrt(2.0 / M_PI); // driver.py:291,323
+        const double* hist = s + STMPM_STATS_HEAD;
+        o->p50 = hist_percentile(hist, h->n_bins, h->cfg.hist_log2_sub, s[6], n, 0.50);
+        o->p90 = hist_percentile(hist, h->n_bins, h->cfg.hist_log2_sub, s[6], n, 0.90);
+        o->p99 = hist_percentile(hist, h->n_bins, h->cfg.hist_log2_sub, s[6], n, 0.99);
+        o->p999 = hist_percentile(hist, h->n_bins, h->cfg.hist_log2_sub, s[6], n, 0.999);
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ launch helper
+template <int MODE, int PREC>
+static int launch_trials(stmpm_handle* h, KArgs& a, cudaStream_t st) {
+    const SmemLayout L = smem_layout(a.n_stars, a.n_cells_pad, a.n_bands, a.n_bins + 2);
+    if (L.total > (size_t)h->prop.sharedMemPerBlockOptin)
+        return fail(STMPM_E_ARG, "catalog too large for shared-memory staging (" + std::to_string(L.total) + " B)");
+    auto kern = trials_kernel<MODE, PREC>;
+    size_t& cached = h->smem_attr_set[MODE][PREC == 64 ? 0 : 1];
+    if (cached < L.total) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+        cached = L.total;
+    }
+    const int n_sm = h->prop.multiProcessorCount;
+    // work units: (segment, part). part_len is a multiple of TPB so every warp sees warp-uniform trip counts.
+    const long long tps = a.trials_per_segment;
+    const long long blocks_per_seg = (tps + TPB - 1) / TPB;
+    long long parts = 1;
+    if (a.n_segments < 4LL * n_sm) parts = std::max(1LL, std::min(blocks_per_seg, (4LL * n_sm + a.n_segments - 1) / a.n_segments));
+    const long long blocks_per_part = (blocks_per_seg + parts - 1) / parts;
+    parts = (blocks_per_seg + blocks_per_part - 1) / blocks_per_part;
+    a.parts_per_segment = (int)parts;
+    a.part_len = blocks_per_part * TPB;
+    const long long n_units = a.n_segments * parts;
+    const int grid = (int)std::min<long long>(n_units, n_sm);
+    if (grid <= 0) return 0;
+    kern<<<grid, TPB, L.total, st>>>(a, L);
+    CK(cudaGetLastError());
+    ++h->launches;
+    return 0;
+}
+
+static int fill_common(stmpm_handle* h, KArgs& a, int precision) {
+    if (!h) return fail(STMPM_E_ARG, "null handle");
+    if (!h->have_catalog || !h->have_sensor)
+        return fail(STMPM_E_STATE, "call stmpm_set_catalog and stmpm_set_sensor before running trials");
+    if (precision != 64 && precision != 32) return fail(STMPM_E_ARG, "precision must be 64 or 32");
+    std::memset(&a, 0, sizeof(a));
+    a.cat32 = h->cat32; a.cat64 = h->cat64; a.cell_start = h->cell_start; a.band_tab = h->band_tab;
+    a.n_stars = h->n_stars; a.n_cells_pad = h->n_cells_pad; a.n_bands = h->n_bands;
+    a.inv_band_h = (float)((double)h->n_bands / M_PI);
+    a.f_ideal = h->cfg.f_ideal; a.half_u = h->cfg.half_u; a.half_v = h->cfg.half_v; a.n_min = h->cfg.n_min;
+    a.hist_shift = 52 - h->cfg.hist_log2_sub; a.n_bins = h->n_bins;
+    a.stats_len = STMPM_STATS_HEAD + h->n_bins;
+    return 0;
+}
+
+extern "C" int stmpm_trials_presampled(stmpm_t* h, int precision, int64_t n, uint64_t seed, int64_t trial0,
+                                       const double* const* cols, double* err, int32_t* ndet, double* stats,
+                                       void* stream) {
+    KArgs a;
+    if (int rc = fill_common(h, a, precision)) return rc;
+    if (n < 0 || !cols) return fail(STMPM_E_ARG, "stmpm_trials_presampled: bad n / cols");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(h->device));
+    for (int i = 0; i < STMPM_NCOLS; ++i) {
+        if (!cols[i]) return fail(STMPM_E_ARG, "stmpm_trials_presampled: null column pointer");
+        a.cols[i] = cols[i];
+    }
+    a.n_segments = 1; a.trials_per_segment = n; a.trial0 = trial0;
+    a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
+    a.err = err; a.ndet = ndet; a.stats = stats;
+    return precision == 64 ? launch_trials<0, 64>(h, a, (cudaStream_t)stream)
+                           : launch_trials<0, 32>(h, a, (cudaStream_t)stream);
+}
+
+static void to_dev_dist(const stmpm_dist& s, DistDev& d) {
+    for (int i = 0; i < STMPM_NNORMAL; ++i) { d.mean[i] = s.mean[i]; d.sigma[i] = s.sigma[i]; }
+    d.thermal_coef = s.thermal_coef;
+}
+
+extern "C" int stmpm_trials_rng(stmpm_t* h, int precision, int64_t n_segments, int64_t tps, uint64_t seed,
+                                int64_t trial0, const stmpm_dist* dists, double* err, int32_t* ndet, double* stats,
+                                void* stream) {
+    KArgs a;
+    if (int rc = fill_common(h, a, precision)) return rc;
+    if (n_segments < 0 || tps < 0 || !dists) return fail(STMPM_E_ARG, "stmpm_trials_rng: bad arguments");
+    if (n_segments == 0 || tps == 0) return 0;
+    CK(cudaSetDevice(h->device));
+    static_assert(sizeof(DistDev) == sizeof(stmpm_dist), "dist layout");
+    if (n_segments == 1) {
+        to_dev_dist(dists[0], a.dist0);
+    } else {   // NOTE: multi-segment calls on one handle share this buffer: do not issue them concurrently
+        if (h->dists_cap < n_segments) {
+            CK(cudaStreamSynchronize((cudaStream_t)stream));
+            cudaFree(h->dists); h->dists = nullptr; h->dists_cap = 0;
+            CK(cudaMalloc(&h->dists, sizeof(DistDev) * n_segments));
+            h->dists_cap = n_segments;
+        }
+        CK(cudaMemcpyAsync(h->dists, dists, sizeof(DistDev) * n_segments, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+        a.dists = h->dists;
+    }
+    a.n_segments = n_segments; a.trials_per_segment = tps; a.trial0 = trial0;
+    a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
+    a.err = err; a.ndet = ndet; a.stats = stats;
+    return precision == 64 ? launch_trials<1, 64>(h, a, (cudaStream_t)stream)
+                           : launch_trials<1, 32>(h, a, (cudaStream_t)stream);
+}
+
+extern "C" int stmpm_fill_presampled(stmpm_t* h, int64_t n, uint64_t seed, int64_t trial0, const stmpm_dist* dist,
+                                     double* const* cols, void* stream) {
+    if (!h || !dist || !cols || n < 0) return fail(STMPM_E_ARG, "stmpm_fill_presampled: bad arguments");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(h->device));
+    for (int i = 0; i < STMPM_NCOLS; ++i) if (!cols[i]) return fail(STMPM_E_ARG, "stmpm_fill_presampled: null column");
+    DistDev d;
+    to_dev_dist(*dist, d);
+    const int grid = (int)std::min<long long>((n + 255) / 256, (long long)h->prop.multiProcessorCount * 8);
+    fill_presampled_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        n, trial0, (uint32_t)seed, (uint32_t)(seed >> 32), d, cols[0], cols[1], cols[2], cols[3], cols[4], cols[5],
+        cols[6], cols[7], cols[8], cols[9], cols[10], cols[11], cols[12]);
+    CK(cudaGetLastError());
+    ++h->launches;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ host pipelines
+static int ensure_stage(stmpm_handle* h, long long chunk, bool need_cols) {
+    if (h->stage_cap >= chunk && (!need_cols || h->stage_cols[0])) return 0;
+    free_stage(h);
+    for (int i = 0; i < stmpm_handle::NBUF; ++i) {
+        if (need_cols) CK(cudaMalloc(&h->stage_cols[i], sizeof(double) * STMPM_NCOLS * chunk));
+        CK(cudaMalloc(&h->stage_err[i], sizeof(double) * chunk));
+        CK(cudaMalloc(&h->stage_ndet[i], sizeof(int) * chunk));
+    }
+    h->stage_cap = chunk;
+    return 0;
+}
+static int ensure_stats(stmpm_handle* h, long long n_doubles) {
+    if (h->stage_stats && h->stage_stats_cap >= n_doubles) return 0;
+    cudaFree(h->stage_stats); h->stage_stats = nullptr; h->stage_stats_cap = 0;
+    CK(cudaMalloc(&h->stage_stats, sizeof(double) * n_doubles));
+    h->stage_stats_cap = n_doubles;
+    return 0;
+}
+
+static constexpr long long HOST_CHUNK = 1LL << 22;   // trials per pipeline stage
+
+extern "C" int stmpm_run_presampled_host(stmpm_t* h, int precision, int64_t n, uint64_t seed, int64_t trial0,
+                                         const double* const* cols, double* err, int32_t* ndet, double* stats) {
+    KArgs probe;
+    if (int rc = fill_common(h, probe, precision)) return rc;
+    if (n < 0 || !cols || !err || !ndet) return fail(STMPM_E_ARG, "stmpm_run_presampled_host: bad arguments");
+    for (int i = 0; i < STMPM_NCOLS; ++i) if (!cols[i]) return fail(STMPM_E_ARG, "null column pointer");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(h->device));
+    const long long chunk = std::min<long long>(HOST_CHUNK, n);
+    if (int rc = ensure_stage(h, chunk, true)) return rc;
+    const long long slen = probe.stats_len;
+    if (stats) {
+        if (int rc = ensure_stats(h, slen)) return rc;
+        CK(cudaMemsetAsync(h->stage_stats, 0, sizeof(double) * slen, h->streams[0]));
+        CK(cudaStreamSynchronize(h->streams[0]));
+    }
+    int k = 0;
+    for (long long off = 0; off < n; off += chunk, ++k) {
+        const int b = k % stmpm_handle::NBUF;
+        const long long m = std::min<long long>(chunk, n - off);
+        cudaStream_t st = h->streams[b];
+        const double* dcols[STMPM_NCOLS];
+        for (int c = 0; c < STMPM_NCOLS; ++c) {
+            double* dst = h->stage_cols[b] + (long long)c * h->stage_cap;
+            CK(cudaMemcpyAsync(dst, cols[c] + off, sizeof(double) * m, cudaMemcpyHostToDevice, st));
+            dcols[c] = dst;
+        }
+        if (int rc = stmpm_trials_presampled(h, precision, m, seed, trial0 + off, dcols, h->stage_err[b],
+                                             h->stage_ndet[b], stats ? h->stage_stats : nullptr, st)) return rc;
+        CK(cudaMemcpyAsync(err + off, h->stage_err[b], sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ndet + off, h->stage_ndet[b], sizeof(int) * m, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < stmpm_handle::NBUF; ++i) CK(cudaStreamSynchronize(h->streams[i]));
+    if (stats) CK(cudaMemcpy(stats, h->stage_stats, sizeof(double) * slen, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int stmpm_run_rng_host(stmpm_t* h, int precision, int64_t n_segments, int64_t tps, uint64_t seed,
+                                  int64_t trial0, const stmpm_dist* dists, double* err, int32_t* ndet, double* stats) {
+    KArgs probe;
+    if (int rc = fill_common(h, probe, precision)) return rc;
+    if (n_segments < 0 || tps < 0 || !dists) return fail(STMPM_E_ARG, "stmpm_run_rng_host: bad arguments");
+    if ((err == nullptr) != (ndet == nullptr)) return fail(STMPM_E_ARG, "err and n_det must both be given or both NULL");
+    if (n_segments == 0 || tps == 0) return 0;
+    CK(cudaSetDevice(h->device));
+    const long long slen = probe.stats_len;
+    cudaStream_t s0 = h->streams[0];
+    if (stats) {
+        if (int rc = ensure_stats(h, slen * n_segments)) return rc;
+        CK(cudaMemsetAsync(h->stage_stats, 0, sizeof(double) * slen * n_segments, s0));
+    }
+    if (!err) {   // stats only: one launch over all segments
+        if (int rc = stmpm_trials_rng(h, precision, n_segments, tps, seed, trial0, dists, nullptr, nullptr,
+                                      stats ? h->stage_stats : nullptr, s0)) return rc;
+    } else {      // records: per segment, chunked + double-buffered D2H
+        const long long chunk = std::min<long long>(HOST_CHUNK, tps);
+        if (int rc = ensure_stage(h, chunk, false)) return rc;
+        CK(cudaStreamSynchronize(s0));
+        int k = 0;
+        for (long long s = 0; s < n_segments; ++s) {
+            for (long long off = 0; off < tps; off += chunk, ++k) {
+                const int b = k % stmpm_handle::NBUF;
+                const long long m = std::min<long long>(chunk, tps - off);
+                cudaStream_t st = h->streams[b];
+                if (int rc = stmpm_trials_rng(h, precision, 1, m, seed, trial0 + s * tps + off, dists + s,
+                                              h->stage_err[b], h->stage_ndet[b],
+                                              stats ? h->stage_stats + s * slen : nullptr, st)) return rc;
+                CK(cudaMemcpyAsync(err + s * tps + off, h->stage_err[b], sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(ndet + s * tps + off, h->stage_ndet[b], sizeof(int) * m, cudaMemcpyDeviceToHost, st));
+            }
+        }
+    }
+    for (int i = 0; i < stmpm_handle::NBUF; ++i) CK(cudaStreamSynchronize(h->streams[i]));
+    if (stats) CK(cudaMemcpy(stats, h->stage_stats, sizeof(double) * slen * n_segments, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ misc
+extern "C" int stmpm_fma_peak(stmpm_t* h, int precision, double* tflops) {
+    if (!h || !tflops) return fail(STMPM_E_ARG, "stmpm_fma_peak: null");
+    if (precision != 64 && precision != 32) return fail(STMPM_E_ARG, "precision must be 64 or 32");
+    CK(cudaSetDevice(h->device));
+    void* out = nullptr;
+    CK(cudaMalloc(&out, 64));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int grid = h->prop.multiProcessorCount * 8, iters = precision == 64 ? 1 << 15 : 1 << 16;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(e0, h->streams[0]));
+        if (precision == 64) fma_peak_kernel<double><<<grid, 256, 0, h->streams[0]>>>((double*)out, iters, 1.0000001, 1e-9);
+        else fma_peak_kernel<float><<<grid, 256, 0, h->streams[0]>>>((float*)out, iters, 1.0001f, 1e-6f);
+        CK(cudaEventRecord(e1, h->streams[0]));
+        CK(cudaEventSynchronize(e1));
+        ++h->launches;
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8.0 * (double)iters * 256.0 * (double)grid;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    *tflops = best;
+    return 0;
+}
+
+extern "C" int stmpm_launch_count(const stmpm_t* h, int64_t* n) {
+    if (!h || !n) return fail(STMPM_E_ARG, "null");
+    *n = h->launches;
+    return 0;
+}

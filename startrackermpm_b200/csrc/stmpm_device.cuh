@@ -1,0 +1,278 @@
+// stmpm_device.cuh — device-side building blocks of the trial (docs/MODEL.md). sm_100a only.
+//
+// Replaces the per-row body of Simulation.run_sim + quest_objective (called at /root/reference/monte_carlo.py:52 and
+// sensitivity.py:77; bodies absent from the mount).  One trial per thread:
+//   setup (fp64)  ->  sky-grid scan with an fp32 conservative pre-filter out of shared memory (phase A)
+//                 ->  exact per-star projection + Philox centroid noise + detection + B accumulation (phase B)
+//                 ->  QUEST Newton solve in the body frame + error angle (fp64).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace stmpm {
+
+constexpr int TPB = 512;          // threads per CTA (1 CTA / SM: the fp32 catalog lives in shared memory)
+constexpr int LIST_CAP = 32;      // per-thread candidate list length (phase A -> phase B hand-off)
+constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u, PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
+constexpr uint32_t TAG_STAR = 0x53544152u, TAG_PARA = 0x50415241u;
+constexpr double RAD2ARCSEC = 206264.80624709636;
+constexpr double DEG2RAD = 0.017453292519943295;
+constexpr double TWO_M32 = 2.3283064365386963e-10;   // 2^-32
+
+struct __align__(32) StarRec {    // exactly one 32-byte sector per star
+    double x, y, z;
+    uint32_t star_id;
+    float mag;
+};
+
+struct TrialParams {              // one DataFrame row (MODEL.md §1)
+    double ra, dec, roll, f, ex, ey, ez, phi, theta, psi, devx, devy, maxmag;
+};
+
+// Philox4x32-10 (Salmon et al., SC'11).  Ten rounds, key bumped between rounds.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t& o0, uint32_t& o1, uint32_t& o2, uint32_t& o3) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(PHILOX_M0, c0), lo0 = PHILOX_M0 * c0;
+        const uint32_t hi1 = __umulhi(PHILOX_M1, c2), lo1 = PHILOX_M1 * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += PHILOX_W0;
+        k1 += PHILOX_W1;
+    }
+    o0 = c0; o1 = c1; o2 = c2; o3 = c3;
+}
+
+__device__ __forceinline__ double u01(uint32_t w) { return ((double)w + 0.5) * TWO_M32; }
+
+// MODEL.md §5: R = sqrt(-2 ln u1); z1 = R cos(2 pi u2); z2 = R sin(2 pi u2)
+__device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, double& z1, double& z2) {
+    const double r = sqrt(-2.0 * log(u01(wa)));
+    double s, c;
+    sincospi(2.0 * u01(wb), &s, &c);
+    z1 = r * c;
+    z2 = r * s;
+}
+__device__ __forceinline__ void box_muller_f(uint32_t wa, uint32_t wb, float& z1, float& z2) {
+    // u in (0,1): (w + 0.5) * 2^-32 rounded to float can reach 1.0f -> clamp below 1 so that R stays finite and real
+    const float u1 = fminf(((float)wa + 0.5f) * 2.3283064365386963e-10f, 0.99999994f);
+    const float r = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincospif(2.0f * (((float)wb + 0.5f) * 2.3283064365386963e-10f), &s, &c);
+    z1 = r * c;
+    z2 = r * s;
+}
+
+// Everything a trial needs after setup.  Inertial-frame plane vectors: NI = C n, EU = C e_u, EV = C e_v, so that for a
+// catalog vector s:  n.r = NI.s,  u = (n.p0 / NI.s) EU.s - e_u.p0,  v likewise  (r = C^T s never materialised).
+struct TrialCtx {
+    double C[9];                  // body -> inertial, row-major
+    double NI[3], EU[3], EV[3];
+    double np0, cu, cv;           // n.p0, e_u.p0, e_v.p0
+    double sx, sy;                // |BASE_DEV_X|, |BASE_DEV_Y|
+    float NIf[3], EUf[3], EVf[3], np0f, cuf, cvf, limu, limv, magf;
+    float ra0, dec0, cone, dalpha;   // scan geometry (fp32, conservative); dalpha < 0 => full circle
+};
+
+__device__ __forceinline__ void trial_setup(const TrialParams& p, double half_u, double half_v, TrialCtx& c) {
+    double sa, ca, sd, cd, sr, cr;
+    sincos(p.ra, &sa, &ca);
+    sincos(p.dec, &sd, &cd);
+    sincos(p.roll, &sr, &cr);
+    // C = Rz(ra) Ry(pi/2 - dec) Rz(roll)   (MODEL.md §2; primitives: constants.py:81-94)
+    c.C[0] = ca * sd * cr - sa * sr;  c.C[1] = -ca * sd * sr - sa * cr;  c.C[2] = ca * cd;
+    c.C[3] = sa * sd * cr + ca * sr;  c.C[4] = -sa * sd * sr + ca * cr;  c.C[5] = sa * cd;
+    c.C[6] = -cd * cr;                c.C[7] = cd * sr;                  c.C[8] = sd;
+    double sp, cp, st, ct, ss, cs;
+    sincos(p.phi * DEG2RAD, &sp, &cp);
+    sincos(p.theta * DEG2RAD, &st, &ct);
+    sincos(p.psi * DEG2RAD, &ss, &cs);
+    // R_p = Rx(phi) Ry(theta) Rz(psi): columns e_u, e_v, n
+    const double eu[3] = {ct * cs, cp * ss + sp * st * cs, sp * ss - cp * st * cs};
+    const double ev[3] = {-ct * ss, cp * cs - sp * st * ss, sp * cs + cp * st * ss};
+    const double nn[3] = {st, -sp * ct, cp * ct};
+    const double p0[3] = {p.ex, p.ey, p.f + p.ez};
+    c.np0 = nn[0] * p0[0] + nn[1] * p0[1] + nn[2] * p0[2];
+    c.cu = eu[0] * p0[0] + eu[1] * p0[1] + eu[2] * p0[2];
+    c.cv = ev[0] * p0[0] + ev[1] * p0[1] + ev[2] * p0[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        c.NI[i] = c.C[3 * i] * nn[0] + c.C[3 * i + 1] * nn[1] + c.C[3 * i + 2] * nn[2];
+        c.EU[i] = c.C[3 * i] * eu[0] + c.C[3 * i + 1] * eu[1] + c.C[3 * i + 2] * eu[2];
+        c.EV[i] = c.C[3 * i] * ev[0] + c.C[3 * i + 1] * ev[1] + c.C[3 * i + 2] * ev[2];
+        c.NIf[i] = (float)c.NI[i];
+        c.EUf[i] = (float)c.EU[i];
+        c.EVf[i] = (float)c.EV[i];
+    }
+    c.sx = fabs(p.devx);
+    c.sy = fabs(p.devy);
+    c.np0f = (float)c.np0;
+    c.cuf = (float)c.cu;
+    c.cvf = (float)c.cv;
+    // conservative pre-filter window: Box-Muller with 32-bit u1 has |z| <= sqrt(-2 ln 2^-33) = 6.77; fp32 slack
+    const float ff = (float)fabs(p.f);
+    const float noise = 6.8f * fmaxf((float)c.sx, (float)c.sy) + 0.02f + 4e-6f * ff;
+    c.limu = (float)half_u + noise;
+    c.limv = (float)half_v + noise;
+    c.magf = __double2float_rd(p.maxmag);   // (double)mag <= maxmag  <=>  mag <= round-down-to-float(maxmag), exactly
+    // scan cone about the boresight (= third column of C): every point of the (tilted, shifted, noise-padded) array
+    // lies within atan(reach / depth) of +z  (MODEL.md §8: acceleration only)
+    const float reach = 1.41421357f * (fmaxf((float)half_u, (float)half_v) + noise)
+                        + hypotf((float)p.ex, (float)p.ey) + 1.0f;
+    const float tilt = fminf(((float)fabs(p.phi) + (float)fabs(p.theta)) * 0.0174532925f, 0.5f);
+    const float depth = (float)p.f + (float)p.ez - reach * tilt;
+    c.cone = (depth > 1.0f) ? atanf(reach / depth) + 0.002f : 3.2f;
+    c.dec0 = asinf(fminf(fmaxf((float)c.C[8], -1.0f), 1.0f));
+    float a0 = atan2f((float)c.C[5], (float)c.C[2]);
+    c.ra0 = a0 < 0.0f ? a0 + 6.28318531f : a0;
+    if (fabsf(c.dec0) + c.cone >= 1.5607963f) c.dalpha = -1.0f;
+    else c.dalpha = asinf(fminf(sinf(c.cone) / cosf(c.dec0), 1.0f)) + 0.002f;
+}
+
+// fp32 conservative pre-filter on one shared-memory catalog entry (x, y, z, mag)
+__device__ __forceinline__ bool prefilter(const TrialCtx& c, const float4 s) {
+    if (!(s.w <= c.magf)) return false;
+    const float dn = c.NIf[0] * s.x + c.NIf[1] * s.y + c.NIf[2] * s.z;
+    if (!(dn > 0.02f)) return false;
+    const float rl = __fdividef(c.np0f, dn);
+    const float u = fmaf(rl, c.EUf[0] * s.x + c.EUf[1] * s.y + c.EUf[2] * s.z, -c.cuf);
+    const float v = fmaf(rl, c.EVf[0] * s.x + c.EVf[1] * s.y + c.EVf[2] * s.z, -c.cvf);
+    return fabsf(u) <= c.limu && fabsf(v) <= c.limv;
+}
+
+// Exact (fp64) star evaluation: MODEL.md §2-§4. Returns detected?; on detection adds b s^T into B.
+__device__ __forceinline__ bool star_exact(const TrialCtx& c, const StarRec& s, uint32_t t_lo, uint32_t t_hi,
+                                           uint32_t k0, uint32_t k1, double f_ideal, double half_u, double half_v,
+                                           double* __restrict__ B) {
+    const double dn = c.NI[0] * s.x + c.NI[1] * s.y + c.NI[2] * s.z;
+    const double du = c.EU[0] * s.x + c.EU[1] * s.y + c.EU[2] * s.z;
+    const double dv = c.EV[0] * s.x + c.EV[1] * s.y + c.EV[2] * s.z;
+    const double lam = c.np0 / dn;
+    uint32_t x0, x1, x2, x3;
+    philox4x32_10(t_lo, t_hi, s.star_id, TAG_STAR, k0, k1, x0, x1, x2, x3);
+    double z1, z2;
+    box_muller(x0, x1, z1, z2);
+    const double um = fma(c.sx, z1, fma(lam, du, -c.cu));
+    const double vm = fma(c.sy, z2, fma(lam, dv, -c.cv));
+    const bool det = (dn > 0.0) && (fabs(um) <= half_u) && (fabs(vm) <= half_v);
+    if (det) {
+        const double inv = rsqrt(um * um + vm * vm + f_ideal * f_ideal);
+        const double bx = um * inv, by = vm * inv, bz = f_ideal * inv;
+        B[0] = fma(bx, s.x, B[0]); B[1] = fma(bx, s.y, B[1]); B[2] = fma(bx, s.z, B[2]);
+        B[3] = fma(by, s.x, B[3]); B[4] = fma(by, s.y, B[4]); B[5] = fma(by, s.z, B[5]);
+        B[6] = fma(bz, s.x, B[6]); B[7] = fma(bz, s.y, B[7]); B[8] = fma(bz, s.z, B[8]);
+    }
+    return det;
+}
+
+// fp32 star evaluation (precision = 32).  The detection decision is re-taken in fp64 when the fp32 centroid lies inside
+// a guard band around the array edge, so detection counts stay bit-exact with the fp64 oracle.
+__device__ __forceinline__ bool star_f32(const TrialCtx& c, const StarRec& s, uint32_t t_lo, uint32_t t_hi, uint32_t k0,
+                                         uint32_t k1, double f_ideal, double half_u, double half_v,
+                                         float* __restrict__ Bf, double* __restrict__ Bd) {
+    const float sx = (float)s.x, sy = (float)s.y, sz = (float)s.z;
+    const float dn = c.NIf[0] * sx + c.NIf[1] * sy + c.NIf[2] * sz;
+    const float du = c.EUf[0] * sx + c.EUf[1] * sy + c.EUf[2] * sz;
+    const float dv = c.EVf[0] * sx + c.EVf[1] * sy + c.EVf[2] * sz;
+    const float lam = c.np0f / dn;
+    uint32_t x0, x1, x2, x3;
+    philox4x32_10(t_lo, t_hi, s.star_id, TAG_STAR, k0, k1, x0, x1, x2, x3);
+    float z1, z2;
+    box_muller_f(x0, x1, z1, z2);
+    const float um = fmaf((float)c.sx, z1, fmaf(lam, du, -c.cuf));
+    const float vm = fmaf((float)c.sy, z2, fmaf(lam, dv, -c.cvf));
+    const float hu = (float)half_u, hv = (float)half_v;
+    const float guard = 0.05f + 1e-5f * fabsf(c.np0f) + 1e-4f * ((float)c.sx + (float)c.sy);
+    if (!(dn > 0.02f) || fabsf(fabsf(um) - hu) <= guard || fabsf(fabsf(vm) - hv) <= guard)
+        return star_exact(c, s, t_lo, t_hi, k0, k1, f_ideal, half_u, half_v, Bd);   // rare: exact decision + exact b
+    const bool det = (fabsf(um) <= hu) && (fabsf(vm) <= hv);
+    if (det) {
+        const float fi = (float)f_ideal;
+        const float inv = rsqrtf(um * um + vm * vm + fi * fi);
+        const float bx = um * inv, by = vm * inv, bz = fi * inv;
+        Bf[0] = fmaf(bx, sx, Bf[0]); Bf[1] = fmaf(bx, sy, Bf[1]); Bf[2] = fmaf(bx, sz, Bf[2]);
+        Bf[3] = fmaf(by, sx, Bf[3]); Bf[4] = fmaf(by, sy, Bf[4]); Bf[5] = fmaf(by, sz, Bf[5]);
+        Bf[6] = fmaf(bz, sx, Bf[6]); Bf[7] = fmaf(bz, sy, Bf[7]); Bf[8] = fmaf(bz, sz, Bf[8]);
+    }
+    return det;
+}
+
+// Wahba solve in the body frame: B' = (B / n) C, QUEST Newton from lambda0 = 1 (Shuster & Oh 1981), error angle
+// 2 atan2(|q_v|, |q_w|) of the optimal rotation A_est C (MODEL.md §4).  Returns arcsec.
+__device__ __forceinline__ double quest_error_arcsec(const double* __restrict__ Bi, const double* __restrict__ C,
+                                                     int n_det) {
+    const double w = 1.0 / (double)n_det;
+    double B[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            B[3 * i + j] = w * (Bi[3 * i] * C[j] + Bi[3 * i + 1] * C[3 + j] + Bi[3 * i + 2] * C[6 + j]);
+    const double S00 = 2.0 * B[0], S11 = 2.0 * B[4], S22 = 2.0 * B[8];
+    const double S01 = B[1] + B[3], S02 = B[2] + B[6], S12 = B[5] + B[7];
+    const double sig = B[0] + B[4] + B[8];
+    const double Z0 = B[5] - B[7], Z1 = B[6] - B[2], Z2 = B[1] - B[3];
+    const double kap = (S11 * S22 - S12 * S12) + (S00 * S22 - S02 * S02) + (S00 * S11 - S01 * S01);
+    const double del = S00 * (S11 * S22 - S12 * S12) - S01 * (S01 * S22 - S12 * S02) + S02 * (S01 * S12 - S11 * S02);
+    const double SZ0 = S00 * Z0 + S01 * Z1 + S02 * Z2;
+    const double SZ1 = S01 * Z0 + S11 * Z1 + S12 * Z2;
+    const double SZ2 = S02 * Z0 + S12 * Z1 + S22 * Z2;
+    const double a = sig * sig - kap;
+    const double b = sig * sig + Z0 * Z0 + Z1 * Z1 + Z2 * Z2;
+    const double cc = del + Z0 * SZ0 + Z1 * SZ1 + Z2 * SZ2;
+    const double d = SZ0 * SZ0 + SZ1 * SZ1 + SZ2 * SZ2;
+    const double apb = a + b, k0 = a * b + cc * sig - d;
+    double lam = 1.0;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const double l2 = lam * lam;
+        const double f = l2 * l2 - apb * l2 - cc * lam + k0;
+        const double fp = 4.0 * l2 * lam - 2.0 * apb * lam - cc;
+        lam -= f / fp;
+    }
+    const double alpha = lam * lam - sig * sig + kap;
+    const double beta = lam - sig;
+    const double gamma = (lam + sig) * alpha - del;
+    const double X0 = alpha * Z0 + beta * SZ0 + (S00 * SZ0 + S01 * SZ1 + S02 * SZ2);
+    const double X1 = alpha * Z1 + beta * SZ1 + (S01 * SZ0 + S11 * SZ1 + S12 * SZ2);
+    const double X2 = alpha * Z2 + beta * SZ2 + (S02 * SZ0 + S12 * SZ1 + S22 * SZ2);
+    const double vn = sqrt(X0 * X0 + X1 * X1 + X2 * X2);
+    return 2.0 * atan2(vn, fabs(gamma)) * RAD2ARCSEC;
+}
+
+// MODEL.md §6: native-RNG parameter draw for one trial.
+struct DistDev {
+    double mean[11], sigma[11], thermal_coef;
+};
+__device__ __forceinline__ void sample_params(const DistDev& d, uint32_t t_lo, uint32_t t_hi, uint32_t k0, uint32_t k1,
+                                              TrialParams& p) {
+    uint32_t w[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        philox4x32_10(t_lo, t_hi, (uint32_t)j, TAG_PARA, k0, k1, w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+    const double fov = 0.17453292519943295;   // deg2rad(10), monte_carlo.py:87
+    const double PI = 3.141592653589793;
+    p.ra = fov + (2.0 * PI - 2.0 * fov) * u01(w[0]);
+    p.dec = (-0.5 * PI + fov) + (PI - 2.0 * fov) * u01(w[1]);
+    p.roll = -PI + 2.0 * PI * u01(w[2]);
+    double z[12];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) box_muller(w[4 + 2 * k], w[5 + 2 * k], z[2 * k], z[2 * k + 1]);
+    const double F = d.mean[0] + d.sigma[0] * z[0];
+    p.ex = d.mean[1] + d.sigma[1] * z[1];
+    p.ey = d.mean[2] + d.sigma[2] * z[2];
+    p.ez = d.mean[3] + d.sigma[3] * z[3];
+    p.phi = d.mean[4] + d.sigma[4] * z[4];
+    p.theta = d.mean[5] + d.sigma[5] * z[5];
+    p.psi = d.mean[6] + d.sigma[6] * z[6];
+    p.devx = d.mean[7] + d.sigma[7] * z[7];
+    p.devy = d.mean[8] + d.sigma[8] * z[8];
+    p.maxmag = d.mean[9] + d.sigma[9] * z[9];
+    const double dtemp = d.mean[10] + d.sigma[10] * z[10];
+    p.f = F * (1.0 + dtemp * d.thermal_coef);   // sensitivity.py:115-117
+}
+
+}  // namespace stmpm

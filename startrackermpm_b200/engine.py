@@ -1,0 +1,202 @@
+"""Bulk host API over the C ABI (include/stmpm.h): the call sites `simObjects.Simulation.run_sim` and bench.py use.
+
+Everything numerical happens in libstmpm.so on the GPU.  numpy arrays carry host buffers, torch CUDA tensors carry
+device buffers (`tensor.data_ptr()`); neither does any arithmetic of the trial.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Mapping, Sequence
+
+import numpy as np
+
+from . import _abi
+from .catalog import SkyGrid, build_sky_grid, load_catalog
+
+COLUMNS = _abi.COLUMNS
+NORMAL_PARAMS = _abi.NORMAL_PARAMS
+SENSOR_WIDTH = 1024    # /root/reference/constants.py:97
+SENSOR_HEIGHT = 1024   # /root/reference/constants.py:98
+N_MIN = 3
+
+
+def make_dist(means: Mapping[str, float] | Sequence[float], sigmas: Mapping[str, float] | Sequence[float],
+              thermal_coef: float = 0.0) -> _abi.Dist:
+    """Parameter distributions of native-RNG mode, in NORMAL_PARAMS order (docs/MODEL.md §6)."""
+    if isinstance(means, Mapping):
+        means = [float(means.get(k, 0.0)) for k in NORMAL_PARAMS]
+    if isinstance(sigmas, Mapping):
+        sigmas = [float(sigmas.get(k, 0.0)) for k in NORMAL_PARAMS]
+    if len(means) != _abi.NNORMAL or len(sigmas) != _abi.NNORMAL:
+        raise ValueError(f"need {_abi.NNORMAL} means and sigmas in order {NORMAL_PARAMS}")
+    d = _abi.Dist()
+    for i in range(_abi.NNORMAL):
+        d.mean[i] = float(means[i])
+        d.sigma[i] = float(sigmas[i])
+    d.thermal_coef = float(thermal_coef)
+    return d
+
+
+def _ptr(a) -> int:
+    """Address of a numpy array / torch tensor / None."""
+    if a is None:
+        return 0
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return int(a.data_ptr())
+
+
+class TrialEngine:
+    """One handle = one GPU + one catalog + one sensor description."""
+
+    def __init__(self, device: int = 0, catalog=None, f_ideal: float = 3500.0, half_u: float = SENSOR_WIDTH / 2,
+                 half_v: float = SENSOR_HEIGHT / 2, n_min: int = N_MIN, hist_log2_sub: int = 8,
+                 cell_deg: float = 3.0):
+        self._lib = _abi.load()
+        self._h = C.c_void_p()
+        _abi.check(self._lib.stmpm_create(C.byref(self._h), int(device)))
+        self.device = int(device)
+        xyz, mag = catalog if catalog is not None else load_catalog()
+        self.set_catalog(build_sky_grid(xyz, mag, cell_deg))
+        self.set_sensor(f_ideal, half_u, half_v, n_min, hist_log2_sub)
+
+    # ---------------------------------------------------------------- configuration
+    def set_catalog(self, grid: SkyGrid) -> None:
+        self.grid = grid
+        xyz = np.ascontiguousarray(grid.xyz, dtype=np.float64)
+        mag = np.ascontiguousarray(grid.mag, dtype=np.float32)
+        sid = np.ascontiguousarray(grid.star_id, dtype=np.int32)
+        n_ra = np.ascontiguousarray(grid.n_ra, dtype=np.int32)
+        cs = np.ascontiguousarray(grid.cell_start, dtype=np.int32)
+        _abi.check(self._lib.stmpm_set_catalog(self._h, _ptr(xyz), _ptr(mag), _ptr(sid), xyz.shape[0], grid.n_bands,
+                                               _ptr(n_ra), _ptr(cs)))
+
+    def set_sensor(self, f_ideal: float, half_u: float = SENSOR_WIDTH / 2, half_v: float = SENSOR_HEIGHT / 2,
+                   n_min: int = N_MIN, hist_log2_sub: int = 8) -> None:
+        cfg = _abi.SensorCfg(float(f_ideal), float(half_u), float(half_v), int(n_min), int(hist_log2_sub))
+        _abi.check(self._lib.stmpm_set_sensor(self._h, C.byref(cfg)))
+        self.f_ideal = float(f_ideal)
+        self.hist_log2_sub = int(hist_log2_sub)
+        n = C.c_int64()
+        _abi.check(self._lib.stmpm_stats_len(self._h, C.byref(n)))
+        self.stats_len = int(n.value)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.stmpm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---------------------------------------------------------------- info
+    def device_info(self) -> dict:
+        sm, smem, skhz, mkhz = C.c_int32(), C.c_int64(), C.c_int32(), C.c_int32()
+        _abi.check(self._lib.stmpm_device_info(self._h, C.byref(sm), C.byref(smem), C.byref(skhz), C.byref(mkhz)))
+        return {"sm_count": sm.value, "smem_per_block": smem.value, "sm_khz": skhz.value, "mem_khz": mkhz.value}
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        _abi.check(self._lib.stmpm_launch_count(self._h, C.byref(n)))
+        return int(n.value)
+
+    def fma_peak(self, precision: int = 64) -> float:
+        t = C.c_double()
+        _abi.check(self._lib.stmpm_fma_peak(self._h, int(precision), C.byref(t)))
+        return float(t.value)
+
+    # ---------------------------------------------------------------- pre-sampled mode
+    @staticmethod
+    def _col_ptrs(cols, n_expected=None):
+        """cols: [13, n] array/tensor (rows = COLUMNS) or a sequence of 13 1-D float64 arrays/tensors."""
+        rows = [cols[i] for i in range(_abi.NCOLS)]
+        n = int(rows[0].shape[0])
+        for r in rows:
+            if int(r.shape[0]) != n or r.dtype not in (np.float64, _torch_f64()):
+                raise ValueError("every column must be float64 with the same length")
+            if isinstance(r, np.ndarray):
+                if not r.flags["C_CONTIGUOUS"]:
+                    raise ValueError("columns must be contiguous")
+            elif not r.is_contiguous():
+                raise ValueError("columns must be contiguous")
+        arr = (C.c_void_p * _abi.NCOLS)(*[_ptr(r) for r in rows])
+        return arr, n
+
+    def run_presampled(self, cols, seed: int, trial0: int = 0, precision: int = 64, want_stats: bool = False,
+                       out_err: np.ndarray | None = None, out_ndet: np.ndarray | None = None):
+        """HOST buffers in, HOST buffers out (H2D, kernel, D2H inside the call) — `Simulation.run_sim`'s path.
+        cols: float64 [13, n] in COLUMNS order.  Returns (err_arcsec f64 [n] with -1 = failed, n_det i32 [n][, stats])."""
+        if not isinstance(cols, np.ndarray) and not isinstance(cols, (list, tuple)):
+            cols = cols.numpy()
+        if isinstance(cols, np.ndarray):
+            cols = np.ascontiguousarray(cols, dtype=np.float64)
+        ptrs, n = self._col_ptrs(cols)
+        err = out_err if out_err is not None else np.empty(n, dtype=np.float64)
+        ndet = out_ndet if out_ndet is not None else np.empty(n, dtype=np.int32)
+        stats = np.zeros(self.stats_len, dtype=np.float64) if want_stats else None
+        _abi.check(self._lib.stmpm_run_presampled_host(self._h, int(precision), n, int(seed) & (2**64 - 1), int(trial0),
+                                                       ptrs, _ptr(err), _ptr(ndet), _ptr(stats)))
+        return (err, ndet, stats) if want_stats else (err, ndet)
+
+    def run_presampled_device(self, cols, err, ndet, stats=None, *, seed: int, trial0: int = 0, precision: int = 64,
+                              stream: int = 0) -> None:
+        """DEVICE buffers (torch CUDA tensors), stream-ordered, asynchronous."""
+        ptrs, n = self._col_ptrs(cols)
+        _abi.check(self._lib.stmpm_trials_presampled(self._h, int(precision), n, int(seed) & (2**64 - 1), int(trial0),
+                                                     ptrs, _ptr(err), _ptr(ndet), _ptr(stats), int(stream)))
+
+    def fill_presampled_device(self, cols, dist: _abi.Dist, *, seed: int, trial0: int = 0, stream: int = 0) -> None:
+        """The seeded generator kernel of config 2: fills 13 device columns with native-RNG mode's draws."""
+        ptrs, n = self._col_ptrs(cols)
+        _abi.check(self._lib.stmpm_fill_presampled(self._h, n, int(seed) & (2**64 - 1), int(trial0), C.byref(dist), ptrs,
+                                                   int(stream)))
+
+    # ---------------------------------------------------------------- native-RNG mode
+    @staticmethod
+    def _dist_array(dists):
+        if isinstance(dists, _abi.Dist):
+            dists = [dists]
+        arr = (_abi.Dist * len(dists))(*dists)
+        return arr, len(dists)
+
+    def run_rng(self, dists, trials_per_segment: int, seed: int, trial0: int = 0, precision: int = 64,
+                records: bool = False):
+        """HOST results.  Returns stats [n_segments, stats_len] (and err, n_det [n_segments*trials_per_segment] if records)."""
+        arr, ns = self._dist_array(dists)
+        n = ns * int(trials_per_segment)
+        err = np.empty(n, dtype=np.float64) if records else None
+        ndet = np.empty(n, dtype=np.int32) if records else None
+        stats = np.zeros((ns, self.stats_len), dtype=np.float64)
+        _abi.check(self._lib.stmpm_run_rng_host(self._h, int(precision), ns, int(trials_per_segment),
+                                                int(seed) & (2**64 - 1), int(trial0), arr, _ptr(err), _ptr(ndet),
+                                                _ptr(stats)))
+        return (stats, err, ndet) if records else stats
+
+    def run_rng_device(self, dists, trials_per_segment: int, stats, err=None, ndet=None, *, seed: int, trial0: int = 0,
+                       precision: int = 64, stream: int = 0) -> None:
+        """DEVICE buffers, stream-ordered, asynchronous. stats (+=) must be zeroed by the caller: [n_segments, stats_len]."""
+        arr, ns = self._dist_array(dists)
+        _abi.check(self._lib.stmpm_trials_rng(self._h, int(precision), ns, int(trials_per_segment),
+                                              int(seed) & (2**64 - 1), int(trial0), arr, _ptr(err), _ptr(ndet),
+                                              _ptr(stats), int(stream)))
+
+    # ---------------------------------------------------------------- statistics
+    def summarize(self, stats: np.ndarray) -> dict:
+        """Final reductions (driver.py:321-324; toolplot.py:82) of one packed stats buffer."""
+        stats = np.ascontiguousarray(stats, dtype=np.float64).reshape(-1)
+        if stats.shape[0] != self.stats_len:
+            raise ValueError(f"packed stats buffer must have {self.stats_len} doubles")
+        s = _abi.Summary()
+        _abi.check(self._lib.stmpm_stats_finalize(self._h, _ptr(stats), C.byref(s)))
+        return {k: getattr(s, k) for k, _ in _abi.Summary._fields_}
+
+
+def _torch_f64():
+    try:
+        import torch
+        return torch.float64
+    except Exception:  # torch absent: only numpy host buffers are usable
+        return None
