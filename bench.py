@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on BASELINE.json's config (contract: task brief §④).
+
+Metric   : MC trials/s (= attitude solves/s), whole job over N GPUs.
+Workload : configs[1] — default sensor config, 10^8 trials per GPU per step, pre-sampled fp64 parameter columns
+           resident in HBM (written by the seeded generator kernel), per-trial (error f64, n_det i32) records out,
+           streaming statistics accumulated; fp64 mode (the reference computes in float64).
+A "step" : one pass of the hot path (stmpm_trials_presampled) over that batch.  Inputs are 10.4 GB per step, far
+           larger than the 126 MB L2, so no explicit L2 flush is needed between steps.
+value    : device-resident throughput (CUDA events on the launching stream, barrier + synchronize both sides, max over ranks).
+e2e      : the same batch through the host-buffer C-ABI call (stmpm_run_presampled_host: pinned host columns -> H2D ->
+           kernel -> D2H records), wall-clocked around the synchronous call.
+--impl reference : the CPU arm — the numpy oracle port (the reference's own trial code is absent from its mount,
+           SURVEY.md §0) on all host cores, bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "mc_trials_per_sec"
+UNIT = "trials/s"
+SEED = 20231105
+F_IDEAL = 3500.0
+THERMAL_COEF = 2e-5
+BASIC_MEAN = dict(FOCAL_LENGTH=3500.0, F_ARR_EPS_X=0.0, F_ARR_EPS_Y=0.0, F_ARR_EPS_Z=0.0, F_ARR_PHI=0.0,
+                  F_ARR_THETA=0.0, F_ARR_PSI=0.0, BASE_DEV_X=0.0, BASE_DEV_Y=0.0, MAX_MAGNITUDE=6.0, D_TEMP=0.0)
+BASIC_SIGMA = dict(FOCAL_LENGTH=2.0, F_ARR_EPS_X=1.0, F_ARR_EPS_Y=1.0, F_ARR_EPS_Z=1.0, F_ARR_PHI=0.05,
+                   F_ARR_THETA=0.05, F_ARR_PSI=0.05, BASE_DEV_X=0.1, BASE_DEV_Y=0.1, MAX_MAGNITUDE=0.25, D_TEMP=5.0)
+BYTES_IN_PER_TRIAL = 13 * 8          # pre-sampled columns
+BYTES_OUT_PER_TRIAL = 8 + 4          # error f64 + n_det i32
+
+
+def work_flops_per_trial(n_cand: float, n_star: float) -> float:
+    """Algorithmic work per pre-sampled trial: FMA = 2 flop, every transcendental / div /
+    rsqrt = 1 flop.  F = 430 + 7 N_cand + 75 N_star + 6 N_star (Box-Muller arithmetic of the 2 N_star centroid normals)."""
+    return 430.0 + 7.0 * n_cand + 81.0 * n_star
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
+def _cpu_worker(args):
+    t0, n = args
+    from oracle import trial
+    from startrackermpm_b200.catalog import load_catalog
+    xyz, mag = load_catalog()
+    cols = trial.sample_params(BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF, SEED, t0, n)
+    e, d = trial.run_trials(cols, xyz, mag, F_IDEAL, SEED, t0)
+    return int((e >= 0).sum()), float(e[e >= 0].sum())
+
+
+def cpu_trials_per_sec(per_core: int, cores: int, pool=None):
+    """Times the numpy fp64 oracle (kind 'port') on `cores` processes, per_core trials each. Returns (trials/s, seconds)."""
+    import multiprocessing as mp
+    own = pool is None
+    if own:
+        os.environ.setdefault("OMP_NUM_THREADS", "1")    # one process per core; no BLAS oversubscription
+        pool = mp.get_context("spawn").Pool(cores)
+        pool.map(_cpu_worker, [(i * 64, 64) for i in range(cores)])      # warm: imports + catalog load
+    t = time.perf_counter()
+    res = pool.map(_cpu_worker, [(i * per_core, per_core) for i in range(cores)])
+    dt = time.perf_counter() - t
+    if own:
+        pool.close()
+    assert sum(r[0] for r in res) > 0
+    return cores * per_core / dt, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per_core = args.cpu_trials_per_core
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    pool = mp.get_context("spawn").Pool(cores)
+    pool.map(_cpu_worker, [(i * 64, 64) for i in range(cores)])
+    for _ in range(args.warmup):
+        cpu_trials_per_sec(max(256, per_core // 8), cores, pool)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_trials_per_sec(per_core, cores, pool)
+    dt = time.perf_counter() - t
+    pool.close()
+    n = cores * per_core
+    v = n * args.steps / dt
+    sample = f"{n} trials per step ({per_core} per process x {cores} processes) of the same default-config workload"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(n, args.gpus),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "numpy fp64 oracle port (oracle/trial.py): the reference's own trial code is absent from its mount "
+                "(SURVEY.md §0), so no unmodified reference exists to install or time",
+    }))
+    return 0
+
+
+def workload_config(trials_per_gpu_step: int, n_gpus: int):
+    return {"workload": "configs[1]: default sensor config (cameraBasic + simpleCentroid), pre-sampled fp64 parameter "
+                        "columns -> per-trial error records + streaming statistics",
+            "trials_per_gpu_per_step": int(trials_per_gpu_step), "catalog": "synthetic 9110 stars, seed 20231105",
+            "f_ideal_px": F_IDEAL, "sensor_px": 1024, "precision": 64, "sharding": f"trial-index ranges x{n_gpus}",
+            "l2_policy": "inputs (10.4 GB/step at 1e8 trials) larger than L2; no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [l.split(", ") for t, l in self.lines if t0 <= t <= t1] or [l.split(", ") for _, l in self.lines[-3:]]
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, flag in zip(names, r[4:8]):
+                    if flag.strip().lower() == "active":
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from startrackermpm_b200 import build, sharding
+    from startrackermpm_b200.engine import TrialEngine, make_dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the trial loop has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = int(args.trials)
+    eng = TrialEngine(local, f_ideal=F_IDEAL)
+    d = make_dist(BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF)
+    trial0 = rank * n                                      # weak scaling: every rank its own global trial-index range
+    cols = torch.empty((13, n), dtype=torch.float64, device="cuda")
+    err = torch.empty(n, dtype=torch.float64, device="cuda")
+    ndet = torch.empty(n, dtype=torch.int32, device="cuda")
+    stats = torch.zeros(eng.stats_len, dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    eng.fill_presampled_device(cols, d, seed=SEED, trial0=trial0, stream=stream)
+
+    def step():
+        eng.run_presampled_device(cols, err, ndet, stats, seed=SEED, trial0=trial0, precision=64, stream=stream)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    stats.zero_()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    l0 = eng.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    ev[0].record()
+    for k in range(args.steps):
+        step()
+        ev[k + 1].record()
+    if world > 1:
+        sharding.allreduce_stats(stats)                     # the one collective of the path
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop(t_wall0, t_wall1)
+    ms_total = ev[0].elapsed_time(ev[-1])
+    kernel_ms = float(np.mean([ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]))
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * n * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: host pinned buffers through the host C-ABI call, copies inside the timed region
+    n_e2e = min(n, int(args.e2e_trials))
+    e2e = None
+    try:
+        h_cols = torch.empty((13, n_e2e), dtype=torch.float64, pin_memory=True)
+        h_cols.copy_(cols[:, :n_e2e])
+        h_err = torch.empty(n_e2e, dtype=torch.float64, pin_memory=True)
+        h_ndet = torch.empty(n_e2e, dtype=torch.int32, pin_memory=True)
+        hc, he, hn = h_cols.numpy(), h_err.numpy(), h_ndet.numpy()
+        eng.run_presampled(hc, SEED, trial0, 64, out_err=he, out_ndet=hn)       # warm: staging buffers allocate here
+        barrier()
+        e2e_steps = max(1, min(args.steps, 3))
+        tw = time.perf_counter()
+        for _ in range(e2e_steps):
+            eng.run_presampled(hc, SEED, trial0, 64, out_err=he, out_ndet=hn)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - tw], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n_e2e * e2e_steps / float(dt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": BYTES_IN_PER_TRIAL * n_e2e, "d2h_bytes_per_step": BYTES_OUT_PER_TRIAL * n_e2e,
+               "trials_per_gpu_per_step": n_e2e, "steps": e2e_steps,
+               "api": "stmpm_run_presampled_host (pinned host columns in, host records out, chunked H2D/kernel/D2H pipeline)",
+               "records_match_device_run": bool(np.array_equal(he, err[:n_e2e].cpu().numpy()))}
+    except RuntimeError as ex:                                                   # pinned allocation refused
+        e2e = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
+
+    out = None
+    if rank == 0:
+        st = stats.cpu().numpy()
+        summ = eng.summarize(st)
+        wc = eng.work_counters(d, 1 << 20, SEED, 0)
+        flops_trial = work_flops_per_trial(wc["visits"], wc["detected"])
+        peak64 = eng.fma_peak(64)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        k_s = kernel_ms * 1e-3
+        achieved_tf = flops_trial * n / k_s / 1e12
+        achieved_gbs = (BYTES_IN_PER_TRIAL + BYTES_OUT_PER_TRIAL) * n / k_s / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_trial")
+            traffic = traffic * n if traffic is not None else None
+        except (OSError, ValueError):
+            pass
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(n, world),
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {
+                "bound": "fp64", "kernel": "trials_kernel<presampled, fp64>",
+                "achieved": achieved_tf, "peak": peak64, "unit": "TFLOP/s", "frac": achieved_tf / peak64 if peak64 else None,
+                "peak_source": "stmpm_fma_peak: FP64 FMA-chain microbenchmark measured live on this GPU "
+                               "(MEASURED_PEAKS.json holds no FP64 figure)",
+                "flops_per_trial": flops_trial, "work_model": "430 + 7*N_visit + 81*N_star (DESIGN.md §4)",
+                "n_visit": wc["visits"], "n_mag_pass": wc["mag_pass"], "n_survivors": wc["survivors"],
+                "n_star": wc["detected"], "kernel_ms": kernel_ms, "traffic": traffic,
+                "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                        "bytes_per_trial": BYTES_IN_PER_TRIAL + BYTES_OUT_PER_TRIAL,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
+            },
+            "result": {k: summ[k] for k in ("n_ok", "n_fail", "fail_rate", "mean", "std", "sigma_halfnormal", "p99",
+                                            "p999", "mean_ndet")},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            v, dt = cpu_trials_per_sec(args.cpu_trials_per_core, cores)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": f"{cores * args.cpu_trials_per_core} trials of the same workload "
+                                             f"({args.cpu_trials_per_core} per process x {cores} processes, numpy fp64 "
+                                             f"oracle, {dt:.1f} s)"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--trials", type=float, default=1e8, help="trials per GPU per step (configs[1]: 1e8)")
+    ap.add_argument("--e2e-trials", type=float, default=1e8, help="trials per GPU per e2e step")
+    ap.add_argument("--cpu-trials-per-core", type=int, default=16384)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

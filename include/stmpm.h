@@ -82,8 +82,10 @@ int stmpm_set_catalog(stmpm_t* h, const double* xyz_host, const float* mag_host,
                       int32_t n_stars, int32_t n_bands, const int32_t* n_ra_host, const int32_t* cell_start_host);
 int stmpm_set_sensor(stmpm_t* h, const stmpm_sensor_cfg* cfg);
 
-int stmpm_stats_len(const stmpm_t* h, int64_t* n_doubles);
-int stmpm_stats_finalize(const stmpm_t* h, const double* packed_host, stmpm_summary* out);
+/* Packed statistics buffer (MODEL.md §9): STMPM_STATS_HEAD doubles then 34 * 2^hist_log2_sub histogram bins; every entry
+ * but x_max is a sum, so ranks merge with one allreduce(sum).  Host-only helpers (no GPU needed). */
+int stmpm_stats_len(int32_t hist_log2_sub, int64_t* n_doubles);
+int stmpm_stats_finalize(int32_t hist_log2_sub, const double* packed_host, stmpm_summary* out);
 
 /* (1) Pre-sampled mode == Simulation.run_sim(params, obj_func=quest_objective[, trueData]) over n DataFrame rows
  * (monte_carlo.py:52; sensitivity.py:77).  cols_dev: STMPM_NCOLS device pointers to n float64 each.
@@ -119,6 +121,10 @@ int stmpm_run_rng_host(stmpm_t* h, int precision, int64_t n_segments, int64_t tr
 
 /* FMA-chain microbenchmark: measured FP64 / FP32 FMA peak of this GPU in TFLOP/s (roofline denominator). */
 int stmpm_fma_peak(stmpm_t* h, int precision, double* tflops);
+/* Work-model calibration: runs n native-RNG trials through an instrumented build of the trial kernel and
+ * returns per-trial means [sky-grid stars visited, magnitude passes, pre-filter survivors, detected stars]. */
+int stmpm_work_counters(stmpm_t* h, int64_t n, uint64_t seed, int64_t trial0, const stmpm_dist* dist_host,
+                        double* per_trial4_host);
 /* Number of kernels this library has launched on this handle (bench.py's gpu_launches claim). */
 int stmpm_launch_count(const stmpm_t* h, int64_t* n);
 

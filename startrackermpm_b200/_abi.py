@@ -24,7 +24,7 @@ NORMAL_PARAMS = ("FOCAL_LENGTH", "F_ARR_EPS_X", "F_ARR_EPS_Y", "F_ARR_EPS_Z", "F
 EXPORTS = ("stmpm_last_error", "stmpm_version", "stmpm_create", "stmpm_destroy", "stmpm_device_info",
            "stmpm_set_catalog", "stmpm_set_sensor", "stmpm_stats_len", "stmpm_stats_finalize",
            "stmpm_trials_presampled", "stmpm_trials_rng", "stmpm_fill_presampled", "stmpm_run_presampled_host",
-           "stmpm_run_rng_host", "stmpm_fma_peak", "stmpm_launch_count")
+           "stmpm_run_rng_host", "stmpm_fma_peak", "stmpm_work_counters", "stmpm_launch_count")
 
 
 class SensorCfg(C.Structure):
@@ -67,14 +67,15 @@ def load():
     lib.stmpm_device_info.argtypes = [vp, P(i32), P(i64), P(i32), P(i32)]
     lib.stmpm_set_catalog.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
     lib.stmpm_set_sensor.argtypes = [vp, P(SensorCfg)]
-    lib.stmpm_stats_len.argtypes = [vp, P(i64)]
-    lib.stmpm_stats_finalize.argtypes = [vp, vp, P(Summary)]
+    lib.stmpm_stats_len.argtypes = [i32, P(i64)]
+    lib.stmpm_stats_finalize.argtypes = [i32, vp, P(Summary)]
     lib.stmpm_trials_presampled.argtypes = [vp, C.c_int, i64, u64, i64, P(vp), vp, vp, vp, vp]
     lib.stmpm_trials_rng.argtypes = [vp, C.c_int, i64, i64, u64, i64, P(Dist), vp, vp, vp, vp]
     lib.stmpm_fill_presampled.argtypes = [vp, i64, u64, i64, P(Dist), P(vp), vp]
     lib.stmpm_run_presampled_host.argtypes = [vp, C.c_int, i64, u64, i64, P(vp), vp, vp, vp]
     lib.stmpm_run_rng_host.argtypes = [vp, C.c_int, i64, i64, u64, i64, P(Dist), vp, vp, vp]
     lib.stmpm_fma_peak.argtypes = [vp, C.c_int, P(dbl)]
+    lib.stmpm_work_counters.argtypes = [vp, i64, u64, i64, P(Dist), P(dbl)]
     lib.stmpm_launch_count.argtypes = [vp, P(i64)]
     for name in EXPORTS:
         if name not in ("stmpm_last_error",):

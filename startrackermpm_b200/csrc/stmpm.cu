@@ -36,6 +36,7 @@ struct KArgs {
     int* ndet;
     double* stats;
     long long stats_len;
+    unsigned long long* counters;   // INSTR only: [visits, mag_pass, survivors, detected]
 };
 
 struct SmemLayout {
@@ -56,7 +57,8 @@ static SmemLayout smem_layout(int n_stars, int n_cells_pad, int n_bands, int n_b
 
 // ------------------------------------------------------------------------------------------------ the trial kernel
 // MODE 0: pre-sampled columns.  MODE 1: native RNG.  PREC 64 / 32: per-star arithmetic.
-template <int MODE, int PREC>
+// INSTR 1: also count sky-grid visits / magnitude passes / pre-filter survivors (work-model calibration, not timed).
+template <int MODE, int PREC, int INSTR>
 __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const SmemLayout L) {
     extern __shared__ __align__(16) unsigned char smem[];
     float4* s_cat = reinterpret_cast<float4*>(smem + L.cat32);
@@ -92,6 +94,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
         unsigned int acc_ok = 0, acc_fail = 0;
         unsigned long long acc_ndet = 0;
         double acc_x = 0.0, acc_xx = 0.0, acc_max = 0.0;
+        unsigned long long ins_visit = 0, ins_mag = 0, ins_surv = 0, ins_det = 0;
 
         for (long long tb = t_begin; tb < t_end; tb += TPB) {   // warp-uniform trip count
             const long long t = tb + threadIdx.x;
@@ -128,7 +131,6 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
             bool scanning = valid;
             int cnt = 0, n_det = 0;
             double B[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-            float Bf[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 
             do {
                 // ---- phase A: scan cells, push pre-filter survivors onto the per-thread list
@@ -154,7 +156,8 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
                         }
                         continue;
                     }
-                    if (prefilter(c, s_cat[i])) { s_list[cnt * TPB] = (uint16_t)i; ++cnt; }
+                    if (INSTR) { ++ins_visit; if (s_cat[i].w <= c.magf) ++ins_mag; }
+                    if (prefilter(c, s_cat[i])) { s_list[cnt * TPB] = (uint16_t)i; ++cnt; if (INSTR) ++ins_surv; }
                     ++i;
                 }
                 __syncwarp();
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
                     }
                     bool det;
                     if (PREC == 64) det = star_exact(c, s, t_lo, t_hi, a.k0, a.k1, a.f_ideal, a.half_u, a.half_v, B);
-                    else det = star_f32(c, s, t_lo, t_hi, a.k0, a.k1, a.f_ideal, a.half_u, a.half_v, Bf, B);
+                    else det = star_f32(c, s, t_lo, t_hi, a.k0, a.k1, a.f_ideal, a.half_u, a.half_v, B);
                     n_det += det ? 1 : 0;
                 }
                 cnt = 0;
@@ -178,11 +181,8 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
 
             // ---- solve + record
             double err = -1.0;
-            if (PREC == 32) {
-#pragma unroll
-                for (int k = 0; k < 9; ++k) B[k] += (double)Bf[k];
-            }
             if (n_det >= a.n_min) err = quest_error_arcsec(B, c.C, n_det);
+            if (INSTR && valid) ins_det += (unsigned long long)n_det;
             if (valid) {
                 if (a.err) __stcs(a.err + rec, err);
                 if (a.ndet) __stcs(a.ndet + rec, n_det);
@@ -206,6 +206,10 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
             }
         }
 
+        if (INSTR) {
+            atomicAdd(a.counters + 0, ins_visit); atomicAdd(a.counters + 1, ins_mag);
+            atomicAdd(a.counters + 2, ins_surv);  atomicAdd(a.counters + 3, ins_det);
+        }
         // ---- unit epilogue: block reduction of the moments, one atomic per CTA per quantity; histogram flush
         if (want_stats) {
             double v[5] = {(double)acc_ok, (double)acc_fail, acc_x, acc_xx, (double)acc_ndet};
@@ -310,7 +314,8 @@ struct stmpm_handle {
     double* stage_stats = nullptr;
     long long stage_stats_cap = 0;
     long long launches = 0;
-    size_t smem_attr_set[2][2] = {{0, 0}, {0, 0}};
+    size_t smem_attr_set[2][2][2] = {};
+    unsigned long long* counters = nullptr;
 };
 
 extern "C" const char* stmpm_last_error(void) { return g_err.c_str(); }
@@ -345,7 +350,7 @@ extern "C" int stmpm_destroy(stmpm_t* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaFree(h->cat32); cudaFree(h->cat64); cudaFree(h->cell_start); cudaFree(h->band_tab); cudaFree(h->dists);
-    cudaFree(h->stage_stats);
+    cudaFree(h->stage_stats); cudaFree(h->counters);
     free_stage(h);
     for (int i = 0; i < stmpm_handle::NBUF; ++i) if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
     delete h;
@@ -419,10 +424,10 @@ extern "C" int stmpm_set_sensor(stmpm_t* h, const stmpm_sensor_cfg* cfg) {
     return 0;
 }
 
-extern "C" int stmpm_stats_len(const stmpm_t* h, int64_t* n) {
-    if (!h || !n) return fail(STMPM_E_ARG, "stmpm_stats_len: null");
-    if (!h->have_sensor) return fail(STMPM_E_STATE, "stmpm_stats_len: call stmpm_set_sensor first");
-    *n = STMPM_STATS_HEAD + h->n_bins;
+extern "C" int stmpm_stats_len(int32_t hist_log2_sub, int64_t* n) {
+    if (!n) return fail(STMPM_E_ARG, "stmpm_stats_len: null");
+    if (hist_log2_sub < 4 || hist_log2_sub > 8) return fail(STMPM_E_ARG, "hist_log2_sub must be in [4, 8]");
+    *n = STMPM_STATS_HEAD + ((int64_t)STMPM_HIST_OCTAVES << hist_log2_sub);
     return 0;
 }
 
@@ -444,9 +449,10 @@ static double hist_percentile(const double* hist, int n_bins, int log2_sub, doub
     return std::ldexp(1.0, STMPM_HIST_MIN_EXP + STMPM_HIST_OCTAVES);
 }
 
-extern "C" int stmpm_stats_finalize(const stmpm_t* h, const double* s, stmpm_summary* o) {
-    if (!h || !s || !o) return fail(STMPM_E_ARG, "stmpm_stats_finalize: null");
-    if (!h->have_sensor) return fail(STMPM_E_STATE, "stmpm_stats_finalize: call stmpm_set_sensor first");
+extern "C" int stmpm_stats_finalize(int32_t hist_log2_sub, const double* s, stmpm_summary* o) {
+    if (!s || !o) return fail(STMPM_E_ARG, "stmpm_stats_finalize: null");
+    if (hist_log2_sub < 4 || hist_log2_sub > 8) return fail(STMPM_E_ARG, "hist_log2_sub must be in [4, 8]");
+    const int n_bins = STMPM_HIST_OCTAVES << hist_log2_sub;
     std::memset(o, 0, sizeof(*o));
     const double n = s[0], nf = s[1];
     o->n_ok = n; o->n_fail = nf;
@@ -461,22 +467,22 @@ extern "C" int stmpm_stats_finalize(const stmpm_t* h, const double* s, stmpm_sum
         o->sigma_halfnormal = o->std / std::sqrt(1.0 - 2.0 / M_PI);      // driver.py:290,324
         o->mean_halfnormal = o->sigma_halfnormal * std::sqrt(2.0 / M_PI); // driver.py:291,323
         const double* hist = s + STMPM_STATS_HEAD;
-        o->p50 = hist_percentile(hist, h->n_bins, h->cfg.hist_log2_sub, s[6], n, 0.50);
-        o->p90 = hist_percentile(hist, h->n_bins, h->cfg.hist_log2_sub, s[6], n, 0.90);
-        o->p99 = hist_percentile(hist, h->n_bins, h->cfg.hist_log2_sub, s[6], n, 0.99);
-        o->p999 = hist_percentile(hist, h->n_bins, h->cfg.hist_log2_sub, s[6], n, 0.999);
+        o->p50 = hist_percentile(hist, n_bins, hist_log2_sub, s[6], n, 0.50);
+        o->p90 = hist_percentile(hist, n_bins, hist_log2_sub, s[6], n, 0.90);
+        o->p99 = hist_percentile(hist, n_bins, hist_log2_sub, s[6], n, 0.99);
+        o->p999 = hist_percentile(hist, n_bins, hist_log2_sub, s[6], n, 0.999);
     }
     return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ launch helper
-template <int MODE, int PREC>
+template <int MODE, int PREC, int INSTR = 0>
 static int launch_trials(stmpm_handle* h, KArgs& a, cudaStream_t st) {
     const SmemLayout L = smem_layout(a.n_stars, a.n_cells_pad, a.n_bands, a.n_bins + 2);
     if (L.total > (size_t)h->prop.sharedMemPerBlockOptin)
         return fail(STMPM_E_ARG, "catalog too large for shared-memory staging (" + std::to_string(L.total) + " B)");
-    auto kern = trials_kernel<MODE, PREC>;
-    size_t& cached = h->smem_attr_set[MODE][PREC == 64 ? 0 : 1];
+    auto kern = trials_kernel<MODE, PREC, INSTR>;
+    size_t& cached = h->smem_attr_set[MODE][PREC == 64 ? 0 : 1][INSTR];
     if (cached < L.total) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
         cached = L.total;
@@ -708,6 +714,26 @@ extern "C" int stmpm_fma_peak(stmpm_t* h, int precision, double* tflops) {
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
     *tflops = best;
+    return 0;
+}
+
+extern "C" int stmpm_work_counters(stmpm_t* h, int64_t n, uint64_t seed, int64_t trial0, const stmpm_dist* dist,
+                                   double* per_trial4) {
+    KArgs a;
+    if (int rc = fill_common(h, a, 64)) return rc;
+    if (n <= 0 || !dist || !per_trial4) return fail(STMPM_E_ARG, "stmpm_work_counters: bad arguments");
+    CK(cudaSetDevice(h->device));
+    if (!h->counters) CK(cudaMalloc(&h->counters, 4 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(h->counters, 0, 4 * sizeof(unsigned long long), h->streams[0]));
+    to_dev_dist(*dist, a.dist0);
+    a.n_segments = 1; a.trials_per_segment = n; a.trial0 = trial0;
+    a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
+    a.counters = h->counters;
+    if (int rc = launch_trials<1, 64, 1>(h, a, h->streams[0])) return rc;
+    unsigned long long c[4];
+    CK(cudaMemcpyAsync(c, h->counters, sizeof(c), cudaMemcpyDeviceToHost, h->streams[0]));
+    CK(cudaStreamSynchronize(h->streams[0]));
+    for (int i = 0; i < 4; ++i) per_trial4[i] = (double)c[i] / (double)n;
     return 0;
 }
 

@@ -168,11 +168,14 @@ __device__ __forceinline__ bool star_exact(const TrialCtx& c, const StarRec& s, 
     return det;
 }
 
-// fp32 star evaluation (precision = 32).  The detection decision is re-taken in fp64 when the fp32 centroid lies inside
-// a guard band around the array edge, so detection counts stay bit-exact with the fp64 oracle.
+// fp32 star evaluation (precision = 32): projection, noise and back-projection in fp32.  Two things stay fp64 because
+// they decide the parity bars: (a) the detection decision is re-taken in fp64 when the fp32
+// centroid lies inside a guard band around the array edge, so detection counts stay bit-exact with the fp64 oracle;
+// (b) B is accumulated in fp64 against the fp64 reference vector — roll about the boresight is ~1/sin(FOV/2) less
+// observable than pointing, and fp32 partial sums of B (ulp ~1e-6 at |B| ~ 16) would cost ~1e-6 rad of roll.
 __device__ __forceinline__ bool star_f32(const TrialCtx& c, const StarRec& s, uint32_t t_lo, uint32_t t_hi, uint32_t k0,
                                          uint32_t k1, double f_ideal, double half_u, double half_v,
-                                         float* __restrict__ Bf, double* __restrict__ Bd) {
+                                         double* __restrict__ B) {
     const float sx = (float)s.x, sy = (float)s.y, sz = (float)s.z;
     const float dn = c.NIf[0] * sx + c.NIf[1] * sy + c.NIf[2] * sz;
     const float du = c.EUf[0] * sx + c.EUf[1] * sy + c.EUf[2] * sz;
@@ -187,15 +190,15 @@ __device__ __forceinline__ bool star_f32(const TrialCtx& c, const StarRec& s, ui
     const float hu = (float)half_u, hv = (float)half_v;
     const float guard = 0.05f + 1e-5f * fabsf(c.np0f) + 1e-4f * ((float)c.sx + (float)c.sy);
     if (!(dn > 0.02f) || fabsf(fabsf(um) - hu) <= guard || fabsf(fabsf(vm) - hv) <= guard)
-        return star_exact(c, s, t_lo, t_hi, k0, k1, f_ideal, half_u, half_v, Bd);   // rare: exact decision + exact b
+        return star_exact(c, s, t_lo, t_hi, k0, k1, f_ideal, half_u, half_v, B);   // rare: exact decision + exact b
     const bool det = (fabsf(um) <= hu) && (fabsf(vm) <= hv);
     if (det) {
         const float fi = (float)f_ideal;
         const float inv = rsqrtf(um * um + vm * vm + fi * fi);
-        const float bx = um * inv, by = vm * inv, bz = fi * inv;
-        Bf[0] = fmaf(bx, sx, Bf[0]); Bf[1] = fmaf(bx, sy, Bf[1]); Bf[2] = fmaf(bx, sz, Bf[2]);
-        Bf[3] = fmaf(by, sx, Bf[3]); Bf[4] = fmaf(by, sy, Bf[4]); Bf[5] = fmaf(by, sz, Bf[5]);
-        Bf[6] = fmaf(bz, sx, Bf[6]); Bf[7] = fmaf(bz, sy, Bf[7]); Bf[8] = fmaf(bz, sz, Bf[8]);
+        const double bx = (double)(um * inv), by = (double)(vm * inv), bz = (double)(fi * inv);
+        B[0] = fma(bx, s.x, B[0]); B[1] = fma(bx, s.y, B[1]); B[2] = fma(bx, s.z, B[2]);
+        B[3] = fma(by, s.x, B[3]); B[4] = fma(by, s.y, B[4]); B[5] = fma(by, s.z, B[5]);
+        B[6] = fma(bz, s.x, B[6]); B[7] = fma(bz, s.y, B[7]); B[8] = fma(bz, s.z, B[8]);
     }
     return det;
 }

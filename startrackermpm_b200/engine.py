@@ -78,8 +78,7 @@ class TrialEngine:
         self.f_ideal = float(f_ideal)
         self.hist_log2_sub = int(hist_log2_sub)
         n = C.c_int64()
-        _abi.check(self._lib.stmpm_stats_len(self._h, C.byref(n)))
-        self.stats_len = int(n.value)
+        self.stats_len = stats_len(hist_log2_sub)
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -107,6 +106,13 @@ class TrialEngine:
         t = C.c_double()
         _abi.check(self._lib.stmpm_fma_peak(self._h, int(precision), C.byref(t)))
         return float(t.value)
+
+    def work_counters(self, dist: _abi.Dist, n: int = 1 << 20, seed: int = 1, trial0: int = 0) -> dict:
+        """Per-trial means of the instrumented kernel: stars visited in the sky grid, magnitude passes, pre-filter
+        survivors, detected stars (DESIGN.md §4 work model)."""
+        out = (C.c_double * 4)()
+        _abi.check(self._lib.stmpm_work_counters(self._h, int(n), int(seed), int(trial0), C.byref(dist), out))
+        return {"visits": out[0], "mag_pass": out[1], "survivors": out[2], "detected": out[3]}
 
     # ---------------------------------------------------------------- pre-sampled mode
     @staticmethod
@@ -185,13 +191,23 @@ class TrialEngine:
 
     # ---------------------------------------------------------------- statistics
     def summarize(self, stats: np.ndarray) -> dict:
-        """Final reductions (driver.py:321-324; toolplot.py:82) of one packed stats buffer."""
-        stats = np.ascontiguousarray(stats, dtype=np.float64).reshape(-1)
-        if stats.shape[0] != self.stats_len:
-            raise ValueError(f"packed stats buffer must have {self.stats_len} doubles")
-        s = _abi.Summary()
-        _abi.check(self._lib.stmpm_stats_finalize(self._h, _ptr(stats), C.byref(s)))
-        return {k: getattr(s, k) for k, _ in _abi.Summary._fields_}
+        return summarize(stats, self.hist_log2_sub)
+
+
+def stats_len(hist_log2_sub: int = 8) -> int:
+    n = C.c_int64()
+    _abi.check(_abi.load().stmpm_stats_len(int(hist_log2_sub), C.byref(n)))
+    return int(n.value)
+
+
+def summarize(stats: np.ndarray, hist_log2_sub: int = 8) -> dict:
+    """Final reductions (driver.py:321-324; toolplot.py:82) of one packed stats buffer — host-side C, no GPU needed."""
+    stats = np.ascontiguousarray(stats, dtype=np.float64).reshape(-1)
+    if stats.shape[0] != stats_len(hist_log2_sub):
+        raise ValueError(f"packed stats buffer must have {stats_len(hist_log2_sub)} doubles")
+    s = _abi.Summary()
+    _abi.check(_abi.load().stmpm_stats_finalize(int(hist_log2_sub), _ptr(stats), C.byref(s)))
+    return {k: getattr(s, k) for k, _ in _abi.Summary._fields_}
 
 
 def _torch_f64():

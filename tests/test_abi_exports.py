@@ -1,0 +1,55 @@
+"""The C-ABI library builds (nvcc cross-compiles sm_100a without a GPU), loads, and exports every symbol include/stmpm.h
+declares.  No compute call is made here."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "stmpm.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(stmpm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_documented_surface():
+    syms = header_symbols()
+    for must in ("stmpm_create", "stmpm_set_catalog", "stmpm_set_sensor", "stmpm_trials_presampled",
+                 "stmpm_trials_rng", "stmpm_run_presampled_host", "stmpm_stats_finalize"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol(lib_built):
+    lib = ctypes.CDLL(lib_built)
+    for s in header_symbols():
+        assert hasattr(lib, s), f"{s} declared in include/stmpm.h but not exported"
+    from startrackermpm_b200 import _abi
+    assert sorted(_abi.EXPORTS) == header_symbols()
+
+
+def test_kernels_are_sm100a_only(lib_built):
+    out = subprocess.run(["cuobjdump", "-lelf", lib_built], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_cpu_fallback_without_gpu(lib_built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from startrackermpm_b200 import _abi
+    from startrackermpm_b200.engine import TrialEngine
+    with pytest.raises(_abi.StmpmError, match="no CUDA device"):
+        TrialEngine(0)
+
+
+def test_header_is_plain_c(tmp_path):
+    c = tmp_path / "t.c"
+    c.write_text('#include "stmpm.h"\nint main(void){ stmpm_dist d; stmpm_summary s; (void)d; (void)s; return STMPM_NCOLS == 13 ? 0 : 1; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(c), "-o",
+                    str(tmp_path / "t")], check=True)
+    assert subprocess.run([str(tmp_path / "t")]).returncode == 0
