@@ -45,6 +45,8 @@ typedef struct {
     double  half_v;       /* SENSOR_HEIGHT / 2 = 512 */
     int32_t n_min;        /* minimum detected stars for a solve (3) */
     int32_t hist_log2_sub;/* histogram sub-bins per octave = 2^k, 4 <= k <= 8 (8 -> 8704 bins) */
+    double  scan_pad_px;  /* candidate lists cover the ideal array grown by this many px (0 = default 32); trials
+                             whose perturbations + noise exceed it still run, on the slower sky-grid scan */
 } stmpm_sensor_cfg;
 
 /* Parameter distributions for native-RNG mode (MODEL.md §6): normal(mean, sigma) in the order
@@ -125,6 +127,9 @@ int stmpm_fma_peak(stmpm_t* h, int precision, double* tflops);
  * returns per-trial means [sky-grid stars visited, magnitude passes, pre-filter survivors, detected stars]. */
 int stmpm_work_counters(stmpm_t* h, int64_t n, uint64_t seed, int64_t trial0, const stmpm_dist* dist_host,
                         double* per_trial4_host);
+/* Diagnostic, host-only (no GPU): the table-based Box-Muller of the star loop (MODEL.md §5), compiled for the host from
+ * the same source the kernels use, so its accuracy can be checked against libm without a GPU. */
+int stmpm_debug_box_muller(const uint32_t* wa, const uint32_t* wb, int64_t n, double* z1, double* z2);
 /* Number of kernels this library has launched on this handle (bench.py's gpu_launches claim). */
 int stmpm_launch_count(const stmpm_t* h, int64_t* n);
 

@@ -39,6 +39,29 @@ def philox4x32_10(c0, c1, c2, c3, k0: int, k1: int):
     return tuple(c.astype(np.uint32) for c in (c0, c1, c2, c3))
 
 
+M2 = np.uint64(0xD256D193)   # Philox2x32 multiplier (Random123)
+
+
+def philox2x32_10(c0, c1, k0):
+    """Vectorised Philox2x32-10: counter (c0, c1), ONE 32-bit key word (array or int). Returns 2 uint32 arrays."""
+    c0, c1, k = np.broadcast_arrays(*(np.asarray(c, dtype=np.uint64) & MASK32 for c in (c0, c1, k0)))
+    for _ in range(10):
+        p = M2 * c0
+        c0, c1 = (p >> SHIFT32) ^ k ^ c1, p & MASK32
+        k = (k + np.uint64(W0)) & MASK32
+    return c0.astype(np.uint32), c1.astype(np.uint32)
+
+
+def star_words(seed: int, trial_idx, star_id):
+    """MODEL.md §5: the two 32-bit words behind one star's centroid noise.
+    Per trial a key pair (ka, kb) = first two words of Philox4x32-10(ctr = (trial_lo, trial_hi, 0, "STAR"), key = seed);
+    per star (x0, x1) = Philox2x32-10(ctr = (star_id, kb), key = ka)."""
+    k0, k1 = split_seed(seed)
+    tl, th = split_index(trial_idx)
+    ka, kb, _, _ = philox4x32_10(tl, th, 0, TAG_STAR, k0, k1)
+    return philox2x32_10(np.asarray(star_id, dtype=np.uint64), kb, ka)
+
+
 def u01(w):
     """(w + 0.5) * 2^-32 in float64: strictly inside (0, 1), exact."""
     return (np.asarray(w, dtype=np.float64) + 0.5) * (1.0 / 4294967296.0)

@@ -147,12 +147,13 @@ def candidate_cos_limit(cols):
 
 
 def run_trials(cols, cat_xyz, cat_mag, f_ideal, seed, trial0=0, *, brute=False, chunk=512, n_min=N_MIN,
-               solver="q_method", return_aux=False):
+               solver="q_method", return_aux=False, star_ids=None):
     """The hot path (reference: Simulation.run_sim + quest_objective, called at monte_carlo.py:52 / sensitivity.py:77;
     bodies absent) per docs/MODEL.md §2-§5.
 
     cols: float64 [13, n] in COLUMNS order (pre-sampled rows).  Returns (err_arcsec f64 [n] with -1 = failed,
-    n_det int32 [n]).  Trial i uses global trial index trial0 + i for its Philox stream.
+    n_det int32 [n]).  Trial i uses global trial index trial0 + i for its Philox stream; star_ids (default: row index)
+    are the catalog-file indices that key each star's noise, independent of the order of cat_xyz's rows.
     """
     cols = np.ascontiguousarray(np.asarray(cols, dtype=np.float64))
     assert cols.shape[0] == 13
@@ -162,10 +163,10 @@ def run_trials(cols, cat_xyz, cat_mag, f_ideal, seed, trial0=0, *, brute=False, 
     err = np.empty(n, dtype=np.float64)
     ndet = np.empty(n, dtype=np.int32)
     aux = {"n_cand": 0, "lam": np.empty(n)} if return_aux else None
-    k0, k1 = philox.split_seed(seed)
+    star_ids = np.arange(cat_xyz.shape[0], dtype=np.uint64) if star_ids is None else np.asarray(star_ids, np.uint64)
     for s0 in range(0, n, chunk):
         sl = slice(s0, min(n, s0 + chunk))
-        e, d, a = _run_chunk(cols[:, sl], cat_xyz, cat_mag64, float(f_ideal), k0, k1,
+        e, d, a = _run_chunk(cols[:, sl], cat_xyz, cat_mag64, star_ids, float(f_ideal), seed,
                              np.uint64(trial0) + np.arange(sl.start, sl.stop, dtype=np.uint64), brute, n_min, solver)
         err[sl], ndet[sl] = e, d
         if return_aux:
@@ -174,7 +175,7 @@ def run_trials(cols, cat_xyz, cat_mag, f_ideal, seed, trial0=0, *, brute=False, 
     return (err, ndet, aux) if return_aux else (err, ndet)
 
 
-def _run_chunk(cols, cat_xyz, cat_mag64, f_ideal, k0, k1, trial_idx, brute, n_min, solver):
+def _run_chunk(cols, cat_xyz, cat_mag64, star_ids, f_ideal, seed, trial_idx, brute, n_min, solver):
     m = cols.shape[1]
     ra, dec, roll, f, ex, ey, ez, phi, theta, psi, devx, devy, maxmag = cols
     C = truth_attitude(ra, dec, roll)                      # [m,3,3] body->inertial
@@ -198,8 +199,7 @@ def _run_chunk(cols, cat_xyz, cat_mag64, f_ideal, k0, k1, trial_idx, brute, n_mi
     u = np.einsum("pi,pi->p", e_u[ti], P)
     v = np.einsum("pi,pi->p", e_v[ti], P)
 
-    tl, th = philox.split_index(trial_idx[ti])
-    x0, x1, _, _ = philox.philox4x32_10(tl, th, si.astype(np.uint64), philox.TAG_STAR, k0, k1)
+    x0, x1 = philox.star_words(seed, trial_idx[ti], star_ids[si])
     z1, z2 = philox.box_muller(x0, x1)
     um = u + np.abs(devx[ti]) * z1
     vm = v + np.abs(devy[ti]) * z2

@@ -24,12 +24,12 @@ NORMAL_PARAMS = ("FOCAL_LENGTH", "F_ARR_EPS_X", "F_ARR_EPS_Y", "F_ARR_EPS_Z", "F
 EXPORTS = ("stmpm_last_error", "stmpm_version", "stmpm_create", "stmpm_destroy", "stmpm_device_info",
            "stmpm_set_catalog", "stmpm_set_sensor", "stmpm_stats_len", "stmpm_stats_finalize",
            "stmpm_trials_presampled", "stmpm_trials_rng", "stmpm_fill_presampled", "stmpm_run_presampled_host",
-           "stmpm_run_rng_host", "stmpm_fma_peak", "stmpm_work_counters", "stmpm_launch_count")
+           "stmpm_run_rng_host", "stmpm_fma_peak", "stmpm_work_counters", "stmpm_debug_box_muller", "stmpm_launch_count")
 
 
 class SensorCfg(C.Structure):
     _fields_ = [("f_ideal", C.c_double), ("half_u", C.c_double), ("half_v", C.c_double),
-                ("n_min", C.c_int32), ("hist_log2_sub", C.c_int32)]
+                ("n_min", C.c_int32), ("hist_log2_sub", C.c_int32), ("scan_pad_px", C.c_double)]
 
 
 class Dist(C.Structure):
@@ -76,6 +76,7 @@ def load():
     lib.stmpm_run_rng_host.argtypes = [vp, C.c_int, i64, i64, u64, i64, P(Dist), vp, vp, vp]
     lib.stmpm_fma_peak.argtypes = [vp, C.c_int, P(dbl)]
     lib.stmpm_work_counters.argtypes = [vp, i64, u64, i64, P(Dist), P(dbl)]
+    lib.stmpm_debug_box_muller.argtypes = [vp, vp, i64, vp, vp]
     lib.stmpm_launch_count.argtypes = [vp, P(i64)]
     for name in EXPORTS:
         if name not in ("stmpm_last_error",):

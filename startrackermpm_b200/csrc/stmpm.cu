@@ -24,6 +24,13 @@ struct KArgs {
     const int2* band_tab;         // (cell_base, n_ra) per band
     int n_stars, n_cells_pad, n_bands;
     float inv_band_h;
+    // per-boresight-cell candidate lists (magnitude-sorted star indices), the fast phase-A path
+    const int2* lk_band_tab;      // lookup grid: (cell_base, n_ra) per band
+    const uint32_t* lk_off;       // n_lk_cells + 1 offsets into lk_list (multiples of 8 entries)
+    const uint16_t* lk_list;      // star indices into the sorted catalog, 0xFFFF padded
+    int lk_bands;
+    float lk_inv_band_h, lk_cone; // a trial whose scan cone exceeds lk_cone takes the sky-grid scan instead
+    const MathTables* tables;
     double f_ideal, half_u, half_v;
     int n_min, hist_shift, n_bins;   // hist_shift = 52 - log2(sub-bins per octave)
     long long n_segments, trials_per_segment, trial0, part_len;
@@ -40,14 +47,16 @@ struct KArgs {
 };
 
 struct SmemLayout {
-    size_t cat32, cell_start, band_tab, hist, list, red, total;
+    size_t cat32, cell_start, band_tab, lk_band_tab, tables, hist, list, red, total;
 };
-static SmemLayout smem_layout(int n_stars, int n_cells_pad, int n_bands, int n_bins) {
+static SmemLayout smem_layout(int n_stars, int n_cells_pad, int n_bands, int lk_bands, int n_bins) {
     SmemLayout L;
     size_t o = 0;
     L.cat32 = o;      o += (size_t)n_stars * 16;
     L.cell_start = o; o += (((size_t)n_cells_pad * 2) + 15) / 16 * 16;
     L.band_tab = o;   o += (((size_t)n_bands * 8) + 15) / 16 * 16;
+    L.lk_band_tab = o; o += (((size_t)lk_bands * 8) + 15) / 16 * 16;
+    L.tables = o;     o += (sizeof(MathTables) + 15) / 16 * 16;
     L.hist = o;       o += (size_t)n_bins * 4;
     L.list = o;       o += (size_t)LIST_CAP * TPB * 2;
     L.red = o;        o += (size_t)(TPB / 32) * 8 * 8;
@@ -64,6 +73,8 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
     float4* s_cat = reinterpret_cast<float4*>(smem + L.cat32);
     uint16_t* s_cell = reinterpret_cast<uint16_t*>(smem + L.cell_start);
     int2* s_band = reinterpret_cast<int2*>(smem + L.band_tab);
+    int2* s_lkband = reinterpret_cast<int2*>(smem + L.lk_band_tab);
+    const MathTables* s_tab = reinterpret_cast<const MathTables*>(smem + L.tables);
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem + L.hist);
     uint16_t* s_list = reinterpret_cast<uint16_t*>(smem + L.list) + threadIdx.x;   // entry j at s_list[j * TPB]
     double* s_red = reinterpret_cast<double*>(smem + L.red);
@@ -75,6 +86,12 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
         for (int i = threadIdx.x; i < a.n_stars; i += TPB) s[i] = __ldg(g + i);
         for (int i = threadIdx.x; i < a.n_cells_pad; i += TPB) s_cell[i] = __ldg(a.cell_start + i);
         for (int i = threadIdx.x; i < a.n_bands; i += TPB) s_band[i] = __ldg(a.band_tab + i);
+        for (int i = threadIdx.x; i < a.lk_bands; i += TPB) s_lkband[i] = __ldg(a.lk_band_tab + i);
+        {
+            const double* gt = reinterpret_cast<const double*>(a.tables);
+            double* stb = reinterpret_cast<double*>(smem + L.tables);
+            for (int i = threadIdx.x; i < (int)(sizeof(MathTables) / 8); i += TPB) stb[i] = __ldg(gt + i);
+        }
         for (int i = threadIdx.x; i < a.n_bins + 2; i += TPB) s_hist[i] = 0u;
     }
     __syncthreads();
@@ -124,7 +141,22 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
             TrialCtx c;
             trial_setup(p, a.half_u, a.half_v, c);
 
-            // ---- sky-grid scan state (fp32, conservative)
+            uint32_t ka, kb;
+            star_key(t_lo, t_hi, a.k0, a.k1, ka, kb);
+
+            // ---- phase-A state.  Fast path: the magnitude-sorted candidate list of the boresight's lookup cell.
+            // Fallback (scan cone wider than the lists were built for): walk the sky-grid bands (fp32, conservative).
+            const bool use_list = c.cone <= a.lk_cone;
+            const uint16_t* lp = a.lk_list;
+            int lk = 0, lk_len = 0;
+            if (use_list) {
+                const int lb = min(a.lk_bands - 1, max(0, (int)floorf((c.dec0 + 1.57079633f) * a.lk_inv_band_h)));
+                const int2 bt = s_lkband[lb];
+                const int rc = min(bt.y - 1, max(0, (int)floorf(c.ra0 * 0.159154943f * (float)bt.y)));
+                const uint32_t o0 = __ldg(a.lk_off + bt.x + rc), o1 = __ldg(a.lk_off + bt.x + rc + 1);
+                lp += o0;
+                lk_len = (int)(o1 - o0);
+            }
             int b = max(0, (int)floorf((c.dec0 - c.cone + 1.57079633f) * a.inv_band_h));
             const int b_hi = min(a.n_bands - 1, (int)floorf((c.dec0 + c.cone + 1.57079633f) * a.inv_band_h));
             int i = 0, i_end = 0, pi = 0, p_end = 0;
@@ -133,32 +165,56 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
             double B[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 
             do {
-                // ---- phase A: scan cells, push pre-filter survivors onto the per-thread list
-                while (scanning && cnt < LIST_CAP) {
-                    if (i >= i_end) {
-                        if (pi < p_end) { i = pi; i_end = p_end; pi = p_end = 0; continue; }
-                        if (b > b_hi) { scanning = false; break; }
-                        const int2 bt = s_band[b];
-                        ++b;
-                        const int base = bt.x, n = bt.y;
-                        if (c.dalpha < 0.0f) { i = s_cell[base]; i_end = s_cell[base + n]; continue; }
-                        const float inv_w = (float)n * 0.159154943f;
-                        const int c_lo = (int)floorf((c.ra0 - c.dalpha) * inv_w);
-                        const int c_hi = (int)floorf((c.ra0 + c.dalpha) * inv_w);
-                        const int count = c_hi - c_lo + 1;
-                        if (count >= n) { i = s_cell[base]; i_end = s_cell[base + n]; continue; }
-                        int lo = c_lo % n;
-                        if (lo < 0) lo += n;
-                        if (lo + count <= n) { i = s_cell[base + lo]; i_end = s_cell[base + lo + count]; }
-                        else {
-                            i = s_cell[base + lo]; i_end = s_cell[base + n];
-                            pi = s_cell[base]; p_end = s_cell[base + lo + count - n];
+                if (use_list) {
+                    // ---- phase A (fast): all lanes walk their own list in lock-step, 8 indices per 16-byte load;
+                    // the list is sorted by magnitude, so the first star fainter than MAX_MAGNITUDE ends the scan
+                    while (scanning && cnt <= LIST_CAP - 8) {
+                        if (lk >= lk_len) { scanning = false; break; }
+                        const uint4 pk = __ldg(reinterpret_cast<const uint4*>(lp + lk));
+                        lk += 8;
+                        const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const uint32_t idx = (w4[e >> 1] >> (16 * (e & 1))) & 0xffffu;
+                            if (idx == 0xffffu) { scanning = false; break; }
+                            const float4 sc = s_cat[idx];
+                            if (INSTR) { ++ins_visit; }
+                            if (!(sc.w <= c.magf)) { scanning = false; break; }
+                            if (INSTR) { ++ins_mag; }
+                            if (prefilter_geom(c, sc)) { s_list[cnt * TPB] = (uint16_t)idx; ++cnt; if (INSTR) ++ins_surv; }
                         }
-                        continue;
                     }
-                    if (INSTR) { ++ins_visit; if (s_cat[i].w <= c.magf) ++ins_mag; }
-                    if (prefilter(c, s_cat[i])) { s_list[cnt * TPB] = (uint16_t)i; ++cnt; if (INSTR) ++ins_surv; }
-                    ++i;
+                } else {
+                    // ---- phase A (fallback): scan sky-grid cells, push pre-filter survivors onto the per-thread list
+                    while (scanning && cnt < LIST_CAP) {
+                        if (i >= i_end) {
+                            if (pi < p_end) { i = pi; i_end = p_end; pi = p_end = 0; continue; }
+                            if (b > b_hi) { scanning = false; break; }
+                            const int2 bt = s_band[b];
+                            ++b;
+                            const int base = bt.x, n = bt.y;
+                            if (c.dalpha < 0.0f) { i = s_cell[base]; i_end = s_cell[base + n]; continue; }
+                            const float inv_w = (float)n * 0.159154943f;
+                            const int c_lo = (int)floorf((c.ra0 - c.dalpha) * inv_w);
+                            const int c_hi = (int)floorf((c.ra0 + c.dalpha) * inv_w);
+                            const int count = c_hi - c_lo + 1;
+                            if (count >= n) { i = s_cell[base]; i_end = s_cell[base + n]; continue; }
+                            int lo = c_lo % n;
+                            if (lo < 0) lo += n;
+                            if (lo + count <= n) { i = s_cell[base + lo]; i_end = s_cell[base + lo + count]; }
+                            else {
+                                i = s_cell[base + lo]; i_end = s_cell[base + n];
+                                pi = s_cell[base]; p_end = s_cell[base + lo + count - n];
+                            }
+                            continue;
+                        }
+                        const float4 sc = s_cat[i];
+                        if (INSTR) { ++ins_visit; if (sc.w <= c.magf) ++ins_mag; }
+                        if (sc.w <= c.magf && prefilter_geom(c, sc)) {
+                            s_list[cnt * TPB] = (uint16_t)i; ++cnt; if (INSTR) ++ins_surv;
+                        }
+                        ++i;
+                    }
                 }
                 __syncwarp();
                 // ---- phase B: exact evaluation of the listed stars (lanes in lock-step)
@@ -172,8 +228,8 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
                         s.star_id = (uint32_t)(__double_as_longlong(hi.y) & 0xffffffffll);
                     }
                     bool det;
-                    if (PREC == 64) det = star_exact(c, s, t_lo, t_hi, a.k0, a.k1, a.f_ideal, a.half_u, a.half_v, B);
-                    else det = star_f32(c, s, t_lo, t_hi, a.k0, a.k1, a.f_ideal, a.half_u, a.half_v, B);
+                    if (PREC == 64) det = star_exact(c, s_tab, s, ka, kb, a.f_ideal, a.half_u, a.half_v, B);
+                    else det = star_f32(c, s_tab, s, ka, kb, a.f_ideal, a.half_u, a.half_v, B);
                     n_det += det ? 1 : 0;
                 }
                 cnt = 0;
@@ -298,6 +354,15 @@ struct stmpm_handle {
     uint16_t* cell_start = nullptr;
     int2* band_tab = nullptr;
     int n_stars = 0, n_cells_pad = 0, n_bands = 0;
+    std::vector<float> h_xyzf;    // host copy of the sorted catalog directions + magnitudes (candidate-list builds)
+    std::vector<float> h_mag;
+    int2* lk_band_tab = nullptr;
+    uint32_t* lk_off = nullptr;
+    uint16_t* lk_list = nullptr;
+    int lk_bands = 0;
+    float lk_cone = -1.0f;
+    long long lk_entries = 0;
+    MathTables* tables = nullptr;
     bool have_catalog = false, have_sensor = false;
     stmpm_sensor_cfg cfg{};
     int n_bins = 0;
@@ -318,6 +383,96 @@ struct stmpm_handle {
     unsigned long long* counters = nullptr;
 };
 
+// Tables of box_muller_tab (stmpm_device.cuh), computed with the host libm.
+static void stmpm_host_tables(MathTables* t) {
+    for (int j = 0; j < 128; ++j) {
+        const double c = 1.0 + (j + 0.5) / 128.0;
+        t->log_inv_c[j] = 1.0 / c;
+        t->log_ln_c[j] = std::log(c);
+    }
+    for (int k = 0; k < 34; ++k) t->k_ln2[k] = k * M_LN2;
+    for (int j = 0; j < 64; ++j) {
+        const double a = (M_PI / 2.0) * (j + 0.5) / 64.0;
+        t->sc_sin[j] = std::sin(a);
+        t->sc_cos[j] = std::cos(a);
+    }
+}
+
+// Candidate lists: for every cell of a ~1 degree boresight lookup grid, the indices (into the sorted catalog) of all stars
+// within lk_cone + cell radius of the cell centre, ordered by magnitude (brightest first).  A trial whose boresight falls
+// in the cell and whose scan cone is <= lk_cone finds every star that can reach its sensor in this list.
+static int rebuild_lists(stmpm_handle* h) {
+    if (!h->have_catalog || !h->have_sensor) return 0;
+    const stmpm_sensor_cfg& cfg = h->cfg;
+    const double pad = cfg.scan_pad_px > 0 ? cfg.scan_pad_px : 32.0;
+    const double cone = std::atan(std::sqrt(2.0) * (std::max(cfg.half_u, cfg.half_v) + pad) / cfg.f_ideal) + 0.002;
+    const int S = h->n_stars;
+    // stars in magnitude order, SoA floats
+    std::vector<int> order(S);
+    for (int i = 0; i < S; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h->h_mag[a] < h->h_mag[b]; });
+    std::vector<float> sx(S), sy(S), sz(S), dots(S);
+    for (int i = 0; i < S; ++i) {
+        sx[i] = h->h_xyzf[3 * order[i]]; sy[i] = h->h_xyzf[3 * order[i] + 1]; sz[i] = h->h_xyzf[3 * order[i] + 2];
+    }
+    const int nb = 180;
+    const double bh = M_PI / nb;
+    std::vector<int2> bt(nb);
+    long long n_cells = 0;
+    for (int b = 0; b < nb; ++b) {
+        const double dm = -M_PI / 2 + (b + 0.5) * bh;
+        const int n_ra = std::max(1, (int)std::lround(2.0 * M_PI * std::cos(dm) / bh));
+        bt[b] = make_int2((int)n_cells, n_ra);
+        n_cells += n_ra;
+    }
+    std::vector<uint32_t> off(n_cells + 1, 0);
+    std::vector<uint16_t> list;
+    list.reserve((size_t)n_cells * 160);
+    for (int b = 0; b < nb; ++b) {
+        const double d0 = -M_PI / 2 + b * bh, d1 = d0 + bh, dm = 0.5 * (d0 + d1);
+        const int n_ra = bt[b].y;
+        const double w = 2.0 * M_PI / n_ra;
+        // cell radius: farthest boundary point from the centre (same for every cell of the band), sampled + 10 %
+        double rho = 0.0;
+        for (int e = 0; e <= 16; ++e) {
+            const double ra = -0.5 * w + w * e / 16.0;
+            for (double dd : {d0, d1}) {
+                const double cd = std::cos(dm) * std::cos(dd) * std::cos(ra) + std::sin(dm) * std::sin(dd);
+                rho = std::max(rho, std::acos(std::min(1.0, std::max(-1.0, cd))));
+            }
+            const double dd = d0 + bh * e / 16.0;
+            const double cd = std::cos(dm) * std::cos(dd) * std::cos(0.5 * w) + std::sin(dm) * std::sin(dd);
+            rho = std::max(rho, std::acos(std::min(1.0, std::max(-1.0, cd))));
+        }
+        const double reach = std::min(M_PI, cone + 1.1 * rho + 0.002);
+        const float thresh = (float)std::cos(reach) - 4e-6f;
+        for (int rc = 0; rc < n_ra; ++rc) {
+            const double ra = (rc + 0.5) * w;
+            const float cx = (float)(std::cos(dm) * std::cos(ra)), cy = (float)(std::cos(dm) * std::sin(ra)),
+                        cz = (float)std::sin(dm);
+            for (int i = 0; i < S; ++i) dots[i] = cx * sx[i] + cy * sy[i] + cz * sz[i];
+            const size_t start = list.size();
+            for (int i = 0; i < S; ++i) if (dots[i] >= thresh) list.push_back((uint16_t)order[i]);
+            while ((list.size() - start) % 8) list.push_back((uint16_t)0xffff);
+            if (list.size() > 0xfffffff0ull) return fail(STMPM_E_ARG, "candidate lists exceed 2^32 entries: field of view too wide");
+            off[bt[b].x + rc + 1] = (uint32_t)list.size();
+        }
+    }
+    if (list.empty()) list.resize(8, (uint16_t)0xffff);
+    cudaFree(h->lk_band_tab); cudaFree(h->lk_off); cudaFree(h->lk_list);
+    h->lk_band_tab = nullptr; h->lk_off = nullptr; h->lk_list = nullptr;
+    CK(cudaMalloc(&h->lk_band_tab, sizeof(int2) * nb));
+    CK(cudaMalloc(&h->lk_off, sizeof(uint32_t) * off.size()));
+    CK(cudaMalloc(&h->lk_list, sizeof(uint16_t) * list.size()));
+    CK(cudaMemcpy(h->lk_band_tab, bt.data(), sizeof(int2) * nb, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->lk_off, off.data(), sizeof(uint32_t) * off.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->lk_list, list.data(), sizeof(uint16_t) * list.size(), cudaMemcpyHostToDevice));
+    h->lk_bands = nb;
+    h->lk_cone = (float)cone;
+    h->lk_entries = (long long)list.size();
+    return 0;
+}
+
 extern "C" const char* stmpm_last_error(void) { return g_err.c_str(); }
 extern "C" int stmpm_version(void) { return 100; }
 
@@ -334,6 +489,10 @@ extern "C" int stmpm_create(stmpm_t** out, int device) {
     h->device = device;
     CK(cudaGetDeviceProperties(&h->prop, device));
     for (int i = 0; i < stmpm_handle::NBUF; ++i) CK(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
+    MathTables mt;
+    stmpm_host_tables(&mt);
+    CK(cudaMalloc(&h->tables, sizeof(MathTables)));
+    CK(cudaMemcpy(h->tables, &mt, sizeof(MathTables), cudaMemcpyHostToDevice));
     *out = h;
     return 0;
 }
@@ -351,6 +510,7 @@ extern "C" int stmpm_destroy(stmpm_t* h) {
     cudaSetDevice(h->device);
     cudaFree(h->cat32); cudaFree(h->cat64); cudaFree(h->cell_start); cudaFree(h->band_tab); cudaFree(h->dists);
     cudaFree(h->stage_stats); cudaFree(h->counters);
+    cudaFree(h->lk_band_tab); cudaFree(h->lk_off); cudaFree(h->lk_list); cudaFree(h->tables);
     free_stage(h);
     for (int i = 0; i < stmpm_handle::NBUF; ++i) if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
     delete h;
@@ -408,8 +568,11 @@ extern "C" int stmpm_set_catalog(stmpm_t* h, const double* xyz, const float* mag
     CK(cudaMemcpy(h->cell_start, cs.data(), sizeof(uint16_t) * n_pad, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->band_tab, bt.data(), sizeof(int2) * n_bands, cudaMemcpyHostToDevice));
     h->n_stars = n_stars; h->n_cells_pad = n_pad; h->n_bands = n_bands;
+    h->h_xyzf.resize((size_t)3 * n_stars);
+    h->h_mag.assign(mag, mag + n_stars);
+    for (int i = 0; i < 3 * n_stars; ++i) h->h_xyzf[i] = (float)xyz[i];
     h->have_catalog = true;
-    return 0;
+    return rebuild_lists(h);
 }
 
 extern "C" int stmpm_set_sensor(stmpm_t* h, const stmpm_sensor_cfg* cfg) {
@@ -418,10 +581,11 @@ extern "C" int stmpm_set_sensor(stmpm_t* h, const stmpm_sensor_cfg* cfg) {
         return fail(STMPM_E_ARG, "stmpm_set_sensor: f_ideal, half_u, half_v must be > 0 and n_min >= 2");
     if (cfg->hist_log2_sub < 4 || cfg->hist_log2_sub > 8)
         return fail(STMPM_E_ARG, "stmpm_set_sensor: hist_log2_sub must be in [4, 8]");
+    if (!(cfg->scan_pad_px >= 0)) return fail(STMPM_E_ARG, "stmpm_set_sensor: scan_pad_px must be >= 0 (0 = default 32)");
     h->cfg = *cfg;
     h->n_bins = STMPM_HIST_OCTAVES << cfg->hist_log2_sub;
     h->have_sensor = true;
-    return 0;
+    return rebuild_lists(h);
 }
 
 extern "C" int stmpm_stats_len(int32_t hist_log2_sub, int64_t* n) {
@@ -478,7 +642,7 @@ extern "C" int stmpm_stats_finalize(int32_t hist_log2_sub, const double* s, stmp
 // ------------------------------------------------------------------------------------------------ launch helper
 template <int MODE, int PREC, int INSTR = 0>
 static int launch_trials(stmpm_handle* h, KArgs& a, cudaStream_t st) {
-    const SmemLayout L = smem_layout(a.n_stars, a.n_cells_pad, a.n_bands, a.n_bins + 2);
+    const SmemLayout L = smem_layout(a.n_stars, a.n_cells_pad, a.n_bands, a.lk_bands, a.n_bins + 2);
     if (L.total > (size_t)h->prop.sharedMemPerBlockOptin)
         return fail(STMPM_E_ARG, "catalog too large for shared-memory staging (" + std::to_string(L.total) + " B)");
     auto kern = trials_kernel<MODE, PREC, INSTR>;
@@ -515,6 +679,8 @@ static int fill_common(stmpm_handle* h, KArgs& a, int precision) {
     a.cat32 = h->cat32; a.cat64 = h->cat64; a.cell_start = h->cell_start; a.band_tab = h->band_tab;
     a.n_stars = h->n_stars; a.n_cells_pad = h->n_cells_pad; a.n_bands = h->n_bands;
     a.inv_band_h = (float)((double)h->n_bands / M_PI);
+    a.lk_band_tab = h->lk_band_tab; a.lk_off = h->lk_off; a.lk_list = h->lk_list; a.lk_bands = h->lk_bands;
+    a.lk_inv_band_h = (float)((double)h->lk_bands / M_PI); a.lk_cone = h->lk_cone; a.tables = h->tables;
     a.f_ideal = h->cfg.f_ideal; a.half_u = h->cfg.half_u; a.half_v = h->cfg.half_v; a.n_min = h->cfg.n_min;
     a.hist_shift = 52 - h->cfg.hist_log2_sub; a.n_bins = h->n_bins;
     a.stats_len = STMPM_STATS_HEAD + h->n_bins;
@@ -734,6 +900,14 @@ extern "C" int stmpm_work_counters(stmpm_t* h, int64_t n, uint64_t seed, int64_t
     CK(cudaMemcpyAsync(c, h->counters, sizeof(c), cudaMemcpyDeviceToHost, h->streams[0]));
     CK(cudaStreamSynchronize(h->streams[0]));
     for (int i = 0; i < 4; ++i) per_trial4[i] = (double)c[i] / (double)n;
+    return 0;
+}
+
+extern "C" int stmpm_debug_box_muller(const uint32_t* wa, const uint32_t* wb, int64_t n, double* z1, double* z2) {
+    if (!wa || !wb || !z1 || !z2 || n < 0) return fail(STMPM_E_ARG, "stmpm_debug_box_muller: bad arguments");
+    MathTables mt;
+    stmpm_host_tables(&mt);
+    for (int64_t i = 0; i < n; ++i) box_muller_tab(&mt, wa[i], wb[i], z1[i], z2[i]);
     return 0;
 }
 

@@ -2,18 +2,25 @@
 //
 // Replaces the per-row body of Simulation.run_sim + quest_objective (called at /root/reference/monte_carlo.py:52 and
 // sensitivity.py:77; bodies absent from the mount).  One trial per thread:
-//   setup (fp64)  ->  sky-grid scan with an fp32 conservative pre-filter out of shared memory (phase A)
-//                 ->  exact per-star projection + Philox centroid noise + detection + B accumulation (phase B)
+//   setup (fp64)  ->  phase A: candidate scan with an fp32 conservative pre-filter out of shared memory
+//                 ->  phase B: exact per-star projection + Philox centroid noise + detection + B accumulation
 //                 ->  QUEST Newton solve in the body frame + error angle (fp64).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+
+#if defined(__CUDACC__)
+#define STMPM_HD __host__ __device__ __forceinline__
+#else
+#define STMPM_HD inline
+#endif
 
 namespace stmpm {
 
 constexpr int TPB = 512;          // threads per CTA (1 CTA / SM: the fp32 catalog lives in shared memory)
 constexpr int LIST_CAP = 32;      // per-thread candidate list length (phase A -> phase B hand-off)
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u, PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
+constexpr uint32_t PHILOX2_M = 0xD256D193u;
 constexpr uint32_t TAG_STAR = 0x53544152u, TAG_PARA = 0x50415241u;
 constexpr double RAD2ARCSEC = 206264.80624709636;
 constexpr double DEG2RAD = 0.017453292519943295;
@@ -29,13 +36,22 @@ struct TrialParams {              // one DataFrame row (MODEL.md §1)
     double ra, dec, roll, f, ex, ey, ez, phi, theta, psi, devx, devy, maxmag;
 };
 
+// ------------------------------------------------------------------------------------------------ Philox (MODEL.md §5)
+STMPM_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
 // Philox4x32-10 (Salmon et al., SC'11).  Ten rounds, key bumped between rounds.
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                              uint32_t k1, uint32_t& o0, uint32_t& o1, uint32_t& o2, uint32_t& o3) {
+STMPM_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                            uint32_t& o0, uint32_t& o1, uint32_t& o2, uint32_t& o3) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(PHILOX_M0, c0), lo0 = PHILOX_M0 * c0;
-        const uint32_t hi1 = __umulhi(PHILOX_M1, c2), lo1 = PHILOX_M1 * c2;
+        const uint32_t hi0 = mulhi32(PHILOX_M0, c0), lo0 = PHILOX_M0 * c0;
+        const uint32_t hi1 = mulhi32(PHILOX_M1, c2), lo1 = PHILOX_M1 * c2;
         c0 = hi1 ^ c1 ^ k0;
         c1 = lo1;
         c2 = hi0 ^ c3 ^ k1;
@@ -46,22 +62,115 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     o0 = c0; o1 = c1; o2 = c2; o3 = c3;
 }
 
-__device__ __forceinline__ double u01(uint32_t w) { return ((double)w + 0.5) * TWO_M32; }
-
-// MODEL.md §5: R = sqrt(-2 ln u1); z1 = R cos(2 pi u2); z2 = R sin(2 pi u2)
-__device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, double& z1, double& z2) {
-    const double r = sqrt(-2.0 * log(u01(wa)));
-    double s, c;
-    sincospi(2.0 * u01(wb), &s, &c);
-    z1 = r * c;
-    z2 = r * s;
+// Philox2x32-10: one multiply per round — the per-star generator of the hot loop.
+STMPM_HD void philox2x32_10(uint32_t c0, uint32_t c1, uint32_t k, uint32_t& o0, uint32_t& o1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi = mulhi32(PHILOX2_M, c0), lo = PHILOX2_M * c0;
+        c0 = hi ^ k ^ c1;
+        c1 = lo;
+        k += PHILOX_W0;
+    }
+    o0 = c0; o1 = c1;
 }
+
+// per-trial key pair of the star-noise streams
+STMPM_HD void star_key(uint32_t t_lo, uint32_t t_hi, uint32_t k0, uint32_t k1, uint32_t& ka, uint32_t& kb) {
+    uint32_t x2, x3;
+    philox4x32_10(t_lo, t_hi, 0u, TAG_STAR, k0, k1, ka, kb, x2, x3);
+}
+
+STMPM_HD double u01(uint32_t w) { return ((double)w + 0.5) * TWO_M32; }
+
+// ------------------------------------------------------------------------------------------------ table-based Box-Muller
+// MODEL.md §5: R = sqrt(-2 ln u1), z1 = R cos(2 pi u2), z2 = R sin(2 pi u2), u = (w + 0.5) 2^-32.
+// Evaluated to ~1e-15 absolute with integer argument reduction (no int->double conversions: those go to the XU pipe)
+// and small tables instead of libm's long polynomials: the star loop is FP64-pipe bound.
+//   ln:  2w+1 = m 2^p, m in [1,2); j = top 7 mantissa bits; r = m / c_j - 1, |r| <= 2^-8; ln m = ln c_j + log1p(r)
+//   sin/cos: quadrant = top 2 bits of w; 64 table intervals per quadrant; |d| <= pi/256 remainder by Taylor.
+struct MathTables {
+    double log_inv_c[128], log_ln_c[128];   // c_j = 1 + (j + 0.5) / 128
+    double k_ln2[34];                       // k * ln 2
+    double sc_sin[64], sc_cos[64];          // sin / cos of (pi/2) (j + 0.5) / 64
+};
+
+STMPM_HD double bits_to_double(unsigned long long b) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)b);
+#else
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+#endif
+}
+STMPM_HD int clz64(unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+    return __clzll((long long)v);
+#else
+    return __builtin_clzll(v);
+#endif
+}
+STMPM_HD double fast_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
+STMPM_HD void box_muller_tab(const MathTables* __restrict__ T, uint32_t wa, uint32_t wb, double& z1, double& z2) {
+    // ---- L = -2 ln u1,  u1 = (2 wa + 1) 2^-33
+    const unsigned long long v = 2ull * wa + 1ull;            // 33-bit odd integer
+    const int lz = clz64(v);                                  // top bit at p = 63 - lz, u1 = m 2^(p - 33)
+    const unsigned long long frac = ((v << lz) << 1) >> 12;   // 52 mantissa bits of m (lz + 1 can be 64)
+    const double m = bits_to_double(0x3FF0000000000000ull | frac);
+    const int j = (int)(frac >> 45);
+    const double r = fma(m, T->log_inv_c[j], -1.0);
+    double p = fma(r, -1.0 / 6.0, 0.2);
+    p = fma(r, p, -0.25);
+    p = fma(r, p, 1.0 / 3.0);
+    p = fma(r, p, -0.5);
+    p = fma(r * r, p, r);                                     // log1p(r), |r| <= 2^-8: truncation < 2e-18
+    const double ln_u = (T->log_ln_c[j] + p) - T->k_ln2[lz - 30];   // k = 33 - p = lz - 30
+    const double L = -2.0 * ln_u;
+    const double R = L * fast_rsqrt(L);
+    // ---- angle 2 pi u2 = (pi/2) (q + (64-interval j2 centre) ) + d
+    const uint32_t q = wb >> 30;
+    const uint32_t w30 = wb & 0x3FFFFFFFu;
+    const int j2 = (int)(w30 >> 24);
+    const uint32_t rem = w30 & 0xFFFFFFu;
+    // d = (pi/128) ((rem + 0.5) / 2^24 - 0.5), via the 2^52 magic number (exact, no conversion instruction)
+    const double t = bits_to_double(0x4330000000000000ull | (unsigned long long)(2u * rem + 1u));
+    const double d = (t - 4503599644147712.0) * 7.314590396335798e-10;   // (2^52 + 2^24);  pi / 128 / 2^25
+    const double d2 = d * d;
+    const double sd = fma(d * d2, fma(d2, 1.0 / 120.0, -1.0 / 6.0), d);
+    const double cd = fma(d2, fma(d2, fma(d2, -1.0 / 720.0, 1.0 / 24.0), -0.5), 1.0);
+    const double S = T->sc_sin[j2], C = T->sc_cos[j2];
+    const double sn = fma(S, cd, C * sd);
+    const double cs = fma(C, cd, -S * sd);
+    // quadrant rotation: (cos, sin) -> q=0 (cs, sn); 1 (-sn, cs); 2 (-cs, -sn); 3 (sn, -cs)
+    const double c0 = (q & 1u) ? sn : cs;
+    const double s0 = (q & 1u) ? cs : sn;
+    const double cq = (q == 1u || q == 2u) ? -c0 : c0;
+    const double sq = (q >= 2u) ? -s0 : s0;
+    z1 = R * cq;
+    z2 = R * sq;
+}
+
+#if defined(__CUDACC__)
 __device__ __forceinline__ void box_muller_f(uint32_t wa, uint32_t wb, float& z1, float& z2) {
     // u in (0,1): (w + 0.5) * 2^-32 rounded to float can reach 1.0f -> clamp below 1 so that R stays finite and real
     const float u1 = fminf(((float)wa + 0.5f) * 2.3283064365386963e-10f, 0.99999994f);
     const float r = sqrtf(-2.0f * logf(u1));
     float s, c;
     sincospif(2.0f * (((float)wb + 0.5f) * 2.3283064365386963e-10f), &s, &c);
+    z1 = r * c;
+    z2 = r * s;
+}
+__device__ __forceinline__ void box_muller_lib(uint32_t wa, uint32_t wb, double& z1, double& z2) {   // parameter draws
+    const double r = sqrt(-2.0 * log(u01(wa)));
+    double s, c;
+    sincospi(2.0 * u01(wb), &s, &c);
     z1 = r * c;
     z2 = r * s;
 }
@@ -76,6 +185,11 @@ struct TrialCtx {
     float NIf[3], EUf[3], EVf[3], np0f, cuf, cvf, limu, limv, magf;
     float ra0, dec0, cone, dalpha;   // scan geometry (fp32, conservative); dalpha < 0 => full circle
 };
+
+__device__ __forceinline__ float opaque(float x) {   // stop ptxas re-deriving the fp32 copy from the fp64 value at
+    asm volatile("" : "+f"(x));                       // every use (F2F conversions run on the 16-lane XU pipe)
+    return x;
+}
 
 __device__ __forceinline__ void trial_setup(const TrialParams& p, double half_u, double half_v, TrialCtx& c) {
     double sa, ca, sd, cd, sr, cr;
@@ -103,21 +217,21 @@ __device__ __forceinline__ void trial_setup(const TrialParams& p, double half_u,
         c.NI[i] = c.C[3 * i] * nn[0] + c.C[3 * i + 1] * nn[1] + c.C[3 * i + 2] * nn[2];
         c.EU[i] = c.C[3 * i] * eu[0] + c.C[3 * i + 1] * eu[1] + c.C[3 * i + 2] * eu[2];
         c.EV[i] = c.C[3 * i] * ev[0] + c.C[3 * i + 1] * ev[1] + c.C[3 * i + 2] * ev[2];
-        c.NIf[i] = (float)c.NI[i];
-        c.EUf[i] = (float)c.EU[i];
-        c.EVf[i] = (float)c.EV[i];
+        c.NIf[i] = opaque((float)c.NI[i]);
+        c.EUf[i] = opaque((float)c.EU[i]);
+        c.EVf[i] = opaque((float)c.EV[i]);
     }
     c.sx = fabs(p.devx);
     c.sy = fabs(p.devy);
-    c.np0f = (float)c.np0;
-    c.cuf = (float)c.cu;
-    c.cvf = (float)c.cv;
+    c.np0f = opaque((float)c.np0);
+    c.cuf = opaque((float)c.cu);
+    c.cvf = opaque((float)c.cv);
     // conservative pre-filter window: Box-Muller with 32-bit u1 has |z| <= sqrt(-2 ln 2^-33) = 6.77; fp32 slack
     const float ff = (float)fabs(p.f);
     const float noise = 6.8f * fmaxf((float)c.sx, (float)c.sy) + 0.02f + 4e-6f * ff;
-    c.limu = (float)half_u + noise;
-    c.limv = (float)half_v + noise;
-    c.magf = __double2float_rd(p.maxmag);   // (double)mag <= maxmag  <=>  mag <= round-down-to-float(maxmag), exactly
+    c.limu = opaque((float)half_u + noise);
+    c.limv = opaque((float)half_v + noise);
+    c.magf = opaque(__double2float_rd(p.maxmag));   // (double)mag <= maxmag  <=>  mag <= round-down-to-float(maxmag)
     // scan cone about the boresight (= third column of C): every point of the (tilted, shifted, noise-padded) array
     // lies within atan(reach / depth) of +z  (MODEL.md §8: acceleration only)
     const float reach = 1.41421357f * (fmaxf((float)half_u, (float)half_v) + noise)
@@ -132,29 +246,27 @@ __device__ __forceinline__ void trial_setup(const TrialParams& p, double half_u,
     else c.dalpha = asinf(fminf(sinf(c.cone) / cosf(c.dec0), 1.0f)) + 0.002f;
 }
 
-// fp32 conservative pre-filter on one shared-memory catalog entry (x, y, z, mag)
-__device__ __forceinline__ bool prefilter(const TrialCtx& c, const float4 s) {
-    if (!(s.w <= c.magf)) return false;
+// fp32 conservative geometric pre-filter on one shared-memory catalog entry (x, y, z, mag); magnitude tested by caller
+__device__ __forceinline__ bool prefilter_geom(const TrialCtx& c, const float4 s) {
     const float dn = c.NIf[0] * s.x + c.NIf[1] * s.y + c.NIf[2] * s.z;
-    if (!(dn > 0.02f)) return false;
     const float rl = __fdividef(c.np0f, dn);
     const float u = fmaf(rl, c.EUf[0] * s.x + c.EUf[1] * s.y + c.EUf[2] * s.z, -c.cuf);
     const float v = fmaf(rl, c.EVf[0] * s.x + c.EVf[1] * s.y + c.EVf[2] * s.z, -c.cvf);
-    return fabsf(u) <= c.limu && fabsf(v) <= c.limv;
+    return dn > 0.02f && fabsf(u) <= c.limu && fabsf(v) <= c.limv;
 }
 
 // Exact (fp64) star evaluation: MODEL.md §2-§4. Returns detected?; on detection adds b s^T into B.
-__device__ __forceinline__ bool star_exact(const TrialCtx& c, const StarRec& s, uint32_t t_lo, uint32_t t_hi,
-                                           uint32_t k0, uint32_t k1, double f_ideal, double half_u, double half_v,
+__device__ __forceinline__ bool star_exact(const TrialCtx& c, const MathTables* __restrict__ T, const StarRec& s,
+                                           uint32_t ka, uint32_t kb, double f_ideal, double half_u, double half_v,
                                            double* __restrict__ B) {
     const double dn = c.NI[0] * s.x + c.NI[1] * s.y + c.NI[2] * s.z;
     const double du = c.EU[0] * s.x + c.EU[1] * s.y + c.EU[2] * s.z;
     const double dv = c.EV[0] * s.x + c.EV[1] * s.y + c.EV[2] * s.z;
     const double lam = c.np0 / dn;
-    uint32_t x0, x1, x2, x3;
-    philox4x32_10(t_lo, t_hi, s.star_id, TAG_STAR, k0, k1, x0, x1, x2, x3);
+    uint32_t x0, x1;
+    philox2x32_10(s.star_id, kb, ka, x0, x1);
     double z1, z2;
-    box_muller(x0, x1, z1, z2);
+    box_muller_tab(T, x0, x1, z1, z2);
     const double um = fma(c.sx, z1, fma(lam, du, -c.cu));
     const double vm = fma(c.sy, z2, fma(lam, dv, -c.cv));
     const bool det = (dn > 0.0) && (fabs(um) <= half_u) && (fabs(vm) <= half_v);
@@ -173,16 +285,16 @@ __device__ __forceinline__ bool star_exact(const TrialCtx& c, const StarRec& s, 
 // centroid lies inside a guard band around the array edge, so detection counts stay bit-exact with the fp64 oracle;
 // (b) B is accumulated in fp64 against the fp64 reference vector — roll about the boresight is ~1/sin(FOV/2) less
 // observable than pointing, and fp32 partial sums of B (ulp ~1e-6 at |B| ~ 16) would cost ~1e-6 rad of roll.
-__device__ __forceinline__ bool star_f32(const TrialCtx& c, const StarRec& s, uint32_t t_lo, uint32_t t_hi, uint32_t k0,
-                                         uint32_t k1, double f_ideal, double half_u, double half_v,
+__device__ __forceinline__ bool star_f32(const TrialCtx& c, const MathTables* __restrict__ T, const StarRec& s,
+                                         uint32_t ka, uint32_t kb, double f_ideal, double half_u, double half_v,
                                          double* __restrict__ B) {
     const float sx = (float)s.x, sy = (float)s.y, sz = (float)s.z;
     const float dn = c.NIf[0] * sx + c.NIf[1] * sy + c.NIf[2] * sz;
     const float du = c.EUf[0] * sx + c.EUf[1] * sy + c.EUf[2] * sz;
     const float dv = c.EVf[0] * sx + c.EVf[1] * sy + c.EVf[2] * sz;
     const float lam = c.np0f / dn;
-    uint32_t x0, x1, x2, x3;
-    philox4x32_10(t_lo, t_hi, s.star_id, TAG_STAR, k0, k1, x0, x1, x2, x3);
+    uint32_t x0, x1;
+    philox2x32_10(s.star_id, kb, ka, x0, x1);
     float z1, z2;
     box_muller_f(x0, x1, z1, z2);
     const float um = fmaf((float)c.sx, z1, fmaf(lam, du, -c.cuf));
@@ -190,7 +302,7 @@ __device__ __forceinline__ bool star_f32(const TrialCtx& c, const StarRec& s, ui
     const float hu = (float)half_u, hv = (float)half_v;
     const float guard = 0.05f + 1e-5f * fabsf(c.np0f) + 1e-4f * ((float)c.sx + (float)c.sy);
     if (!(dn > 0.02f) || fabsf(fabsf(um) - hu) <= guard || fabsf(fabsf(vm) - hv) <= guard)
-        return star_exact(c, s, t_lo, t_hi, k0, k1, f_ideal, half_u, half_v, B);   // rare: exact decision + exact b
+        return star_exact(c, T, s, ka, kb, f_ideal, half_u, half_v, B);   // rare: exact decision + exact b
     const bool det = (fabsf(um) <= hu) && (fabsf(vm) <= hv);
     if (det) {
         const float fi = (float)f_ideal;
@@ -263,7 +375,7 @@ __device__ __forceinline__ void sample_params(const DistDev& d, uint32_t t_lo, u
     p.roll = -PI + 2.0 * PI * u01(w[2]);
     double z[12];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) box_muller(w[4 + 2 * k], w[5 + 2 * k], z[2 * k], z[2 * k + 1]);
+    for (int k = 0; k < 6; ++k) box_muller_lib(w[4 + 2 * k], w[5 + 2 * k], z[2 * k], z[2 * k + 1]);
     const double F = d.mean[0] + d.sigma[0] * z[0];
     p.ex = d.mean[1] + d.sigma[1] * z[1];
     p.ey = d.mean[2] + d.sigma[2] * z[2];
@@ -277,5 +389,6 @@ __device__ __forceinline__ void sample_params(const DistDev& d, uint32_t t_lo, u
     const double dtemp = d.mean[10] + d.sigma[10] * z[10];
     p.f = F * (1.0 + dtemp * d.thermal_coef);   // sensitivity.py:115-117
 }
+#endif  // __CUDACC__
 
 }  // namespace stmpm

@@ -51,14 +51,14 @@ class TrialEngine:
 
     def __init__(self, device: int = 0, catalog=None, f_ideal: float = 3500.0, half_u: float = SENSOR_WIDTH / 2,
                  half_v: float = SENSOR_HEIGHT / 2, n_min: int = N_MIN, hist_log2_sub: int = 8,
-                 cell_deg: float = 3.0):
+                 cell_deg: float = 3.0, scan_pad_px: float = 0.0):
         self._lib = _abi.load()
         self._h = C.c_void_p()
         _abi.check(self._lib.stmpm_create(C.byref(self._h), int(device)))
         self.device = int(device)
         xyz, mag = catalog if catalog is not None else load_catalog()
         self.set_catalog(build_sky_grid(xyz, mag, cell_deg))
-        self.set_sensor(f_ideal, half_u, half_v, n_min, hist_log2_sub)
+        self.set_sensor(f_ideal, half_u, half_v, n_min, hist_log2_sub, scan_pad_px)
 
     # ---------------------------------------------------------------- configuration
     def set_catalog(self, grid: SkyGrid) -> None:
@@ -72,8 +72,9 @@ class TrialEngine:
                                                _ptr(n_ra), _ptr(cs)))
 
     def set_sensor(self, f_ideal: float, half_u: float = SENSOR_WIDTH / 2, half_v: float = SENSOR_HEIGHT / 2,
-                   n_min: int = N_MIN, hist_log2_sub: int = 8) -> None:
-        cfg = _abi.SensorCfg(float(f_ideal), float(half_u), float(half_v), int(n_min), int(hist_log2_sub))
+                   n_min: int = N_MIN, hist_log2_sub: int = 8, scan_pad_px: float = 0.0) -> None:
+        cfg = _abi.SensorCfg(float(f_ideal), float(half_u), float(half_v), int(n_min), int(hist_log2_sub),
+                             float(scan_pad_px))
         _abi.check(self._lib.stmpm_set_sensor(self._h, C.byref(cfg)))
         self.f_ideal = float(f_ideal)
         self.hist_log2_sub = int(hist_log2_sub)
@@ -192,6 +193,15 @@ class TrialEngine:
     # ---------------------------------------------------------------- statistics
     def summarize(self, stats: np.ndarray) -> dict:
         return summarize(stats, self.hist_log2_sub)
+
+
+def debug_box_muller(wa: np.ndarray, wb: np.ndarray):
+    """Host build of the kernels' table-based Box-Muller (diagnostic; no GPU needed)."""
+    wa = np.ascontiguousarray(wa, dtype=np.uint32)
+    wb = np.ascontiguousarray(wb, dtype=np.uint32)
+    z1, z2 = np.empty(wa.size), np.empty(wa.size)
+    _abi.check(_abi.load().stmpm_debug_box_muller(_ptr(wa), _ptr(wb), wa.size, _ptr(z1), _ptr(z2)))
+    return z1, z2
 
 
 def stats_len(hist_log2_sub: int = 8) -> int:

@@ -53,3 +53,20 @@ def test_header_is_plain_c(tmp_path):
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(c), "-o",
                     str(tmp_path / "t")], check=True)
     assert subprocess.run([str(tmp_path / "t")]).returncode == 0
+
+
+def test_table_box_muller_matches_libm(lib_built):
+    """The star loop's table-based Box-Muller (compiled for the host from the kernels' own source) vs numpy/libm."""
+    import numpy as np
+    from oracle import philox
+    from startrackermpm_b200 import engine
+    rng = np.random.default_rng(0)
+    wa = rng.integers(0, 2**32, 1_000_000, dtype=np.uint64).astype(np.uint32)
+    wb = rng.integers(0, 2**32, 1_000_000, dtype=np.uint64).astype(np.uint32)
+    edge = np.array([0, 1, 2, 3, 2**31 - 1, 2**31, 2**31 + 1, 2**32 - 1, 2**30 - 1, 2**30, 2**30 + 1, 3 * 2**30 - 1,
+                     3 * 2**30, 2**24 - 1, 2**24, 2**24 + 1], dtype=np.uint32)
+    wa[:16], wb[:16] = edge, edge[::-1]
+    wa[16:32], wb[16:32] = edge, edge
+    z1, z2 = engine.debug_box_muller(wa, wb)
+    r1, r2 = philox.box_muller(wa, wb)
+    assert np.abs(z1 - r1).max() < 1e-13 and np.abs(z2 - r2).max() < 1e-13

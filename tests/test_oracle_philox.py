@@ -20,6 +20,26 @@ def test_known_answer_vectors():
         assert tuple(int(g) for g in got) == want
 
 
+KAT2 = [((0x00000000, 0x00000000), 0x00000000, (0xff1dae59, 0x6cd10df2)),
+        ((0xffffffff, 0xffffffff), 0xffffffff, (0x2c3f628b, 0xab4fd7ad)),
+        ((0x243f6a88, 0x85a308d3), 0x13198a2e, (0xdd7ce038, 0xf62a4c12))]
+
+
+def test_philox2x32_known_answer_vectors():
+    for ctr, key, want in KAT2:
+        got = philox.philox2x32_10(*ctr, key)
+        assert tuple(int(g) for g in got) == want
+
+
+def test_star_words_composition():
+    tr = np.array([0, 5, (7 << 32) | 9], dtype=np.uint64)
+    x0, x1 = philox.star_words((3 << 32) | 11, tr, np.array([1, 2, 3]))
+    for i in range(3):
+        ka, kb, _, _ = philox.philox4x32_10(int(tr[i]) & 0xffffffff, int(tr[i]) >> 32, 0, philox.TAG_STAR, 11, 3)
+        a, b = philox.philox2x32_10(i + 1, int(kb), int(ka))
+        assert (int(x0[i]), int(x1[i])) == (int(a), int(b))
+
+
 def test_vectorised_matches_scalar():
     rng = np.random.default_rng(0)
     c = rng.integers(0, 2**32, size=(4, 64), dtype=np.uint64)
@@ -32,7 +52,7 @@ def test_vectorised_matches_scalar():
 def test_u01_open_interval_and_box_muller_moments():
     assert 0.0 < philox.u01(0) < philox.u01(2**32 - 1) < 1.0
     idx = np.arange(200_000, dtype=np.uint64)
-    x0, x1, _, _ = philox.philox4x32_10(idx, 0, 7, philox.TAG_STAR, 11, 22)
+    x0, x1 = philox.star_words(11 | (22 << 32), idx, 7)
     z1, z2 = philox.box_muller(x0, x1)
     z = np.concatenate([z1, z2])
     assert abs(z.mean()) < 4 / np.sqrt(z.size)
