@@ -47,9 +47,9 @@ struct KArgs {
 };
 
 struct SmemLayout {
-    size_t cat32, cell_start, band_tab, lk_band_tab, tables, hist, list, red, total;
+    size_t cat32, cell_start, band_tab, lk_band_tab, tables, list, red, total;
 };
-static SmemLayout smem_layout(int n_stars, int n_cells_pad, int n_bands, int lk_bands, int n_bins) {
+static SmemLayout smem_layout(int n_stars, int n_cells_pad, int n_bands, int lk_bands) {
     SmemLayout L;
     size_t o = 0;
     L.cat32 = o;      o += (size_t)n_stars * 16;
@@ -57,7 +57,6 @@ static SmemLayout smem_layout(int n_stars, int n_cells_pad, int n_bands, int lk_
     L.band_tab = o;   o += (((size_t)n_bands * 8) + 15) / 16 * 16;
     L.lk_band_tab = o; o += (((size_t)lk_bands * 8) + 15) / 16 * 16;
     L.tables = o;     o += (sizeof(MathTables) + 15) / 16 * 16;
-    L.hist = o;       o += (size_t)n_bins * 4;
     L.list = o;       o += (size_t)LIST_CAP * TPB * 2;
     L.red = o;        o += (size_t)(TPB / 32) * 8 * 8;
     L.total = o;
@@ -75,7 +74,6 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
     int2* s_band = reinterpret_cast<int2*>(smem + L.band_tab);
     int2* s_lkband = reinterpret_cast<int2*>(smem + L.lk_band_tab);
     const MathTables* s_tab = reinterpret_cast<const MathTables*>(smem + L.tables);
-    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem + L.hist);
     uint16_t* s_list = reinterpret_cast<uint16_t*>(smem + L.list) + threadIdx.x;   // entry j at s_list[j * TPB]
     double* s_red = reinterpret_cast<double*>(smem + L.red);
 
@@ -92,7 +90,6 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
             double* stb = reinterpret_cast<double*>(smem + L.tables);
             for (int i = threadIdx.x; i < (int)(sizeof(MathTables) / 8); i += TPB) stb[i] = __ldg(gt + i);
         }
-        for (int i = threadIdx.x; i < a.n_bins + 2; i += TPB) s_hist[i] = 0u;
     }
     __syncthreads();
 
@@ -149,6 +146,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
             const bool use_list = c.cone <= a.lk_cone;
             const uint16_t* lp = a.lk_list;
             int lk = 0, lk_len = 0;
+            uint4 pk_next = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
             if (use_list) {
                 const int lb = min(a.lk_bands - 1, max(0, (int)floorf((c.dec0 + 1.57079633f) * a.lk_inv_band_h)));
                 const int2 bt = s_lkband[lb];
@@ -156,6 +154,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
                 const uint32_t o0 = __ldg(a.lk_off + bt.x + rc), o1 = __ldg(a.lk_off + bt.x + rc + 1);
                 lp += o0;
                 lk_len = (int)(o1 - o0);
+                if (lk_len > 0) pk_next = __ldg(reinterpret_cast<const uint4*>(lp));
             }
             int b = max(0, (int)floorf((c.dec0 - c.cone + 1.57079633f) * a.inv_band_h));
             const int b_hi = min(a.n_bands - 1, (int)floorf((c.dec0 + c.cone + 1.57079633f) * a.inv_band_h));
@@ -170,8 +169,9 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
                     // the list is sorted by magnitude, so the first star fainter than MAX_MAGNITUDE ends the scan
                     while (scanning && cnt <= LIST_CAP - 8) {
                         if (lk >= lk_len) { scanning = false; break; }
-                        const uint4 pk = __ldg(reinterpret_cast<const uint4*>(lp + lk));
+                        const uint4 pk = pk_next;
                         lk += 8;
+                        if (lk < lk_len) pk_next = __ldg(reinterpret_cast<const uint4*>(lp + lk));   // prefetch
                         const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
@@ -218,14 +218,19 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
                 }
                 __syncwarp();
                 // ---- phase B: exact evaluation of the listed stars (lanes in lock-step)
+                // (software-pipelined: the 32-byte record of star j+1 is in flight while star j is evaluated)
+                double2 r_lo = make_double2(0.0, 0.0), r_hi = make_double2(0.0, 0.0);
+                if (cnt > 0) {
+                    const double2* g = reinterpret_cast<const double2*>(a.cat64 + s_list[0]);
+                    r_lo = __ldg(g); r_hi = __ldg(g + 1);
+                }
                 for (int j = 0; j < cnt; ++j) {
-                    const int idx = s_list[j * TPB];
                     StarRec s;
-                    {
-                        const double2* g = reinterpret_cast<const double2*>(a.cat64 + idx);
-                        const double2 lo = __ldg(g), hi = __ldg(g + 1);
-                        s.x = lo.x; s.y = lo.y; s.z = hi.x;
-                        s.star_id = (uint32_t)(__double_as_longlong(hi.y) & 0xffffffffll);
+                    s.x = r_lo.x; s.y = r_lo.y; s.z = r_hi.x;
+                    s.star_id = (uint32_t)(__double_as_longlong(r_hi.y) & 0xffffffffll);
+                    if (j + 1 < cnt) {
+                        const double2* g = reinterpret_cast<const double2*>(a.cat64 + s_list[(j + 1) * TPB]);
+                        r_lo = __ldg(g); r_hi = __ldg(g + 1);
                     }
                     bool det;
                     if (PREC == 64) det = star_exact(c, s_tab, s, ka, kb, a.f_ideal, a.half_u, a.half_v, B);
@@ -251,10 +256,11 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
                         acc_max = fmax(acc_max, err);
                         const long long e = (__double_as_longlong(err) >> a.hist_shift)
                                             - ((long long)(1023 + STMPM_HIST_MIN_EXP) << (52 - a.hist_shift));
-                        int bin = e < 0 ? -1 : (e >= a.n_bins ? a.n_bins : (int)e);
-                        if (bin >= 0 && bin < a.n_bins) atomicAdd(&s_hist[bin], 1u);
-                        else if (bin < 0) atomicAdd(&s_hist[a.n_bins], 1u);       // under
-                        else atomicAdd(&s_hist[a.n_bins + 1], 1u);                 // over
+                        // log-linear histogram: one fire-and-forget RED.ADD.F64 per successful trial, straight into the
+                        // packed statistics in L2 (bins are spread over ~10^3 addresses: no hot spot)
+                        double* st = a.stats + seg * a.stats_len;
+                        const int slot = e < 0 ? 6 : (e >= a.n_bins ? 7 : STMPM_STATS_HEAD + (int)e);
+                        atomicAdd(st + slot, 1.0);
                     } else {
                         ++acc_fail;
                     }
@@ -290,14 +296,6 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
                 if (threadIdx.x == 5)
                     atomicMax(reinterpret_cast<unsigned long long*>(st + 5), (unsigned long long)__double_as_longlong(r));
                 else if (r != 0.0) atomicAdd(st + threadIdx.x, r);
-            }
-            for (int k = threadIdx.x; k < a.n_bins + 2; k += TPB) {
-                const uint32_t h = s_hist[k];
-                if (h) {
-                    const int slot = k < a.n_bins ? STMPM_STATS_HEAD + k : (k == a.n_bins ? 6 : 7);
-                    atomicAdd(st + slot, (double)h);
-                    s_hist[k] = 0u;
-                }
             }
             __syncthreads();
         }
@@ -642,7 +640,7 @@ extern "C" int stmpm_stats_finalize(int32_t hist_log2_sub, const double* s, stmp
 // ------------------------------------------------------------------------------------------------ launch helper
 template <int MODE, int PREC, int INSTR = 0>
 static int launch_trials(stmpm_handle* h, KArgs& a, cudaStream_t st) {
-    const SmemLayout L = smem_layout(a.n_stars, a.n_cells_pad, a.n_bands, a.lk_bands, a.n_bins + 2);
+    const SmemLayout L = smem_layout(a.n_stars, a.n_cells_pad, a.n_bands, a.lk_bands);
     if (L.total > (size_t)h->prop.sharedMemPerBlockOptin)
         return fail(STMPM_E_ARG, "catalog too large for shared-memory staging (" + std::to_string(L.total) + " B)");
     auto kern = trials_kernel<MODE, PREC, INSTR>;

@@ -18,7 +18,7 @@
 namespace stmpm {
 
 constexpr int TPB = 512;          // threads per CTA (1 CTA / SM: the fp32 catalog lives in shared memory)
-constexpr int LIST_CAP = 32;      // per-thread candidate list length (phase A -> phase B hand-off)
+constexpr int LIST_CAP = 64;      // per-thread candidate list length (phase A -> phase B hand-off)
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u, PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
 constexpr uint32_t PHILOX2_M = 0xD256D193u;
 constexpr uint32_t TAG_STAR = 0x53544152u, TAG_PARA = 0x50415241u;
