@@ -1,0 +1,139 @@
+"""Bulk study drivers on the CUDA engine — the callers either side of the trial.
+
+* `monte_carlo_converged`  — the stop rule of MonteCarlo.run_sim (/root/reference/monte_carlo.py:48-76) evaluated on
+  streaming moments: no DataFrame, no O(n^2) pd.concat.
+* `sensitivity_grid`       — BASELINE config 3: translation x rotation x centroid-sigma Cartesian grid, one segment per
+  grid point (a generalisation of Sense.run_sim's 1-D diagonal sweep, sensitivity.py:39-55).
+* `leo_lifetime`           — BASELINE config 4: one segment per orbit step with thermal / radiation parameter overrides
+  (thermal focal update sensitivity.py:115-118; radiation -> image noise -> detection threshold README.md:12).
+
+Nothing numerical about the trial happens here: these build `stmpm_dist` arrays and call `TrialEngine.run_rng*`.
+"""
+from __future__ import annotations
+
+from typing import Mapping, Sequence
+
+import numpy as np
+
+from . import _abi
+from .engine import NORMAL_PARAMS, TrialEngine, make_dist, summarize
+
+HALF_NORMAL_K = np.sqrt(1.0 - 2.0 / np.pi)     # driver.py:290
+
+
+def _merge(total: np.ndarray, part: np.ndarray) -> None:
+    xmax = max(total[5], part[5])
+    total += part
+    total[5] = xmax
+
+
+def monte_carlo_converged(engine: TrialEngine, means: Mapping[str, float], sigmas: Mapping[str, float],
+                          thermal_coef: float = 0.0, *, batch: int = 100, seed: int = 0, max_runs: int = -1,
+                          min_rows: int = 10_000, tol: float = 1e-5, precision: int = 64,
+                          batches_per_launch: int = 1) -> dict:
+    """MonteCarlo.run_sim's loop (monte_carlo.py:48-76): batches of `batch` trials until the kept rows number at least
+    `min_rows` AND the relative change of the half-normal sigma is <= tol, or kept rows >= max_runs > 0.
+    sigma_hat = std(x, ddof=1) / sqrt(1 - 2/pi) over all successful trials so far (monte_carlo.py:60-61), computed from
+    the merged packed statistics instead of a growing DataFrame.  `batches_per_launch` > 1 evaluates the rule every
+    that many batches (one kernel launch each) — the reference's rule is batches_per_launch = 1."""
+    dist = make_dist(means, sigmas, thermal_coef)
+    total = np.zeros(engine.stats_len)
+    prev, ratio, count, trial0 = 1.0, 1.0, 0, 0                      # monte_carlo.py:45-46
+    per_launch = int(batch) * int(batches_per_launch)
+    while ratio > tol or total[0] < min_rows:
+        count += batches_per_launch
+        part = engine.run_rng(dist, per_launch, seed, trial0, precision)[0]
+        trial0 += per_launch
+        _merge(total, part)
+        n = total[0]
+        std = np.sqrt(max(0.0, (total[3] - total[2] ** 2 / n) / (n - 1))) if n > 1 else 0.0
+        sigma_hat = std / HALF_NORMAL_K
+        ratio = abs((prev - sigma_hat) / prev)
+        prev = sigma_hat
+        if max_runs > 0 and n >= max_runs:
+            break
+    out = summarize(total, engine.hist_log2_sub)
+    out.update(count=count, trials=trial0, std_ratio=ratio, stats=total)
+    return out
+
+
+def grid_axes(sig_eps: float, sig_phi: float, sig_dev: float, n_eps: int = 64, n_phi: int = 64, n_dev: int = 16):
+    """Config 3 axes: eps scale, phi scale, centroid sigma, each linspace(0, 3 sigma, n)."""
+    return (np.linspace(0.0, 3.0 * sig_eps, n_eps), np.linspace(0.0, 3.0 * sig_phi, n_phi),
+            np.linspace(0.0, 3.0 * sig_dev, n_dev))
+
+
+def sensitivity_grid_dists(means: Mapping[str, float], sigmas: Mapping[str, float], thermal_coef: float,
+                           eps_axis: Sequence[float], phi_axis: Sequence[float], dev_axis: Sequence[float]):
+    """One stmpm_dist per grid point, C order (eps, phi, dev).  At a grid point the swept quantities are FIXED (sigma 0),
+    like the reference overwrites swept columns with the linspace values (sensitivity.py:54-55): axis 1 sets
+    F_ARR_EPS_X/Y/Z jointly, axis 2 F_ARR_PHI/THETA/PSI jointly, axis 3 BASE_DEV_X = BASE_DEV_Y."""
+    dists = []
+    for e in eps_axis:
+        for p in phi_axis:
+            for d in dev_axis:
+                m, s = dict(means), dict(sigmas)
+                for k in ("F_ARR_EPS_X", "F_ARR_EPS_Y", "F_ARR_EPS_Z"):
+                    m[k], s[k] = float(e), 0.0
+                for k in ("F_ARR_PHI", "F_ARR_THETA", "F_ARR_PSI"):
+                    m[k], s[k] = float(p), 0.0
+                for k in ("BASE_DEV_X", "BASE_DEV_Y"):
+                    m[k], s[k] = float(d), 0.0
+                dists.append(make_dist(m, s, thermal_coef))
+    return dists
+
+
+def sensitivity_grid(engine: TrialEngine, means, sigmas, thermal_coef, eps_axis, phi_axis, dev_axis,
+                     trials_per_point: int, seed: int = 3, precision: int = 64, segments=None) -> np.ndarray:
+    """Runs the grid (or the subset `segments` of flat point indices, e.g. this rank's share from
+    sharding.shard_segments) and returns packed statistics [n_points_run, stats_len].  Global trial index of trial i of
+    point p is p * trials_per_point + i regardless of which rank runs it."""
+    dists = sensitivity_grid_dists(means, sigmas, thermal_coef, eps_axis, phi_axis, dev_axis)
+    return run_segments(engine, dists, trials_per_point, seed, precision, segments)
+
+
+def leo_lifetime_dists(means: Mapping[str, float], sigmas: Mapping[str, float], thermal_coef: float, n_steps: int = 60,
+                       years: float = 5.0, dtemp_amp: float = 15.0, dtemp_sigma: float = 5.0,
+                       mag_loss_per_year: float = 0.12, dev_growth_per_year: float = 0.15):
+    """Config 4 schedule [FREE, SURVEY.md §8d]: monthly steps over `years`.  Thermal: D_TEMP mean follows a seasonal
+    sinusoid of amplitude dtemp_amp K (beta-angle cycle), sigma dtemp_sigma.  Radiation: accumulated dose raises the image
+    noise floor, i.e. lowers the detection threshold MAX_MAGNITUDE linearly by mag_loss_per_year and inflates the
+    centroiding sigma by dev_growth_per_year (fractional)."""
+    dists, sched = [], []
+    for k in range(n_steps):
+        t = years * k / max(1, n_steps - 1)
+        m, s = dict(means), dict(sigmas)
+        m["D_TEMP"] = dtemp_amp * np.sin(2.0 * np.pi * t)
+        s["D_TEMP"] = dtemp_sigma
+        m["MAX_MAGNITUDE"] = means["MAX_MAGNITUDE"] - mag_loss_per_year * t
+        grow = 1.0 + dev_growth_per_year * t
+        s["BASE_DEV_X"] = sigmas.get("BASE_DEV_X", 0.0) * grow
+        s["BASE_DEV_Y"] = sigmas.get("BASE_DEV_Y", 0.0) * grow
+        dists.append(make_dist(m, s, thermal_coef))
+        sched.append({"t_years": t, "D_TEMP": m["D_TEMP"], "MAX_MAGNITUDE": m["MAX_MAGNITUDE"], "dev_sigma": s["BASE_DEV_X"]})
+    return dists, sched
+
+
+def run_segments(engine: TrialEngine, dists: Sequence[_abi.Dist], trials_per_segment: int, seed: int,
+                 precision: int = 64, segments=None, max_segments_per_launch: int = 4096) -> np.ndarray:
+    """Statistics-only multi-segment run; `segments` selects flat indices (default all).  Consecutive selected indices
+    are batched into single launches (segment s always uses global trial indices s * trials_per_segment + i)."""
+    idx = list(range(len(dists))) if segments is None else [int(i) for i in segments]
+    out = np.zeros((len(idx), engine.stats_len))
+    i = 0
+    while i < len(idx):
+        j = i + 1                                                  # grow a run of consecutive segment indices
+        while j < len(idx) and idx[j] == idx[j - 1] + 1 and j - i < max_segments_per_launch:
+            j += 1
+        out[i:j] = engine.run_rng([dists[k] for k in idx[i:j]], trials_per_segment, seed,
+                                  idx[i] * int(trials_per_segment), precision)
+        i = j
+    return out
+
+
+def summaries(stats: np.ndarray, hist_log2_sub: int = 8) -> list[dict]:
+    return [summarize(s, hist_log2_sub) for s in np.atleast_2d(stats)]
+
+
+__all__ = ["monte_carlo_converged", "grid_axes", "sensitivity_grid_dists", "sensitivity_grid", "leo_lifetime_dists",
+           "run_segments", "summaries", "NORMAL_PARAMS"]
