@@ -31,6 +31,8 @@ struct KArgs {
     int lk_bands;
     float lk_inv_band_h, lk_cone; // a trial whose scan cone exceeds lk_cone takes the sky-grid scan instead
     const MathTables* tables;
+    const uint8_t* lk_key;        // [n_lk_cells][KEY_LEVELS]: candidates with mag <= KEY_M0 + (k+1)/16, saturated at 255
+    int win;                      // trials per warp-local sort window (multiple of 32, <= WIN_MAX)
     double f_ideal, half_u, half_v;
     int n_min, hist_shift, n_bins;   // hist_shift = 52 - log2(sub-bins per octave)
     long long n_segments, trials_per_segment, trial0, part_len;
@@ -47,51 +49,93 @@ struct KArgs {
 };
 
 struct SmemLayout {
-    size_t cat32, cell_start, band_tab, lk_band_tab, tables, list, red, total;
+    size_t cat32, band_tab, lk_band_tab, tables, list, win, red, total;
 };
-static SmemLayout smem_layout(int n_stars, int n_cells_pad, int n_bands, int lk_bands) {
+constexpr size_t WIN_BYTES = WIN_MAX /*keys u8*/ + 2 * WIN_MAX /*perm u16*/ + 2 * KEY_BINS /*hist u16*/;
+static SmemLayout smem_layout(int n_stars, int n_bands, int lk_bands) {
     SmemLayout L;
     size_t o = 0;
     L.cat32 = o;      o += (size_t)n_stars * 16;
-    L.cell_start = o; o += (((size_t)n_cells_pad * 2) + 15) / 16 * 16;
     L.band_tab = o;   o += (((size_t)n_bands * 8) + 15) / 16 * 16;
     L.lk_band_tab = o; o += (((size_t)lk_bands * 8) + 15) / 16 * 16;
     L.tables = o;     o += (sizeof(MathTables) + 15) / 16 * 16;
     L.list = o;       o += (size_t)LIST_CAP * TPB * 2;
+    L.win = o;        o += (size_t)(TPB / 32) * WIN_BYTES;
     L.red = o;        o += (size_t)(TPB / 32) * 8 * 8;
     L.total = o;
     return L;
 }
 
+// Walks the magnitude-sorted candidate list of the boresight's lookup cell from position lk on, pushing pre-filter
+// survivors to row[cnt * TPB]; the first star fainter than MAX_MAGNITUDE ends the scan (returns true).  Returns false
+// while candidates remain and fewer than 8 row slots are free: the caller drains the row and calls again.
+template <int INSTR>
+__device__ __forceinline__ bool scan_list(const Ctx32& c, const float4* __restrict__ s_cat, const uint16_t* __restrict__ lp,
+                                          int lk_len, int& lk, uint16_t* __restrict__ row, int& cnt,
+                                          unsigned long long* ins) {
+    if (lk >= lk_len) return true;
+    uint4 pk_next = __ldg(reinterpret_cast<const uint4*>(lp + lk));
+    while (cnt <= LIST_CAP - 8) {
+        const uint4 pk = pk_next;
+        lk += 8;
+        if (lk < lk_len) pk_next = __ldg(reinterpret_cast<const uint4*>(lp + lk));   // prefetch the next 8 candidates
+        const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const uint32_t idx = (w4[e >> 1] >> (16 * (e & 1))) & 0xffffu;
+            if (idx == 0xffffu) return true;
+            const float4 sc = s_cat[idx];
+            if (INSTR) ++ins[0];
+            if (!(sc.w <= c.magf)) return true;          // sorted by magnitude: every later star is fainter still
+            if (INSTR) ++ins[1];
+            if (prefilter_geom(c, sc)) { row[cnt * TPB] = (uint16_t)idx; ++cnt; if (INSTR) ++ins[2]; }
+        }
+        if (lk >= lk_len) return true;
+    }
+    return false;
+}
+
+__device__ __forceinline__ int lookup_cell(const int2* __restrict__ s_lkband, int lk_bands, float lk_inv_band_h, float ra0,
+                                           float dec0) {
+    const int lb = min(lk_bands - 1, max(0, (int)floorf((dec0 + 1.57079633f) * lk_inv_band_h)));
+    const int2 bt = s_lkband[lb];
+    return bt.x + min(bt.y - 1, max(0, (int)floorf(ra0 * 0.159154943f * (float)bt.y)));
+}
+
 // ------------------------------------------------------------------------------------------------ the trial kernel
 // MODE 0: pre-sampled columns.  MODE 1: native RNG.  PREC 64 / 32: per-star arithmetic.
-// INSTR 1: also count sky-grid visits / magnitude passes / pre-filter survivors (work-model calibration, not timed).
+// INSTR 1: also count candidate visits / magnitude passes / pre-filter survivors (work-model calibration, not timed).
 template <int MODE, int PREC, int INSTR>
 __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const SmemLayout L) {
     extern __shared__ __align__(16) unsigned char smem[];
     float4* s_cat = reinterpret_cast<float4*>(smem + L.cat32);
-    uint16_t* s_cell = reinterpret_cast<uint16_t*>(smem + L.cell_start);
     int2* s_band = reinterpret_cast<int2*>(smem + L.band_tab);
     int2* s_lkband = reinterpret_cast<int2*>(smem + L.lk_band_tab);
     const MathTables* s_tab = reinterpret_cast<const MathTables*>(smem + L.tables);
     uint16_t* s_list = reinterpret_cast<uint16_t*>(smem + L.list) + threadIdx.x;   // entry j at s_list[j * TPB]
     double* s_red = reinterpret_cast<double*>(smem + L.red);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // this warp's sort window: keys, permutation, bin counters
+    uint8_t* w_key = smem + L.win + (size_t)warp * WIN_BYTES;
+    uint16_t* w_perm = reinterpret_cast<uint16_t*>(w_key + WIN_MAX);
+    uint16_t* w_hist = w_perm + WIN_MAX;
 
     // ---- stage the catalog + grid into shared memory (once per CTA; the CTA is persistent)
     {
         const uint4* g = reinterpret_cast<const uint4*>(a.cat32);
         uint4* s = reinterpret_cast<uint4*>(s_cat);
         for (int i = threadIdx.x; i < a.n_stars; i += TPB) s[i] = __ldg(g + i);
-        for (int i = threadIdx.x; i < a.n_cells_pad; i += TPB) s_cell[i] = __ldg(a.cell_start + i);
         for (int i = threadIdx.x; i < a.n_bands; i += TPB) s_band[i] = __ldg(a.band_tab + i);
         for (int i = threadIdx.x; i < a.lk_bands; i += TPB) s_lkband[i] = __ldg(a.lk_band_tab + i);
-        {
-            const double* gt = reinterpret_cast<const double*>(a.tables);
-            double* stb = reinterpret_cast<double*>(smem + L.tables);
-            for (int i = threadIdx.x; i < (int)(sizeof(MathTables) / 8); i += TPB) stb[i] = __ldg(gt + i);
-        }
+        const double* gt = reinterpret_cast<const double*>(a.tables);
+        double* stb = reinterpret_cast<double*>(smem + L.tables);
+        for (int i = threadIdx.x; i < (int)(sizeof(MathTables) / 8); i += TPB) stb[i] = __ldg(gt + i);
     }
     __syncthreads();
+
+    const uint16_t* __restrict__ g_cell = a.cell_start;   // sky-grid cell index (fallback scan only): read through L1/L2
+    const float hu32 = (float)a.half_u, hv32 = (float)a.half_v;
+    const int win = a.win;                                 // trials per window, multiple of 32, <= WIN_MAX
 
     const long long n_units = a.n_segments * (long long)a.parts_per_segment;
     for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
@@ -100,179 +144,217 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
         const long long t_begin = part * a.part_len;
         const long long t_end = min(t_begin + a.part_len, a.trials_per_segment);
         const bool want_stats = a.stats != nullptr;
-
-        DistDev dist;
-        if (MODE == 1) dist = (a.n_segments == 1) ? a.dist0 : a.dists[seg];
+        const DistDev* dist = (MODE == 1) ? ((a.n_segments == 1) ? &a.dist0 : a.dists + seg) : nullptr;
 
         // per-thread streaming accumulators (MODEL.md §9)
         unsigned int acc_ok = 0, acc_fail = 0;
         unsigned long long acc_ndet = 0;
         double acc_x = 0.0, acc_xx = 0.0, acc_max = 0.0;
-        unsigned long long ins_visit = 0, ins_mag = 0, ins_surv = 0, ins_det = 0;
+        unsigned long long ins[4] = {0, 0, 0, 0};
 
-        for (long long tb = t_begin; tb < t_end; tb += TPB) {   // warp-uniform trip count
-            const long long t = tb + threadIdx.x;
-            const bool valid = t < t_end;
-            const long long rec = seg * a.trials_per_segment + t;          // record / global trial offset
-            const unsigned long long gidx = (unsigned long long)(a.trial0 + rec);
-            const uint32_t t_lo = (uint32_t)gidx, t_hi = (uint32_t)(gidx >> 32);
+        // warps work independently: warp w takes windows w, w + 16, ... of this unit — no CTA barrier inside the unit
+        for (long long wb = t_begin + (long long)warp * win; wb < t_end; wb += (long long)(TPB / 32) * win) {
+            const int nw = (int)min((long long)win, t_end - wb);     // valid trials in this window
+            const long long rec0 = seg * a.trials_per_segment + wb;
 
-            TrialParams p;
-            if (MODE == 0) {
-                if (valid) {
-                    p.ra = __ldcs(a.cols[0] + rec);     p.dec = __ldcs(a.cols[1] + rec);
-                    p.roll = __ldcs(a.cols[2] + rec);   p.f = __ldcs(a.cols[3] + rec);
-                    p.ex = __ldcs(a.cols[4] + rec);     p.ey = __ldcs(a.cols[5] + rec);
-                    p.ez = __ldcs(a.cols[6] + rec);     p.phi = __ldcs(a.cols[7] + rec);
-                    p.theta = __ldcs(a.cols[8] + rec);  p.psi = __ldcs(a.cols[9] + rec);
-                    p.devx = __ldcs(a.cols[10] + rec);  p.devy = __ldcs(a.cols[11] + rec);
-                    p.maxmag = __ldcs(a.cols[12] + rec);
-                } else {
-                    p.ra = p.dec = p.roll = 0.0; p.f = 1000.0; p.ex = p.ey = p.ez = p.phi = p.theta = p.psi = 0.0;
-                    p.devx = p.devy = 0.0; p.maxmag = -100.0;
+            // ================= key pass: work key per trial, warp-local counting sort
+            for (int i = lane; i < KEY_BINS; i += 32) w_hist[i] = 0;
+            __syncwarp();
+            for (int r = lane; r < win; r += 32) {
+                int key = KEY_BINS - 1;                               // padding slots sort last
+                if (r < nw) {
+                    double ra, dec, mm;
+                    if (MODE == 0) {
+                        ra = __ldg(a.cols[0] + rec0 + r); dec = __ldg(a.cols[1] + rec0 + r); mm = __ldg(a.cols[12] + rec0 + r);
+                    } else {
+                        const unsigned long long gi = (unsigned long long)(a.trial0 + rec0 + r);
+                        sample_key_params(*dist, s_tab, (uint32_t)gi, (uint32_t)(gi >> 32), a.k0, a.k1, ra, dec, mm);
+                    }
+                    // boresight (ra, dec) -> lookup cell (any finite input gives a valid cell; the key is only a hint)
+                    float raf = (float)ra, decf = (float)dec;
+                    raf -= 6.28318531f * floorf(raf * 0.159154943f);
+                    decf = fminf(fmaxf(decf, -1.57079633f), 1.57079633f);
+                    const int cell = lookup_cell(s_lkband, a.lk_bands, a.lk_inv_band_h, raf, decf);
+                    const int lev = min(KEY_LEVELS - 1, (int)floorf(((float)mm - KEY_M0) * 16.0f));
+                    key = lev < 0 ? 0 : (int)(__ldg(a.lk_key + (size_t)cell * KEY_LEVELS + lev) >> 2);
                 }
-            } else {
-                sample_params(dist, t_lo, t_hi, a.k0, a.k1, p);
+                w_key[r] = (uint8_t)key;
+                atomicAdd(reinterpret_cast<unsigned int*>(w_hist) + (key >> 1), (key & 1) ? 0x10000u : 1u);
             }
-
-            TrialCtx c;
-            trial_setup(p, a.half_u, a.half_v, c);
-
-            uint32_t ka, kb;
-            star_key(t_lo, t_hi, a.k0, a.k1, ka, kb);
-
-            // ---- phase-A state.  Fast path: the magnitude-sorted candidate list of the boresight's lookup cell.
-            // Fallback (scan cone wider than the lists were built for): walk the sky-grid bands (fp32, conservative).
-            const bool use_list = c.cone <= a.lk_cone;
-            const uint16_t* lp = a.lk_list;
-            int lk = 0, lk_len = 0;
-            uint4 pk_next = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-            if (use_list) {
-                const int lb = min(a.lk_bands - 1, max(0, (int)floorf((c.dec0 + 1.57079633f) * a.lk_inv_band_h)));
-                const int2 bt = s_lkband[lb];
-                const int rc = min(bt.y - 1, max(0, (int)floorf(c.ra0 * 0.159154943f * (float)bt.y)));
-                const uint32_t o0 = __ldg(a.lk_off + bt.x + rc), o1 = __ldg(a.lk_off + bt.x + rc + 1);
-                lp += o0;
-                lk_len = (int)(o1 - o0);
-                if (lk_len > 0) pk_next = __ldg(reinterpret_cast<const uint4*>(lp));
-            }
-            int b = max(0, (int)floorf((c.dec0 - c.cone + 1.57079633f) * a.inv_band_h));
-            const int b_hi = min(a.n_bands - 1, (int)floorf((c.dec0 + c.cone + 1.57079633f) * a.inv_band_h));
-            int i = 0, i_end = 0, pi = 0, p_end = 0;
-            bool scanning = valid;
-            int cnt = 0, n_det = 0;
-            double B[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-
-            do {
-                if (use_list) {
-                    // ---- phase A (fast): all lanes walk their own list in lock-step, 8 indices per 16-byte load;
-                    // the list is sorted by magnitude, so the first star fainter than MAX_MAGNITUDE ends the scan
-                    while (scanning && cnt <= LIST_CAP - 8) {
-                        if (lk >= lk_len) { scanning = false; break; }
-                        const uint4 pk = pk_next;
-                        lk += 8;
-                        if (lk < lk_len) pk_next = __ldg(reinterpret_cast<const uint4*>(lp + lk));   // prefetch
-                        const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
+            __syncwarp();
+            {   // exclusive scan of the 64 bins: 2 per lane
+                const uint32_t h0 = w_hist[2 * lane], h1 = w_hist[2 * lane + 1];
+                uint32_t incl = h0 + h1;
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const uint32_t idx = (w4[e >> 1] >> (16 * (e & 1))) & 0xffffu;
-                            if (idx == 0xffffu) { scanning = false; break; }
-                            const float4 sc = s_cat[idx];
-                            if (INSTR) { ++ins_visit; }
-                            if (!(sc.w <= c.magf)) { scanning = false; break; }
-                            if (INSTR) { ++ins_mag; }
-                            if (prefilter_geom(c, sc)) { s_list[cnt * TPB] = (uint16_t)idx; ++cnt; if (INSTR) ++ins_surv; }
-                        }
+                for (int off = 1; off < 32; off <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+                    if (lane >= off) incl += o;
+                }
+                const uint32_t excl = incl - (h0 + h1);
+                __syncwarp();
+                w_hist[2 * lane] = (uint16_t)excl;
+                w_hist[2 * lane + 1] = (uint16_t)(excl + h0);
+            }
+            __syncwarp();
+            for (int r = lane; r < win; r += 32) {
+                const int key = w_key[r];
+                const unsigned int old = atomicAdd(reinterpret_cast<unsigned int*>(w_hist) + (key >> 1),
+                                                   (key & 1) ? 0x10000u : 1u);
+                w_perm[(key & 1) ? (old >> 16) : (old & 0xffffu)] = (uint16_t)r;
+            }
+            __syncwarp();
+
+            // ================= the trials of this window, 32 at a time in key order
+            for (int g0 = 0; g0 < win; g0 += 32) {
+                const int r = w_perm[g0 + lane];
+                const bool valid = r < nw;
+                if (!__any_sync(0xffffffffu, valid)) continue;
+                const long long rec = rec0 + r;
+                const unsigned long long gidx = (unsigned long long)(a.trial0 + rec);
+                const uint32_t t_lo = (uint32_t)gidx, t_hi = (uint32_t)(gidx >> 32);
+
+                TrialParams p;
+                if (MODE == 0) {
+                    if (valid) {
+                        p.ra = __ldg(a.cols[0] + rec);     p.dec = __ldg(a.cols[1] + rec);
+                        p.roll = __ldg(a.cols[2] + rec);   p.f = __ldg(a.cols[3] + rec);
+                        p.ex = __ldg(a.cols[4] + rec);     p.ey = __ldg(a.cols[5] + rec);
+                        p.ez = __ldg(a.cols[6] + rec);     p.phi = __ldg(a.cols[7] + rec);
+                        p.theta = __ldg(a.cols[8] + rec);  p.psi = __ldg(a.cols[9] + rec);
+                        p.devx = __ldg(a.cols[10] + rec);  p.devy = __ldg(a.cols[11] + rec);
+                        p.maxmag = __ldg(a.cols[12] + rec);
+                    } else {
+                        p.ra = p.dec = p.roll = 0.0; p.f = 1000.0; p.ex = p.ey = p.ez = p.phi = p.theta = p.psi = 0.0;
+                        p.devx = p.devy = 0.0; p.maxmag = -100.0;
                     }
                 } else {
-                    // ---- phase A (fallback): scan sky-grid cells, push pre-filter survivors onto the per-thread list
-                    while (scanning && cnt < LIST_CAP) {
-                        if (i >= i_end) {
-                            if (pi < p_end) { i = pi; i_end = p_end; pi = p_end = 0; continue; }
-                            if (b > b_hi) { scanning = false; break; }
-                            const int2 bt = s_band[b];
-                            ++b;
-                            const int base = bt.x, n = bt.y;
-                            if (c.dalpha < 0.0f) { i = s_cell[base]; i_end = s_cell[base + n]; continue; }
-                            const float inv_w = (float)n * 0.159154943f;
-                            const int c_lo = (int)floorf((c.ra0 - c.dalpha) * inv_w);
-                            const int c_hi = (int)floorf((c.ra0 + c.dalpha) * inv_w);
-                            const int count = c_hi - c_lo + 1;
-                            if (count >= n) { i = s_cell[base]; i_end = s_cell[base + n]; continue; }
-                            int lo = c_lo % n;
-                            if (lo < 0) lo += n;
-                            if (lo + count <= n) { i = s_cell[base + lo]; i_end = s_cell[base + lo + count]; }
-                            else {
-                                i = s_cell[base + lo]; i_end = s_cell[base + n];
-                                pi = s_cell[base]; p_end = s_cell[base + lo + count - n];
+                    sample_params(*dist, s_tab, t_lo, t_hi, a.k0, a.k1, p);
+                }
+                Ctx64 c;
+                setup64(p, c);
+                Ctx32 cf;
+                derive32(p, c, hu32, hv32, cf);
+                uint32_t ka, kb;
+                star_key(t_lo, t_hi, a.k0, a.k1, ka, kb);
+
+                // ---- phase-A state.  Fast path: the magnitude-sorted candidate list of the boresight's lookup cell.
+                // Fallback (scan cone wider than the lists were built for): walk the sky-grid bands.
+                const bool use_list = cf.cone <= a.lk_cone;
+                const uint16_t* lp = a.lk_list;
+                int lk = 0, lk_len = 0;
+                int b = 0, b_hi = -1, i = 0, i_end = 0, pi = 0, p_end = 0;
+                float dalpha = -1.0f;
+                if (use_list) {
+                    const int cell = lookup_cell(s_lkband, a.lk_bands, a.lk_inv_band_h, cf.ra0, cf.dec0);
+                    const uint32_t o0 = __ldg(a.lk_off + cell), o1 = __ldg(a.lk_off + cell + 1);
+                    lp += o0;
+                    lk_len = (int)(o1 - o0);
+                } else {
+                    b = max(0, (int)floorf((cf.dec0 - cf.cone + 1.57079633f) * a.inv_band_h));
+                    b_hi = min(a.n_bands - 1, (int)floorf((cf.dec0 + cf.cone + 1.57079633f) * a.inv_band_h));
+                    if (fabsf(cf.dec0) + cf.cone < 1.5607963f)
+                        dalpha = asinf(fminf(sinf(cf.cone) / cosf(cf.dec0), 1.0f)) + 0.002f;
+                }
+                bool scanning = valid;
+                int cnt = 0, n_det = 0;
+                double B[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+
+                do {
+                    if (scanning) {
+                        if (use_list) {
+                            if (scan_list<INSTR>(cf, s_cat, lp, lk_len, lk, s_list, cnt, ins)) scanning = false;
+                        } else {
+                            // sky-grid band walk (fp32, conservative): cells overlapping the scan cone
+                            while (scanning && cnt < LIST_CAP) {
+                                if (i >= i_end) {
+                                    if (pi < p_end) { i = pi; i_end = p_end; pi = p_end = 0; continue; }
+                                    if (b > b_hi) { scanning = false; break; }
+                                    const int2 bt = s_band[b];
+                                    ++b;
+                                    const int base = bt.x, n = bt.y;
+                                    if (dalpha < 0.0f) { i = g_cell[base]; i_end = g_cell[base + n]; continue; }
+                                    const float inv_w = (float)n * 0.159154943f;
+                                    const int c_lo = (int)floorf((cf.ra0 - dalpha) * inv_w);
+                                    const int c_hi = (int)floorf((cf.ra0 + dalpha) * inv_w);
+                                    const int count = c_hi - c_lo + 1;
+                                    if (count >= n) { i = g_cell[base]; i_end = g_cell[base + n]; continue; }
+                                    int lo = c_lo % n;
+                                    if (lo < 0) lo += n;
+                                    if (lo + count <= n) { i = g_cell[base + lo]; i_end = g_cell[base + lo + count]; }
+                                    else {
+                                        i = g_cell[base + lo]; i_end = g_cell[base + n];
+                                        pi = g_cell[base]; p_end = g_cell[base + lo + count - n];
+                                    }
+                                    continue;
+                                }
+                                const float4 sc = s_cat[i];
+                                if (INSTR) { ++ins[0]; if (sc.w <= cf.magf) ++ins[1]; }
+                                if (sc.w <= cf.magf && prefilter_geom(cf, sc)) {
+                                    s_list[cnt * TPB] = (uint16_t)i; ++cnt; if (INSTR) ++ins[2];
+                                }
+                                ++i;
                             }
-                            continue;
                         }
-                        const float4 sc = s_cat[i];
-                        if (INSTR) { ++ins_visit; if (sc.w <= c.magf) ++ins_mag; }
-                        if (sc.w <= c.magf && prefilter_geom(c, sc)) {
-                            s_list[cnt * TPB] = (uint16_t)i; ++cnt; if (INSTR) ++ins_surv;
-                        }
-                        ++i;
                     }
-                }
-                __syncwarp();
-                // ---- phase B: exact evaluation of the listed stars (lanes in lock-step)
-                // (software-pipelined: the 32-byte record of star j+1 is in flight while star j is evaluated)
-                double2 r_lo = make_double2(0.0, 0.0), r_hi = make_double2(0.0, 0.0);
-                if (cnt > 0) {
-                    const double2* g = reinterpret_cast<const double2*>(a.cat64 + s_list[0]);
-                    r_lo = __ldg(g); r_hi = __ldg(g + 1);
-                }
-                for (int j = 0; j < cnt; ++j) {
-                    StarRec s;
-                    s.x = r_lo.x; s.y = r_lo.y; s.z = r_hi.x;
-                    s.star_id = (uint32_t)(__double_as_longlong(r_hi.y) & 0xffffffffll);
-                    if (j + 1 < cnt) {
-                        const double2* g = reinterpret_cast<const double2*>(a.cat64 + s_list[(j + 1) * TPB]);
+                    __syncwarp();
+                    // ---- phase B: exact evaluation of the listed stars (lanes in lock-step).
+                    // Software-pipelined: the 32-byte record of star j+1 is in flight while star j is evaluated.
+                    double2 r_lo = make_double2(0.0, 0.0), r_hi = make_double2(0.0, 0.0);
+                    if (cnt > 0) {
+                        const double2* g = reinterpret_cast<const double2*>(a.cat64 + s_list[0]);
                         r_lo = __ldg(g); r_hi = __ldg(g + 1);
                     }
-                    bool det;
-                    if (PREC == 64) det = star_exact(c, s_tab, s, ka, kb, a.f_ideal, a.half_u, a.half_v, B);
-                    else det = star_f32(c, s_tab, s, ka, kb, a.f_ideal, a.half_u, a.half_v, B);
-                    n_det += det ? 1 : 0;
-                }
-                cnt = 0;
-            } while (__any_sync(0xffffffffu, scanning));
+                    for (int j = 0; j < cnt; ++j) {
+                        StarRec s;
+                        s.x = r_lo.x; s.y = r_lo.y; s.z = r_hi.x;
+                        s.star_id = (uint32_t)(__double_as_longlong(r_hi.y) & 0xffffffffll);
+                        if (j + 1 < cnt) {
+                            const double2* g = reinterpret_cast<const double2*>(a.cat64 + s_list[(j + 1) * TPB]);
+                            r_lo = __ldg(g); r_hi = __ldg(g + 1);
+                        }
+                        bool det;
+                        if (PREC == 64) det = star_exact(c, s_tab, s, ka, kb, a.f_ideal, a.half_u, a.half_v, B);
+                        else det = star_f32(c, cf, s_tab, s, ka, kb, a.f_ideal, a.half_u, a.half_v, B);
+                        n_det += det ? 1 : 0;
+                    }
+                    cnt = 0;
+                } while (__any_sync(0xffffffffu, scanning));
 
-            // ---- solve + record
-            double err = -1.0;
-            if (n_det >= a.n_min) err = quest_error_arcsec(B, c.C, n_det);
-            if (INSTR && valid) ins_det += (unsigned long long)n_det;
-            if (valid) {
-                if (a.err) __stcs(a.err + rec, err);
-                if (a.ndet) __stcs(a.ndet + rec, n_det);
-                if (want_stats) {
-                    acc_ndet += (unsigned long long)n_det;
-                    if (err >= 0.0) {
-                        ++acc_ok;
-                        acc_x += err;
-                        acc_xx = fma(err, err, acc_xx);
-                        acc_max = fmax(acc_max, err);
-                        const long long e = (__double_as_longlong(err) >> a.hist_shift)
-                                            - ((long long)(1023 + STMPM_HIST_MIN_EXP) << (52 - a.hist_shift));
-                        // log-linear histogram: one fire-and-forget RED.ADD.F64 per successful trial, straight into the
-                        // packed statistics in L2 (bins are spread over ~10^3 addresses: no hot spot)
-                        double* st = a.stats + seg * a.stats_len;
-                        const int slot = e < 0 ? 6 : (e >= a.n_bins ? 7 : STMPM_STATS_HEAD + (int)e);
-                        atomicAdd(st + slot, 1.0);
-                    } else {
-                        ++acc_fail;
+                // ---- solve + record
+                double err = -1.0;
+                if (n_det >= a.n_min) err = quest_error_arcsec(B, c.C, n_det);
+                if (valid) {
+                    if (INSTR) ins[3] += (unsigned long long)n_det;
+                    if (a.err) a.err[rec] = err;
+                    if (a.ndet) a.ndet[rec] = n_det;
+                    if (want_stats) {
+                        acc_ndet += (unsigned long long)n_det;
+                        if (err >= 0.0) {
+                            ++acc_ok;
+                            acc_x += err;
+                            acc_xx = fma(err, err, acc_xx);
+                            acc_max = fmax(acc_max, err);
+                            const long long e = (__double_as_longlong(err) >> a.hist_shift)
+                                                - ((long long)(1023 + STMPM_HIST_MIN_EXP) << (52 - a.hist_shift));
+                            // log-linear histogram: one fire-and-forget RED.ADD.F64 per successful trial, straight into
+                            // the packed statistics in L2 (bins are spread over ~10^3 addresses: no hot spot)
+                            double* st = a.stats + seg * a.stats_len;
+                            const int slot = e < 0 ? 6 : (e >= a.n_bins ? 7 : STMPM_STATS_HEAD + (int)e);
+                            atomicAdd(st + slot, 1.0);
+                        } else {
+                            ++acc_fail;
+                        }
                     }
                 }
             }
+            __syncwarp();   // the window buffers are reused by this warp's next window
         }
 
         if (INSTR) {
-            atomicAdd(a.counters + 0, ins_visit); atomicAdd(a.counters + 1, ins_mag);
-            atomicAdd(a.counters + 2, ins_surv);  atomicAdd(a.counters + 3, ins_det);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) atomicAdd(a.counters + k, ins[k]);
         }
-        // ---- unit epilogue: block reduction of the moments, one atomic per CTA per quantity; histogram flush
+        // ---- unit epilogue: block reduction of the moments, one atomic per CTA per quantity
         if (want_stats) {
             double v[5] = {(double)acc_ok, (double)acc_fail, acc_x, acc_xx, (double)acc_ndet};
 #pragma unroll
@@ -281,7 +363,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
                 for (int k = 0; k < 5; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
                 acc_max = fmax(acc_max, __shfl_xor_sync(0xffffffffu, acc_max, off));
             }
-            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            __syncthreads();
             if (lane == 0) {
 #pragma unroll
                 for (int k = 0; k < 5; ++k) s_red[warp * 8 + k] = v[k];
@@ -297,21 +379,20 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
                     atomicMax(reinterpret_cast<unsigned long long*>(st + 5), (unsigned long long)__double_as_longlong(r));
                 else if (r != 0.0) atomicAdd(st + threadIdx.x, r);
             }
-            __syncthreads();
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------ generator kernel
 __global__ void __launch_bounds__(256) fill_presampled_kernel(long long n, long long trial0, uint32_t k0, uint32_t k1,
-                                                              DistDev dist, double* c0, double* c1, double* c2,
+                                                              DistDev dist, const MathTables* __restrict__ tab, double* c0, double* c1, double* c2,
                                                               double* c3, double* c4, double* c5, double* c6,
                                                               double* c7, double* c8, double* c9, double* c10,
                                                               double* c11, double* c12) {
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
         const unsigned long long g = (unsigned long long)(trial0 + t);
         TrialParams p;
-        sample_params(dist, (uint32_t)g, (uint32_t)(g >> 32), k0, k1, p);
+        sample_params(dist, tab, (uint32_t)g, (uint32_t)(g >> 32), k0, k1, p);
         c0[t] = p.ra; c1[t] = p.dec; c2[t] = p.roll; c3[t] = p.f; c4[t] = p.ex; c5[t] = p.ey; c6[t] = p.ez;
         c7[t] = p.phi; c8[t] = p.theta; c9[t] = p.psi; c10[t] = p.devx; c11[t] = p.devy; c12[t] = p.maxmag;
     }
@@ -361,6 +442,7 @@ struct stmpm_handle {
     float lk_cone = -1.0f;
     long long lk_entries = 0;
     MathTables* tables = nullptr;
+    uint8_t* lk_key = nullptr;    // work-key table [n_lk_cells][KEY_LEVELS]
     bool have_catalog = false, have_sensor = false;
     stmpm_sensor_cfg cfg{};
     int n_bins = 0;
@@ -385,14 +467,14 @@ struct stmpm_handle {
 static void stmpm_host_tables(MathTables* t) {
     for (int j = 0; j < 128; ++j) {
         const double c = 1.0 + (j + 0.5) / 128.0;
-        t->log_inv_c[j] = 1.0 / c;
-        t->log_ln_c[j] = std::log(c);
+        t->log_tab[j][0] = 1.0 / c;
+        t->log_tab[j][1] = std::log(c);
     }
     for (int k = 0; k < 34; ++k) t->k_ln2[k] = k * M_LN2;
     for (int j = 0; j < 64; ++j) {
         const double a = (M_PI / 2.0) * (j + 0.5) / 64.0;
-        t->sc_sin[j] = std::sin(a);
-        t->sc_cos[j] = std::cos(a);
+        t->sc_tab[j][0] = std::sin(a);
+        t->sc_tab[j][1] = std::cos(a);
     }
 }
 
@@ -426,6 +508,9 @@ static int rebuild_lists(stmpm_handle* h) {
     std::vector<uint32_t> off(n_cells + 1, 0);
     std::vector<uint16_t> list;
     list.reserve((size_t)n_cells * 160);
+    std::vector<uint8_t> key_tab((size_t)n_cells * KEY_LEVELS, 0);   // candidate visits per cell at magnitude levels
+    std::vector<float> smag(S);
+    for (int i = 0; i < S; ++i) smag[i] = h->h_mag[order[i]];
     for (int b = 0; b < nb; ++b) {
         const double d0 = -M_PI / 2 + b * bh, d1 = d0 + bh, dm = 0.5 * (d0 + d1);
         const int n_ra = bt[b].y;
@@ -450,7 +535,18 @@ static int rebuild_lists(stmpm_handle* h) {
                         cz = (float)std::sin(dm);
             for (int i = 0; i < S; ++i) dots[i] = cx * sx[i] + cy * sy[i] + cz * sz[i];
             const size_t start = list.size();
-            for (int i = 0; i < S; ++i) if (dots[i] >= thresh) list.push_back((uint16_t)order[i]);
+            {
+                uint8_t* kt = key_tab.data() + (size_t)(bt[b].x + rc) * KEY_LEVELS;
+                int lev = 0, n_in = 0;
+                for (int i = 0; i < S; ++i) {
+                    if (dots[i] < thresh) continue;
+                    // stars come in magnitude order: close every level this star is fainter than
+                    while (lev < KEY_LEVELS && smag[i] > KEY_M0 + (lev + 1) / 16.0f) kt[lev++] = (uint8_t)std::min(n_in, 255);
+                    list.push_back((uint16_t)order[i]);
+                    ++n_in;
+                }
+                while (lev < KEY_LEVELS) kt[lev++] = (uint8_t)std::min(n_in, 255);
+            }
             while ((list.size() - start) % 8) list.push_back((uint16_t)0xffff);
             if (list.size() > 0xfffffff0ull) return fail(STMPM_E_ARG, "candidate lists exceed 2^32 entries: field of view too wide");
             off[bt[b].x + rc + 1] = (uint32_t)list.size();
@@ -468,6 +564,9 @@ static int rebuild_lists(stmpm_handle* h) {
     h->lk_bands = nb;
     h->lk_cone = (float)cone;
     h->lk_entries = (long long)list.size();
+    cudaFree(h->lk_key); h->lk_key = nullptr;
+    CK(cudaMalloc(&h->lk_key, key_tab.size()));
+    CK(cudaMemcpy(h->lk_key, key_tab.data(), key_tab.size(), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -509,6 +608,7 @@ extern "C" int stmpm_destroy(stmpm_t* h) {
     cudaFree(h->cat32); cudaFree(h->cat64); cudaFree(h->cell_start); cudaFree(h->band_tab); cudaFree(h->dists);
     cudaFree(h->stage_stats); cudaFree(h->counters);
     cudaFree(h->lk_band_tab); cudaFree(h->lk_off); cudaFree(h->lk_list); cudaFree(h->tables);
+    cudaFree(h->lk_key);
     free_stage(h);
     for (int i = 0; i < stmpm_handle::NBUF; ++i) if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
     delete h;
@@ -640,7 +740,7 @@ extern "C" int stmpm_stats_finalize(int32_t hist_log2_sub, const double* s, stmp
 // ------------------------------------------------------------------------------------------------ launch helper
 template <int MODE, int PREC, int INSTR = 0>
 static int launch_trials(stmpm_handle* h, KArgs& a, cudaStream_t st) {
-    const SmemLayout L = smem_layout(a.n_stars, a.n_cells_pad, a.n_bands, a.lk_bands);
+    const SmemLayout L = smem_layout(a.n_stars, a.n_bands, a.lk_bands);
     if (L.total > (size_t)h->prop.sharedMemPerBlockOptin)
         return fail(STMPM_E_ARG, "catalog too large for shared-memory staging (" + std::to_string(L.total) + " B)");
     auto kern = trials_kernel<MODE, PREC, INSTR>;
@@ -650,15 +750,23 @@ static int launch_trials(stmpm_handle* h, KArgs& a, cudaStream_t st) {
         cached = L.total;
     }
     const int n_sm = h->prop.multiProcessorCount;
-    // work units: (segment, part). part_len is a multiple of TPB so every warp sees warp-uniform trip counts.
+    // work units: (segment, part).  Inside a unit each warp sorts + runs windows of `win` trials; small launches shrink
+    // the window so that all 16 warps of the CTAs in use have work.
     const long long tps = a.trials_per_segment;
-    const long long blocks_per_seg = (tps + TPB - 1) / TPB;
+    const long long total = tps * a.n_segments;
+    long long win = WIN_DEFAULT;
+    if (const char* e = getenv("STMPM_WIN")) win = std::max(32, std::min(WIN_MAX, atoi(e) / 32 * 32));   // tuning knob
+    const long long per_warp = (total + (long long)n_sm * (TPB / 32) - 1) / ((long long)n_sm * (TPB / 32));
+    if (per_warp < win) win = std::max(32LL, (per_warp + 31) / 32 * 32);
+    a.win = (int)win;
+    const long long cta_round = win * (TPB / 32);                    // trials one CTA covers per sweep of its warps
+    const long long rounds_per_seg = (tps + cta_round - 1) / cta_round;
     long long parts = 1;
-    if (a.n_segments < 4LL * n_sm) parts = std::max(1LL, std::min(blocks_per_seg, (4LL * n_sm + a.n_segments - 1) / a.n_segments));
-    const long long blocks_per_part = (blocks_per_seg + parts - 1) / parts;
-    parts = (blocks_per_seg + blocks_per_part - 1) / blocks_per_part;
+    if (a.n_segments < 4LL * n_sm) parts = std::max(1LL, std::min(rounds_per_seg, (4LL * n_sm + a.n_segments - 1) / a.n_segments));
+    const long long rounds_per_part = (rounds_per_seg + parts - 1) / parts;
+    parts = (rounds_per_seg + rounds_per_part - 1) / rounds_per_part;
     a.parts_per_segment = (int)parts;
-    a.part_len = blocks_per_part * TPB;
+    a.part_len = rounds_per_part * cta_round;
     const long long n_units = a.n_segments * parts;
     const int grid = (int)std::min<long long>(n_units, n_sm);
     if (grid <= 0) return 0;
@@ -679,6 +787,7 @@ static int fill_common(stmpm_handle* h, KArgs& a, int precision) {
     a.inv_band_h = (float)((double)h->n_bands / M_PI);
     a.lk_band_tab = h->lk_band_tab; a.lk_off = h->lk_off; a.lk_list = h->lk_list; a.lk_bands = h->lk_bands;
     a.lk_inv_band_h = (float)((double)h->lk_bands / M_PI); a.lk_cone = h->lk_cone; a.tables = h->tables;
+    a.lk_key = h->lk_key;
     a.f_ideal = h->cfg.f_ideal; a.half_u = h->cfg.half_u; a.half_v = h->cfg.half_v; a.n_min = h->cfg.n_min;
     a.hist_shift = 52 - h->cfg.hist_log2_sub; a.n_bins = h->n_bins;
     a.stats_len = STMPM_STATS_HEAD + h->n_bins;
@@ -747,7 +856,7 @@ extern "C" int stmpm_fill_presampled(stmpm_t* h, int64_t n, uint64_t seed, int64
     to_dev_dist(*dist, d);
     const int grid = (int)std::min<long long>((n + 255) / 256, (long long)h->prop.multiProcessorCount * 8);
     fill_presampled_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-        n, trial0, (uint32_t)seed, (uint32_t)(seed >> 32), d, cols[0], cols[1], cols[2], cols[3], cols[4], cols[5],
+        n, trial0, (uint32_t)seed, (uint32_t)(seed >> 32), d, h->tables, cols[0], cols[1], cols[2], cols[3], cols[4], cols[5],
         cols[6], cols[7], cols[8], cols[9], cols[10], cols[11], cols[12]);
     CK(cudaGetLastError());
     ++h->launches;

@@ -2,9 +2,12 @@
 //
 // Replaces the per-row body of Simulation.run_sim + quest_objective (called at /root/reference/monte_carlo.py:52 and
 // sensitivity.py:77; bodies absent from the mount).  One trial per thread:
-//   setup (fp64)  ->  phase A: candidate scan with an fp32 conservative pre-filter out of shared memory
-//                 ->  phase B: exact per-star projection + Philox centroid noise + detection + B accumulation
-//                 ->  QUEST Newton solve in the body frame + error angle (fp64).
+//   key pass : per warp, a window of up to 512 trials is ordered by its work key (the number of catalog candidates the
+//              trial will visit: a table look-up from boresight cell and MAX_MAGNITUDE) — warp-local counting sort,
+//              so the 32 trials a warp runs together do the same amount of work; keys never affect results
+//   set-up (fp64) -> phase A: candidate scan with a conservative fp32 pre-filter out of shared memory
+//                 -> phase B: exact per-star projection + Philox centroid noise + detection + B accumulation
+//                 -> QUEST Newton solve in the body frame + error angle.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -18,7 +21,12 @@
 namespace stmpm {
 
 constexpr int TPB = 512;          // threads per CTA (1 CTA / SM: the fp32 catalog lives in shared memory)
-constexpr int LIST_CAP = 64;      // per-thread candidate list length (phase A -> phase B hand-off)
+constexpr int LIST_CAP = 48;      // per-thread survivor list in shared memory (phase A -> phase B hand-off), drained in rounds
+constexpr int WIN_MAX = 512;      // largest warp-local sort window (trials)
+constexpr int WIN_DEFAULT = 128;  // default: 128 x 16 warps x 148 SMs x 104 B of permuted inputs stays L2-resident
+constexpr int KEY_LEVELS = 128;   // work-key table: candidate visits per lookup cell at magnitude levels KEY_M0 + (k+1)/16
+constexpr float KEY_M0 = 1.0f;
+constexpr int KEY_BINS = 64;      // sort bins (visits / 4)
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u, PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
 constexpr uint32_t PHILOX2_M = 0xD256D193u;
 constexpr uint32_t TAG_STAR = 0x53544152u, TAG_PARA = 0x50415241u;
@@ -88,11 +96,19 @@ STMPM_HD double u01(uint32_t w) { return ((double)w + 0.5) * TWO_M32; }
 // and small tables instead of libm's long polynomials: the star loop is FP64-pipe bound.
 //   ln:  2w+1 = m 2^p, m in [1,2); j = top 7 mantissa bits; r = m / c_j - 1, |r| <= 2^-8; ln m = ln c_j + log1p(r)
 //   sin/cos: quadrant = top 2 bits of w; 64 table intervals per quadrant; |d| <= pi/256 remainder by Taylor.
-struct MathTables {
-    double log_inv_c[128], log_ln_c[128];   // c_j = 1 + (j + 0.5) / 128
+struct __align__(16) MathTables {
+    double log_tab[128][2];                 // {1 / c_j, ln c_j},  c_j = 1 + (j + 0.5) / 128   (one 16-byte load)
+    double sc_tab[64][2];                   // {sin, cos} of (pi/2) (j + 0.5) / 64             (one 16-byte load)
     double k_ln2[34];                       // k * ln 2
-    double sc_sin[64], sc_cos[64];          // sin / cos of (pi/2) (j + 0.5) / 64
 };
+STMPM_HD void load2(const double* p, double& a, double& b) {
+#if defined(__CUDA_ARCH__)
+    const double2 v = *reinterpret_cast<const double2*>(p);
+    a = v.x; b = v.y;
+#else
+    a = p[0]; b = p[1];
+#endif
+}
 
 STMPM_HD double bits_to_double(unsigned long long b) {
 #if defined(__CUDA_ARCH__)
@@ -125,13 +141,15 @@ STMPM_HD void box_muller_tab(const MathTables* __restrict__ T, uint32_t wa, uint
     const unsigned long long frac = ((v << lz) << 1) >> 12;   // 52 mantissa bits of m (lz + 1 can be 64)
     const double m = bits_to_double(0x3FF0000000000000ull | frac);
     const int j = (int)(frac >> 45);
-    const double r = fma(m, T->log_inv_c[j], -1.0);
+    double inv_c, ln_c;
+    load2(T->log_tab[j], inv_c, ln_c);
+    const double r = fma(m, inv_c, -1.0);
     double p = fma(r, -1.0 / 6.0, 0.2);
     p = fma(r, p, -0.25);
     p = fma(r, p, 1.0 / 3.0);
     p = fma(r, p, -0.5);
     p = fma(r * r, p, r);                                     // log1p(r), |r| <= 2^-8: truncation < 2e-18
-    const double ln_u = (T->log_ln_c[j] + p) - T->k_ln2[lz - 30];   // k = 33 - p = lz - 30
+    const double ln_u = (ln_c + p) - T->k_ln2[lz - 30];   // k = 33 - p = lz - 30
     const double L = -2.0 * ln_u;
     const double R = L * fast_rsqrt(L);
     // ---- angle 2 pi u2 = (pi/2) (q + (64-interval j2 centre) ) + d
@@ -145,7 +163,8 @@ STMPM_HD void box_muller_tab(const MathTables* __restrict__ T, uint32_t wa, uint
     const double d2 = d * d;
     const double sd = fma(d * d2, fma(d2, 1.0 / 120.0, -1.0 / 6.0), d);
     const double cd = fma(d2, fma(d2, fma(d2, -1.0 / 720.0, 1.0 / 24.0), -0.5), 1.0);
-    const double S = T->sc_sin[j2], C = T->sc_cos[j2];
+    double S, C;
+    load2(T->sc_tab[j2], S, C);
     const double sn = fma(S, cd, C * sd);
     const double cs = fma(C, cd, -S * sd);
     // quadrant rotation: (cos, sin) -> q=0 (cs, sn); 1 (-sn, cs); 2 (-cs, -sn); 3 (sn, -cs)
@@ -167,31 +186,27 @@ __device__ __forceinline__ void box_muller_f(uint32_t wa, uint32_t wb, float& z1
     z1 = r * c;
     z2 = r * s;
 }
-__device__ __forceinline__ void box_muller_lib(uint32_t wa, uint32_t wb, double& z1, double& z2) {   // parameter draws
-    const double r = sqrt(-2.0 * log(u01(wa)));
-    double s, c;
-    sincospi(2.0 * u01(wb), &s, &c);
-    z1 = r * c;
-    z2 = r * s;
-}
 
-// Everything a trial needs after setup.  Inertial-frame plane vectors: NI = C n, EU = C e_u, EV = C e_v, so that for a
-// catalog vector s:  n.r = NI.s,  u = (n.p0 / NI.s) EU.s - e_u.p0,  v likewise  (r = C^T s never materialised).
-struct TrialCtx {
+// Everything phase B needs.  Inertial-frame plane vectors: NI = C n, EU = C e_u, EV = C e_v, so that for a catalog vector
+// s:  n.r = NI.s,  u = (n.p0 / NI.s) EU.s - e_u.p0,  v likewise  (r = C^T s never materialised).
+struct Ctx64 {
     double C[9];                  // body -> inertial, row-major
     double NI[3], EU[3], EV[3];
     double np0, cu, cv;           // n.p0, e_u.p0, e_v.p0
     double sx, sy;                // |BASE_DEV_X|, |BASE_DEV_Y|
-    float NIf[3], EUf[3], EVf[3], np0f, cuf, cvf, limu, limv, magf;
-    float ra0, dec0, cone, dalpha;   // scan geometry (fp32, conservative); dalpha < 0 => full circle
+};
+// Everything phase A (the conservative fp32 candidate scan) needs.
+struct Ctx32 {
+    float NI[3], EU[3], EV[3], np0, cu, cv, limu, limv, magf;
+    float ra0, dec0, cone;        // boresight (lookup-cell key) and scan-cone half angle
 };
 
-__device__ __forceinline__ float opaque(float x) {   // stop ptxas re-deriving the fp32 copy from the fp64 value at
-    asm volatile("" : "+f"(x));                       // every use (F2F conversions run on the 16-lane XU pipe)
+__device__ __forceinline__ float opaque(float x) {   // stop ptxas re-deriving an fp32 copy from its fp64 source at every
+    asm volatile("" : "+f"(x));                       // use (F2F conversions run on the 16-lane XU pipe)
     return x;
 }
 
-__device__ __forceinline__ void trial_setup(const TrialParams& p, double half_u, double half_v, TrialCtx& c) {
+__device__ __forceinline__ void setup64(const TrialParams& p, Ctx64& c) {
     double sa, ca, sd, cd, sr, cr;
     sincos(p.ra, &sa, &ca);
     sincos(p.dec, &sd, &cd);
@@ -217,46 +232,91 @@ __device__ __forceinline__ void trial_setup(const TrialParams& p, double half_u,
         c.NI[i] = c.C[3 * i] * nn[0] + c.C[3 * i + 1] * nn[1] + c.C[3 * i + 2] * nn[2];
         c.EU[i] = c.C[3 * i] * eu[0] + c.C[3 * i + 1] * eu[1] + c.C[3 * i + 2] * eu[2];
         c.EV[i] = c.C[3 * i] * ev[0] + c.C[3 * i + 1] * ev[1] + c.C[3 * i + 2] * ev[2];
-        c.NIf[i] = opaque((float)c.NI[i]);
-        c.EUf[i] = opaque((float)c.EU[i]);
-        c.EVf[i] = opaque((float)c.EV[i]);
     }
     c.sx = fabs(p.devx);
     c.sy = fabs(p.devy);
-    c.np0f = opaque((float)c.np0);
-    c.cuf = opaque((float)c.cu);
-    c.cvf = opaque((float)c.cv);
-    // conservative pre-filter window: Box-Muller with 32-bit u1 has |z| <= sqrt(-2 ln 2^-33) = 6.77; fp32 slack
-    const float ff = (float)fabs(p.f);
-    const float noise = 6.8f * fmaxf((float)c.sx, (float)c.sy) + 0.02f + 4e-6f * ff;
-    c.limu = opaque((float)half_u + noise);
-    c.limv = opaque((float)half_v + noise);
+}
+
+// pre-filter window and scan cone shared by both fp32 set-ups.  Window = array + 6.8 sigma_centroid (Box-Muller with a
+// 32-bit u1 has |z| <= sqrt(-2 ln 2^-33) = 6.77) + slack for fp32 rounding of the projection (~1e-3 px at f = 3500).
+// Cone: every point of the (tilted, shifted, noise-padded) array lies within atan(reach / depth) of the boresight.
+__device__ __forceinline__ void window_and_cone(const TrialParams& p, float half_u, float half_v, Ctx32& c) {
+    const float ff = fabsf((float)p.f);
+    const float noise = 6.8f * fmaxf(fabsf((float)p.devx), fabsf((float)p.devy)) + 0.05f + 1e-5f * ff;
+    c.limu = opaque(half_u + noise);
+    c.limv = opaque(half_v + noise);
     c.magf = opaque(__double2float_rd(p.maxmag));   // (double)mag <= maxmag  <=>  mag <= round-down-to-float(maxmag)
-    // scan cone about the boresight (= third column of C): every point of the (tilted, shifted, noise-padded) array
-    // lies within atan(reach / depth) of +z  (MODEL.md §8: acceleration only)
-    const float reach = 1.41421357f * (fmaxf((float)half_u, (float)half_v) + noise)
-                        + hypotf((float)p.ex, (float)p.ey) + 1.0f;
-    const float tilt = fminf(((float)fabs(p.phi) + (float)fabs(p.theta)) * 0.0174532925f, 0.5f);
+    const float reach = 1.41421357f * (fmaxf(half_u, half_v) + noise) + hypotf((float)p.ex, (float)p.ey) + 1.0f;
+    const float tilt = fminf((fabsf((float)p.phi) + fabsf((float)p.theta)) * 0.0174532925f, 0.5f);
     const float depth = (float)p.f + (float)p.ez - reach * tilt;
     c.cone = (depth > 1.0f) ? atanf(reach / depth) + 0.002f : 3.2f;
-    c.dec0 = asinf(fminf(fmaxf((float)c.C[8], -1.0f), 1.0f));
-    float a0 = atan2f((float)c.C[5], (float)c.C[2]);
+}
+
+// fp32 context derived from the fp64 one (pass 2: overflow / wide-cone trials, and the fp32 precision mode)
+__device__ __forceinline__ void derive32(const TrialParams& p, const Ctx64& d, float half_u, float half_v, Ctx32& c) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        c.NI[i] = opaque((float)d.NI[i]);
+        c.EU[i] = opaque((float)d.EU[i]);
+        c.EV[i] = opaque((float)d.EV[i]);
+    }
+    c.np0 = opaque((float)d.np0);
+    c.cu = opaque((float)d.cu);
+    c.cv = opaque((float)d.cv);
+    window_and_cone(p, half_u, half_v, c);
+    c.dec0 = asinf(fminf(fmaxf((float)d.C[8], -1.0f), 1.0f));
+    const float a0 = atan2f((float)d.C[5], (float)d.C[2]);
     c.ra0 = a0 < 0.0f ? a0 + 6.28318531f : a0;
-    if (fabsf(c.dec0) + c.cone >= 1.5607963f) c.dalpha = -1.0f;
-    else c.dalpha = asinf(fminf(sinf(c.cone) / cosf(c.dec0), 1.0f)) + 0.002f;
+}
+
+// fp32 context straight from the parameters (pass 1): fp32 sincosf of the fp32-rounded angles.  Angle errors ~|x| 6e-8
+// move a star by < 0.03 px for |x| <= 64 rad, inside the window slack; larger arguments are refused (caller takes the
+// fp64-derived path).  Returns false when the trial must take that path.
+__device__ __forceinline__ bool setup32(const TrialParams& p, float half_u, float half_v, Ctx32& c) {
+    const float ra = (float)p.ra, dec = (float)p.dec, roll = (float)p.roll;
+    if (!(fabsf(ra) <= 64.0f && fabsf(dec) <= 64.0f && fabsf(roll) <= 64.0f)) return false;
+    float sa, ca, sd, cd, sr, cr, sp, cp, st, ct, ss, cs;
+    sincosf(ra, &sa, &ca);
+    sincosf(dec, &sd, &cd);
+    sincosf(roll, &sr, &cr);
+    sincosf((float)p.phi * 0.0174532925f, &sp, &cp);
+    sincosf((float)p.theta * 0.0174532925f, &st, &ct);
+    sincosf((float)p.psi * 0.0174532925f, &ss, &cs);
+    const float C[9] = {ca * sd * cr - sa * sr, -ca * sd * sr - sa * cr, ca * cd,
+                        sa * sd * cr + ca * sr, -sa * sd * sr + ca * cr, sa * cd,
+                        -cd * cr, cd * sr, sd};
+    const float eu[3] = {ct * cs, cp * ss + sp * st * cs, sp * ss - cp * st * cs};
+    const float ev[3] = {-ct * ss, cp * cs - sp * st * ss, sp * cs + cp * st * ss};
+    const float nn[3] = {st, -sp * ct, cp * ct};
+    const float p0[3] = {(float)p.ex, (float)p.ey, (float)p.f + (float)p.ez};
+    c.np0 = nn[0] * p0[0] + nn[1] * p0[1] + nn[2] * p0[2];
+    c.cu = eu[0] * p0[0] + eu[1] * p0[1] + eu[2] * p0[2];
+    c.cv = ev[0] * p0[0] + ev[1] * p0[1] + ev[2] * p0[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        c.NI[i] = C[3 * i] * nn[0] + C[3 * i + 1] * nn[1] + C[3 * i + 2] * nn[2];
+        c.EU[i] = C[3 * i] * eu[0] + C[3 * i + 1] * eu[1] + C[3 * i + 2] * eu[2];
+        c.EV[i] = C[3 * i] * ev[0] + C[3 * i + 1] * ev[1] + C[3 * i + 2] * ev[2];
+    }
+    window_and_cone(p, half_u, half_v, c);
+    // boresight = third column of C; its (ra, dec) key the lookup grid
+    c.dec0 = asinf(fminf(fmaxf(C[8], -1.0f), 1.0f));
+    const float a0 = atan2f(C[5], C[2]);
+    c.ra0 = a0 < 0.0f ? a0 + 6.28318531f : a0;
+    return true;
 }
 
 // fp32 conservative geometric pre-filter on one shared-memory catalog entry (x, y, z, mag); magnitude tested by caller
-__device__ __forceinline__ bool prefilter_geom(const TrialCtx& c, const float4 s) {
-    const float dn = c.NIf[0] * s.x + c.NIf[1] * s.y + c.NIf[2] * s.z;
-    const float rl = __fdividef(c.np0f, dn);
-    const float u = fmaf(rl, c.EUf[0] * s.x + c.EUf[1] * s.y + c.EUf[2] * s.z, -c.cuf);
-    const float v = fmaf(rl, c.EVf[0] * s.x + c.EVf[1] * s.y + c.EVf[2] * s.z, -c.cvf);
+__device__ __forceinline__ bool prefilter_geom(const Ctx32& c, const float4 s) {
+    const float dn = c.NI[0] * s.x + c.NI[1] * s.y + c.NI[2] * s.z;
+    const float rl = __fdividef(c.np0, dn);
+    const float u = fmaf(rl, c.EU[0] * s.x + c.EU[1] * s.y + c.EU[2] * s.z, -c.cu);
+    const float v = fmaf(rl, c.EV[0] * s.x + c.EV[1] * s.y + c.EV[2] * s.z, -c.cv);
     return dn > 0.02f && fabsf(u) <= c.limu && fabsf(v) <= c.limv;
 }
 
 // Exact (fp64) star evaluation: MODEL.md §2-§4. Returns detected?; on detection adds b s^T into B.
-__device__ __forceinline__ bool star_exact(const TrialCtx& c, const MathTables* __restrict__ T, const StarRec& s,
+__device__ __forceinline__ bool star_exact(const Ctx64& c, const MathTables* __restrict__ T, const StarRec& s,
                                            uint32_t ka, uint32_t kb, double f_ideal, double half_u, double half_v,
                                            double* __restrict__ B) {
     const double dn = c.NI[0] * s.x + c.NI[1] * s.y + c.NI[2] * s.z;
@@ -285,22 +345,22 @@ __device__ __forceinline__ bool star_exact(const TrialCtx& c, const MathTables* 
 // centroid lies inside a guard band around the array edge, so detection counts stay bit-exact with the fp64 oracle;
 // (b) B is accumulated in fp64 against the fp64 reference vector — roll about the boresight is ~1/sin(FOV/2) less
 // observable than pointing, and fp32 partial sums of B (ulp ~1e-6 at |B| ~ 16) would cost ~1e-6 rad of roll.
-__device__ __forceinline__ bool star_f32(const TrialCtx& c, const MathTables* __restrict__ T, const StarRec& s,
-                                         uint32_t ka, uint32_t kb, double f_ideal, double half_u, double half_v,
-                                         double* __restrict__ B) {
+__device__ __forceinline__ bool star_f32(const Ctx64& c, const Ctx32& cf, const MathTables* __restrict__ T,
+                                         const StarRec& s, uint32_t ka, uint32_t kb, double f_ideal, double half_u,
+                                         double half_v, double* __restrict__ B) {
     const float sx = (float)s.x, sy = (float)s.y, sz = (float)s.z;
-    const float dn = c.NIf[0] * sx + c.NIf[1] * sy + c.NIf[2] * sz;
-    const float du = c.EUf[0] * sx + c.EUf[1] * sy + c.EUf[2] * sz;
-    const float dv = c.EVf[0] * sx + c.EVf[1] * sy + c.EVf[2] * sz;
-    const float lam = c.np0f / dn;
+    const float dn = cf.NI[0] * sx + cf.NI[1] * sy + cf.NI[2] * sz;
+    const float du = cf.EU[0] * sx + cf.EU[1] * sy + cf.EU[2] * sz;
+    const float dv = cf.EV[0] * sx + cf.EV[1] * sy + cf.EV[2] * sz;
+    const float lam = cf.np0 / dn;
     uint32_t x0, x1;
     philox2x32_10(s.star_id, kb, ka, x0, x1);
     float z1, z2;
     box_muller_f(x0, x1, z1, z2);
-    const float um = fmaf((float)c.sx, z1, fmaf(lam, du, -c.cuf));
-    const float vm = fmaf((float)c.sy, z2, fmaf(lam, dv, -c.cvf));
+    const float um = fmaf((float)c.sx, z1, fmaf(lam, du, -cf.cu));
+    const float vm = fmaf((float)c.sy, z2, fmaf(lam, dv, -cf.cv));
     const float hu = (float)half_u, hv = (float)half_v;
-    const float guard = 0.05f + 1e-5f * fabsf(c.np0f) + 1e-4f * ((float)c.sx + (float)c.sy);
+    const float guard = 0.05f + 1e-5f * fabsf(cf.np0) + 1e-4f * ((float)c.sx + (float)c.sy);
     if (!(dn > 0.02f) || fabsf(fabsf(um) - hu) <= guard || fabsf(fabsf(vm) - hv) <= guard)
         return star_exact(c, T, s, ka, kb, f_ideal, half_u, half_v, B);   // rare: exact decision + exact b
     const bool det = (fabsf(um) <= hu) && (fabsf(vm) <= hv);
@@ -362,8 +422,8 @@ __device__ __forceinline__ double quest_error_arcsec(const double* __restrict__ 
 struct DistDev {
     double mean[11], sigma[11], thermal_coef;
 };
-__device__ __forceinline__ void sample_params(const DistDev& d, uint32_t t_lo, uint32_t t_hi, uint32_t k0, uint32_t k1,
-                                              TrialParams& p) {
+__device__ __forceinline__ void sample_params(const DistDev& d, const MathTables* __restrict__ T, uint32_t t_lo,
+                                              uint32_t t_hi, uint32_t k0, uint32_t k1, TrialParams& p) {
     uint32_t w[16];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -375,7 +435,7 @@ __device__ __forceinline__ void sample_params(const DistDev& d, uint32_t t_lo, u
     p.roll = -PI + 2.0 * PI * u01(w[2]);
     double z[12];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) box_muller_lib(w[4 + 2 * k], w[5 + 2 * k], z[2 * k], z[2 * k + 1]);
+    for (int k = 0; k < 6; ++k) box_muller_tab(T, w[4 + 2 * k], w[5 + 2 * k], z[2 * k], z[2 * k + 1]);
     const double F = d.mean[0] + d.sigma[0] * z[0];
     p.ex = d.mean[1] + d.sigma[1] * z[1];
     p.ey = d.mean[2] + d.sigma[2] * z[2];
@@ -388,6 +448,20 @@ __device__ __forceinline__ void sample_params(const DistDev& d, uint32_t t_lo, u
     p.maxmag = d.mean[9] + d.sigma[9] * z[9];
     const double dtemp = d.mean[10] + d.sigma[10] * z[10];
     p.f = F * (1.0 + dtemp * d.thermal_coef);   // sensitivity.py:115-117
+}
+// ra, dec, MAX_MAGNITUDE of a native-RNG trial only (the work key needs nothing else): Philox blocks 0 and 3
+__device__ __forceinline__ void sample_key_params(const DistDev& d, const MathTables* __restrict__ T, uint32_t t_lo,
+                                                  uint32_t t_hi, uint32_t k0, uint32_t k1, double& ra, double& dec,
+                                                  double& maxmag) {
+    uint32_t w0, w1, w2, w3, v0, v1, v2, v3;
+    philox4x32_10(t_lo, t_hi, 0u, TAG_PARA, k0, k1, w0, w1, w2, w3);
+    philox4x32_10(t_lo, t_hi, 3u, TAG_PARA, k0, k1, v0, v1, v2, v3);
+    const double fov = 0.17453292519943295, PI = 3.141592653589793;
+    ra = fov + (2.0 * PI - 2.0 * fov) * u01(w0);
+    dec = (-0.5 * PI + fov) + (PI - 2.0 * fov) * u01(w1);
+    double z8, z9;
+    box_muller_tab(T, v0, v1, z8, z9);      // words 12, 13 -> normals 8, 9
+    maxmag = d.mean[9] + d.sigma[9] * z9;
 }
 #endif  // __CUDACC__
 
