@@ -1,4 +1,4 @@
 #!/bin/bash
-for w in 64 128 256 512; do
+for w in ${WINS:-64 128}; do
   STMPM_WIN=$w timeout 200 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-trials 1e6 2>&1 | tail -1 | python scripts/bench_value.py "win=$w"
 done

@@ -16,6 +16,7 @@ import numpy as np
 CATALOG_SEED = 20231105
 CATALOG_SIZE = 9110
 MAG_MIN, MAG_MAX, MAG_SLOPE = -1.5, 7.0, 0.5
+DEFAULT_CELL_DEG = 3.0
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_CATALOG_PATH = os.path.join(_HERE, "utils", "catalog_synth_9110.npz")
@@ -35,9 +36,12 @@ def generate_catalog(n: int = CATALOG_SIZE, seed: int = CATALOG_SEED):
 
 
 def save_catalog(path: str = DEFAULT_CATALOG_PATH, n: int = CATALOG_SIZE, seed: int = CATALOG_SEED) -> None:
+    """The committed file is stored in sky-grid order (DEFAULT_CELL_DEG), so star_id == row index == position in the
+    sorted device catalog: the kernels then take the Philox star key straight from their candidate lists."""
     xyz, mag = generate_catalog(n, seed)
+    g = build_sky_grid(xyz, mag, DEFAULT_CELL_DEG)
     os.makedirs(os.path.dirname(path), exist_ok=True)
-    np.savez(path, xyz=xyz, mag=mag, seed=np.int64(seed))
+    np.savez(path, xyz=g.xyz, mag=g.mag, seed=np.int64(seed))
 
 
 def load_catalog(path: str | None = None):
@@ -72,7 +76,7 @@ class SkyGrid:
         return int(self.xyz.shape[0])
 
 
-def build_sky_grid(xyz: np.ndarray, mag: np.ndarray, cell_deg: float = 3.0) -> SkyGrid:
+def build_sky_grid(xyz: np.ndarray, mag: np.ndarray, cell_deg: float = DEFAULT_CELL_DEG) -> SkyGrid:
     xyz = np.ascontiguousarray(xyz, dtype=np.float64)
     mag = np.ascontiguousarray(mag, dtype=np.float32)
     S = xyz.shape[0]

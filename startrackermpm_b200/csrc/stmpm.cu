@@ -312,9 +312,13 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
                             const double2* g = reinterpret_cast<const double2*>(a.cat64 + s_list[(j + 1) * TPB]);
                             r_lo = __ldg(g); r_hi = __ldg(g + 1);
                         }
+                        // (hand-pipelining Philox one star ahead, or two stars per iteration, both measured slower:
+                        // ptxas already overlaps the integer chain with the fp64 one, and extra live state spills)
+                        uint32_t x0, x1;
+                        philox2x32_10(s.star_id, kb, ka, x0, x1);
                         bool det;
-                        if (PREC == 64) det = star_exact(c, s_tab, s, ka, kb, a.f_ideal, a.half_u, a.half_v, B);
-                        else det = star_f32(c, cf, s_tab, s, ka, kb, a.f_ideal, a.half_u, a.half_v, B);
+                        if (PREC == 64) det = star_exact(c, s_tab, s, x0, x1, a.f_ideal, a.half_u, a.half_v, B);
+                        else det = star_f32(c, cf, s_tab, s, x0, x1, a.f_ideal, a.half_u, a.half_v, B);
                         n_det += det ? 1 : 0;
                     }
                     cnt = 0;
@@ -666,6 +670,7 @@ extern "C" int stmpm_set_catalog(stmpm_t* h, const double* xyz, const float* mag
     CK(cudaMemcpy(h->cell_start, cs.data(), sizeof(uint16_t) * n_pad, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->band_tab, bt.data(), sizeof(int2) * n_bands, cudaMemcpyHostToDevice));
     h->n_stars = n_stars; h->n_cells_pad = n_pad; h->n_bands = n_bands;
+
     h->h_xyzf.resize((size_t)3 * n_stars);
     h->h_mag.assign(mag, mag + n_stars);
     for (int i = 0; i < 3 * n_stars; ++i) h->h_xyzf[i] = (float)xyz[i];
@@ -747,6 +752,9 @@ static int launch_trials(stmpm_handle* h, KArgs& a, cudaStream_t st) {
     size_t& cached = h->smem_attr_set[MODE][PREC == 64 ? 0 : 1][INSTR];
     if (cached < L.total) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+        // leave the rest of the unified array to L1: register spills and the permuted input gathers live there
+        const int pct = (int)std::min<size_t>(100, (L.total + 1024) * 100 / (size_t)h->prop.sharedMemPerMultiprocessor + 1);
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
         cached = L.total;
     }
     const int n_sm = h->prop.multiProcessorCount;

@@ -22,7 +22,7 @@ namespace stmpm {
 
 constexpr int TPB = 512;          // threads per CTA (1 CTA / SM: the fp32 catalog lives in shared memory)
 constexpr int LIST_CAP = 48;      // per-thread survivor list in shared memory (phase A -> phase B hand-off), drained in rounds
-constexpr int WIN_MAX = 512;      // largest warp-local sort window (trials)
+constexpr int WIN_MAX = 128;      // largest warp-local sort window (trials)
 constexpr int WIN_DEFAULT = 128;  // default: 128 x 16 warps x 148 SMs x 104 B of permuted inputs stays L2-resident
 constexpr int KEY_LEVELS = 128;   // work-key table: candidate visits per lookup cell at magnitude levels KEY_M0 + (k+1)/16
 constexpr float KEY_M0 = 1.0f;
@@ -316,15 +316,14 @@ __device__ __forceinline__ bool prefilter_geom(const Ctx32& c, const float4 s) {
 }
 
 // Exact (fp64) star evaluation: MODEL.md §2-§4. Returns detected?; on detection adds b s^T into B.
+// (x0, x1) = the star's Philox2x32-10 words (MODEL.md §5), computed by the caller.
 __device__ __forceinline__ bool star_exact(const Ctx64& c, const MathTables* __restrict__ T, const StarRec& s,
-                                           uint32_t ka, uint32_t kb, double f_ideal, double half_u, double half_v,
+                                           uint32_t x0, uint32_t x1, double f_ideal, double half_u, double half_v,
                                            double* __restrict__ B) {
     const double dn = c.NI[0] * s.x + c.NI[1] * s.y + c.NI[2] * s.z;
     const double du = c.EU[0] * s.x + c.EU[1] * s.y + c.EU[2] * s.z;
     const double dv = c.EV[0] * s.x + c.EV[1] * s.y + c.EV[2] * s.z;
     const double lam = c.np0 / dn;
-    uint32_t x0, x1;
-    philox2x32_10(s.star_id, kb, ka, x0, x1);
     double z1, z2;
     box_muller_tab(T, x0, x1, z1, z2);
     const double um = fma(c.sx, z1, fma(lam, du, -c.cu));
@@ -346,15 +345,13 @@ __device__ __forceinline__ bool star_exact(const Ctx64& c, const MathTables* __r
 // (b) B is accumulated in fp64 against the fp64 reference vector — roll about the boresight is ~1/sin(FOV/2) less
 // observable than pointing, and fp32 partial sums of B (ulp ~1e-6 at |B| ~ 16) would cost ~1e-6 rad of roll.
 __device__ __forceinline__ bool star_f32(const Ctx64& c, const Ctx32& cf, const MathTables* __restrict__ T,
-                                         const StarRec& s, uint32_t ka, uint32_t kb, double f_ideal, double half_u,
+                                         const StarRec& s, uint32_t x0, uint32_t x1, double f_ideal, double half_u,
                                          double half_v, double* __restrict__ B) {
     const float sx = (float)s.x, sy = (float)s.y, sz = (float)s.z;
     const float dn = cf.NI[0] * sx + cf.NI[1] * sy + cf.NI[2] * sz;
     const float du = cf.EU[0] * sx + cf.EU[1] * sy + cf.EU[2] * sz;
     const float dv = cf.EV[0] * sx + cf.EV[1] * sy + cf.EV[2] * sz;
     const float lam = cf.np0 / dn;
-    uint32_t x0, x1;
-    philox2x32_10(s.star_id, kb, ka, x0, x1);
     float z1, z2;
     box_muller_f(x0, x1, z1, z2);
     const float um = fmaf((float)c.sx, z1, fmaf(lam, du, -cf.cu));
@@ -362,7 +359,7 @@ __device__ __forceinline__ bool star_f32(const Ctx64& c, const Ctx32& cf, const 
     const float hu = (float)half_u, hv = (float)half_v;
     const float guard = 0.05f + 1e-5f * fabsf(cf.np0) + 1e-4f * ((float)c.sx + (float)c.sy);
     if (!(dn > 0.02f) || fabsf(fabsf(um) - hu) <= guard || fabsf(fabsf(vm) - hv) <= guard)
-        return star_exact(c, T, s, ka, kb, f_ideal, half_u, half_v, B);   // rare: exact decision + exact b
+        return star_exact(c, T, s, x0, x1, f_ideal, half_u, half_v, B);   // rare: exact decision + exact b
     const bool det = (fabsf(um) <= hu) && (fabsf(vm) <= hv);
     if (det) {
         const float fi = (float)f_ideal;

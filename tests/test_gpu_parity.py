@@ -213,3 +213,17 @@ def test_full_size_properties(engine):
     ok = err >= 0
     assert st[0] == int(ok.sum()) and st[4] == int(ndet.sum(dtype=torch.int64))
     assert st[2] == pytest.approx(float(err[ok].sum()), rel=1e-9) and st[5] == float(err.max())
+
+
+def test_custom_catalog_with_non_identity_star_ids(lib_built, catalog):
+    """A catalog file in arbitrary row order: star ids (Philox keys) are file rows, not sky-grid positions."""
+    from startrackermpm_b200.engine import TrialEngine
+    xyz, mag = catalog
+    perm = np.random.default_rng(5).permutation(len(mag))[:6000]             # also a different catalog size
+    eng = TrialEngine(0, catalog=(xyz[perm], mag[perm]), f_ideal=F)
+    assert not np.array_equal(eng.grid.star_id, np.arange(len(perm)))
+    cols = trial.sample_params(dict(BASIC_MEAN, MAX_MAGNITUDE=6.6), BASIC_SIGMA, THERMAL_COEF, 77, 0, 6000)
+    e_ref, d_ref = trial.run_trials(cols, xyz[perm], mag[perm], F, 77, 0)
+    for prec in (64, 32):
+        compare(*eng.run_presampled(cols, 77, 0, precision=prec), e_ref, d_ref, prec)
+    eng.close()
