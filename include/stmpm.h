@@ -97,6 +97,12 @@ int stmpm_trials_presampled(stmpm_t* h, int precision, int64_t n, uint64_t seed,
                             const double* const* cols_dev, double* err_arcsec_dev, int32_t* n_det_dev,
                             double* stats_dev, void* stream);
 
+/* Same, plus the star_mag objective's output (driver.py:246-247, column 'MAXIMUM MAGNITUDE VISIBLE', toolplot.py:241):
+ * maxmag_dev[n] (optional) = catalog magnitude of the faintest detected star of each trial, -inf if none was detected. */
+int stmpm_trials_presampled_ex(stmpm_t* h, int precision, int64_t n, uint64_t seed, int64_t trial0,
+                               const double* const* cols_dev, double* err_arcsec_dev, int32_t* n_det_dev,
+                               float* maxmag_dev, double* stats_dev, void* stream);
+
 /* (2) Native-RNG mode == MonteCarlo.create_data + Simulation.run_sim fused (monte_carlo.py:48-58): parameters are drawn
  * on the device from Philox streams keyed by (seed, global trial index).  n_segments independent parameter sets (a
  * sensitivity grid point / an orbit step: sensitivity.py:39-55) of trials_per_segment trials each; segment s uses
@@ -117,6 +123,9 @@ int stmpm_fill_presampled(stmpm_t* h, int64_t n, uint64_t seed, int64_t trial0, 
 int stmpm_run_presampled_host(stmpm_t* h, int precision, int64_t n, uint64_t seed, int64_t trial0,
                               const double* const* cols_host, double* err_arcsec_host, int32_t* n_det_host,
                               double* stats_host);
+int stmpm_run_presampled_host_ex(stmpm_t* h, int precision, int64_t n, uint64_t seed, int64_t trial0,
+                                 const double* const* cols_host, double* err_arcsec_host, int32_t* n_det_host,
+                                 float* maxmag_host, double* stats_host);
 int stmpm_run_rng_host(stmpm_t* h, int precision, int64_t n_segments, int64_t trials_per_segment, uint64_t seed,
                        int64_t trial0, const stmpm_dist* dists_host, double* err_arcsec_host, int32_t* n_det_host,
                        double* stats_host);

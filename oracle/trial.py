@@ -162,7 +162,7 @@ def run_trials(cols, cat_xyz, cat_mag, f_ideal, seed, trial0=0, *, brute=False, 
     cat_mag64 = np.asarray(cat_mag, dtype=np.float32).astype(np.float64)
     err = np.empty(n, dtype=np.float64)
     ndet = np.empty(n, dtype=np.int32)
-    aux = {"n_cand": 0, "lam": np.empty(n)} if return_aux else None
+    aux = {"n_cand": 0, "lam": np.empty(n), "maxmag": np.empty(n, dtype=np.float32)} if return_aux else None
     star_ids = np.arange(cat_xyz.shape[0], dtype=np.uint64) if star_ids is None else np.asarray(star_ids, np.uint64)
     for s0 in range(0, n, chunk):
         sl = slice(s0, min(n, s0 + chunk))
@@ -172,6 +172,7 @@ def run_trials(cols, cat_xyz, cat_mag, f_ideal, seed, trial0=0, *, brute=False, 
         if return_aux:
             aux["n_cand"] += a["n_cand"]
             aux["lam"][sl] = a["lam"]
+            aux["maxmag"][sl] = a["maxmag"]
     return (err, ndet, aux) if return_aux else (err, ndet)
 
 
@@ -227,7 +228,11 @@ def _run_chunk(cols, cat_xyz, cat_mag64, star_ids, f_ideal, seed, trial_idx, bru
         dA = quat_to_dcm(q) @ C                            # A_est * A_true^T,  A_true = C^T
         theta_err = rotation_angle(dA)
     err = np.where(ok, theta_err * RAD2ARCSEC, -1.0)
-    return err, ndet, {"n_cand": int(cand.sum()), "lam": lam_max}
+    # star_mag objective (driver.py:246-247; output 'MAXIMUM MAGNITUDE VISIBLE', toolplot.py:241): catalog magnitude of
+    # the faintest detected star, -inf when nothing is detected
+    maxmag = np.full(m, -np.inf, dtype=np.float32)
+    np.maximum.at(maxmag, td, cat_mag64[si[det]].astype(np.float32))
+    return err, ndet, {"n_cand": int(cand.sum()), "lam": lam_max, "maxmag": maxmag}
 
 
 # ---------------------------------------------------------------- native-RNG parameter sampling (MODEL.md §6)

@@ -43,6 +43,7 @@ struct KArgs {
     DistDev dist0;                // the single segment's distribution (n_segments == 1): no device buffer to race on
     double* err;
     int* ndet;
+    float* maxmag;                // optional: magnitude of the faintest detected star (-inf if none) — star_mag objective
     double* stats;
     long long stats_len;
     unsigned long long* counters;   // INSTR only: [visits, mag_pass, survivors, detected]
@@ -85,10 +86,10 @@ __device__ __forceinline__ bool scan_list(const Ctx32& c, const float4* __restri
             const uint32_t idx = (w4[e >> 1] >> (16 * (e & 1))) & 0xffffu;
             if (idx == 0xffffu) return true;
             const float4 sc = s_cat[idx];
-            if (INSTR) ++ins[0];
+            if (INSTR == 1) ++ins[0];
             if (!(sc.w <= c.magf)) return true;          // sorted by magnitude: every later star is fainter still
-            if (INSTR) ++ins[1];
-            if (prefilter_geom(c, sc)) { row[cnt * TPB] = (uint16_t)idx; ++cnt; if (INSTR) ++ins[2]; }
+            if (INSTR == 1) ++ins[1];
+            if (prefilter_geom(c, sc)) { row[cnt * TPB] = (uint16_t)idx; ++cnt; if (INSTR == 1) ++ins[2]; }
         }
         if (lk >= lk_len) return true;
     }
@@ -105,6 +106,7 @@ __device__ __forceinline__ int lookup_cell(const int2* __restrict__ s_lkband, in
 // ------------------------------------------------------------------------------------------------ the trial kernel
 // MODE 0: pre-sampled columns.  MODE 1: native RNG.  PREC 64 / 32: per-star arithmetic.
 // INSTR 1: also count candidate visits / magnitude passes / pre-filter survivors (work-model calibration, not timed).
+// INSTR 2: also record the faintest detected star's magnitude (star_mag objective).
 template <int MODE, int PREC, int INSTR>
 __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const SmemLayout L) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -257,6 +259,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
                 }
                 bool scanning = valid;
                 int cnt = 0, n_det = 0;
+                float mag_faintest = -INFINITY;
                 double B[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 
                 do {
@@ -288,9 +291,9 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
                                     continue;
                                 }
                                 const float4 sc = s_cat[i];
-                                if (INSTR) { ++ins[0]; if (sc.w <= cf.magf) ++ins[1]; }
+                                if (INSTR == 1) { ++ins[0]; if (sc.w <= cf.magf) ++ins[1]; }
                                 if (sc.w <= cf.magf && prefilter_geom(cf, sc)) {
-                                    s_list[cnt * TPB] = (uint16_t)i; ++cnt; if (INSTR) ++ins[2];
+                                    s_list[cnt * TPB] = (uint16_t)i; ++cnt; if (INSTR == 1) ++ins[2];
                                 }
                                 ++i;
                             }
@@ -308,6 +311,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
                         StarRec s;
                         s.x = r_lo.x; s.y = r_lo.y; s.z = r_hi.x;
                         s.star_id = (uint32_t)(__double_as_longlong(r_hi.y) & 0xffffffffll);
+                        if (INSTR == 2) s.mag = __int_as_float((int)(__double_as_longlong(r_hi.y) >> 32));
                         if (j + 1 < cnt) {
                             const double2* g = reinterpret_cast<const double2*>(a.cat64 + s_list[(j + 1) * TPB]);
                             r_lo = __ldg(g); r_hi = __ldg(g + 1);
@@ -320,6 +324,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
                         if (PREC == 64) det = star_exact(c, s_tab, s, x0, x1, a.f_ideal, a.half_u, a.half_v, B);
                         else det = star_f32(c, cf, s_tab, s, x0, x1, a.f_ideal, a.half_u, a.half_v, B);
                         n_det += det ? 1 : 0;
+                        if (INSTR == 2 && det) mag_faintest = fmaxf(mag_faintest, s.mag);
                     }
                     cnt = 0;
                 } while (__any_sync(0xffffffffu, scanning));
@@ -328,9 +333,10 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
                 double err = -1.0;
                 if (n_det >= a.n_min) err = quest_error_arcsec(B, c.C, n_det);
                 if (valid) {
-                    if (INSTR) ins[3] += (unsigned long long)n_det;
+                    if (INSTR == 1) ins[3] += (unsigned long long)n_det;
                     if (a.err) a.err[rec] = err;
                     if (a.ndet) a.ndet[rec] = n_det;
+                    if (INSTR == 2 && a.maxmag) a.maxmag[rec] = mag_faintest;
                     if (want_stats) {
                         acc_ndet += (unsigned long long)n_det;
                         if (err >= 0.0) {
@@ -354,7 +360,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
             __syncwarp();   // the window buffers are reused by this warp's next window
         }
 
-        if (INSTR) {
+        if (INSTR == 1) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) atomicAdd(a.counters + k, ins[k]);
         }
@@ -459,11 +465,12 @@ struct stmpm_handle {
     double* stage_cols[NBUF] = {nullptr, nullptr, nullptr};
     double* stage_err[NBUF] = {nullptr, nullptr, nullptr};
     int* stage_ndet[NBUF] = {nullptr, nullptr, nullptr};
+    float* stage_mag[NBUF] = {nullptr, nullptr, nullptr};
     long long stage_cap = 0;
     double* stage_stats = nullptr;
     long long stage_stats_cap = 0;
     long long launches = 0;
-    size_t smem_attr_set[2][2][2] = {};
+    size_t smem_attr_set[2][2][3] = {};
     unsigned long long* counters = nullptr;
 };
 
@@ -600,8 +607,8 @@ extern "C" int stmpm_create(stmpm_t** out, int device) {
 
 static void free_stage(stmpm_handle* h) {
     for (int i = 0; i < stmpm_handle::NBUF; ++i) {
-        cudaFree(h->stage_cols[i]); cudaFree(h->stage_err[i]); cudaFree(h->stage_ndet[i]);
-        h->stage_cols[i] = nullptr; h->stage_err[i] = nullptr; h->stage_ndet[i] = nullptr;
+        cudaFree(h->stage_cols[i]); cudaFree(h->stage_err[i]); cudaFree(h->stage_ndet[i]); cudaFree(h->stage_mag[i]);
+        h->stage_cols[i] = nullptr; h->stage_err[i] = nullptr; h->stage_ndet[i] = nullptr; h->stage_mag[i] = nullptr;
     }
     h->stage_cap = 0;
 }
@@ -805,6 +812,12 @@ static int fill_common(stmpm_handle* h, KArgs& a, int precision) {
 extern "C" int stmpm_trials_presampled(stmpm_t* h, int precision, int64_t n, uint64_t seed, int64_t trial0,
                                        const double* const* cols, double* err, int32_t* ndet, double* stats,
                                        void* stream) {
+    return stmpm_trials_presampled_ex(h, precision, n, seed, trial0, cols, err, ndet, nullptr, stats, stream);
+}
+
+extern "C" int stmpm_trials_presampled_ex(stmpm_t* h, int precision, int64_t n, uint64_t seed, int64_t trial0,
+                                          const double* const* cols, double* err, int32_t* ndet, float* maxmag,
+                                          double* stats, void* stream) {
     KArgs a;
     if (int rc = fill_common(h, a, precision)) return rc;
     if (n < 0 || !cols) return fail(STMPM_E_ARG, "stmpm_trials_presampled: bad n / cols");
@@ -816,7 +829,9 @@ extern "C" int stmpm_trials_presampled(stmpm_t* h, int precision, int64_t n, uin
     }
     a.n_segments = 1; a.trials_per_segment = n; a.trial0 = trial0;
     a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
-    a.err = err; a.ndet = ndet; a.stats = stats;
+    a.err = err; a.ndet = ndet; a.maxmag = maxmag; a.stats = stats;
+    if (maxmag) return precision == 64 ? launch_trials<0, 64, 2>(h, a, (cudaStream_t)stream)
+                                       : launch_trials<0, 32, 2>(h, a, (cudaStream_t)stream);
     return precision == 64 ? launch_trials<0, 64>(h, a, (cudaStream_t)stream)
                            : launch_trials<0, 32>(h, a, (cudaStream_t)stream);
 }
@@ -879,6 +894,7 @@ static int ensure_stage(stmpm_handle* h, long long chunk, bool need_cols) {
         if (need_cols) CK(cudaMalloc(&h->stage_cols[i], sizeof(double) * STMPM_NCOLS * chunk));
         CK(cudaMalloc(&h->stage_err[i], sizeof(double) * chunk));
         CK(cudaMalloc(&h->stage_ndet[i], sizeof(int) * chunk));
+        CK(cudaMalloc(&h->stage_mag[i], sizeof(float) * chunk));
     }
     h->stage_cap = chunk;
     return 0;
@@ -895,6 +911,12 @@ static constexpr long long HOST_CHUNK = 1LL << 22;   // trials per pipeline stag
 
 extern "C" int stmpm_run_presampled_host(stmpm_t* h, int precision, int64_t n, uint64_t seed, int64_t trial0,
                                          const double* const* cols, double* err, int32_t* ndet, double* stats) {
+    return stmpm_run_presampled_host_ex(h, precision, n, seed, trial0, cols, err, ndet, nullptr, stats);
+}
+
+extern "C" int stmpm_run_presampled_host_ex(stmpm_t* h, int precision, int64_t n, uint64_t seed, int64_t trial0,
+                                            const double* const* cols, double* err, int32_t* ndet, float* maxmag,
+                                            double* stats) {
     KArgs probe;
     if (int rc = fill_common(h, probe, precision)) return rc;
     if (n < 0 || !cols || !err || !ndet) return fail(STMPM_E_ARG, "stmpm_run_presampled_host: bad arguments");
@@ -920,10 +942,12 @@ extern "C" int stmpm_run_presampled_host(stmpm_t* h, int precision, int64_t n, u
             CK(cudaMemcpyAsync(dst, cols[c] + off, sizeof(double) * m, cudaMemcpyHostToDevice, st));
             dcols[c] = dst;
         }
-        if (int rc = stmpm_trials_presampled(h, precision, m, seed, trial0 + off, dcols, h->stage_err[b],
-                                             h->stage_ndet[b], stats ? h->stage_stats : nullptr, st)) return rc;
+        if (int rc = stmpm_trials_presampled_ex(h, precision, m, seed, trial0 + off, dcols, h->stage_err[b],
+                                                h->stage_ndet[b], maxmag ? h->stage_mag[b] : nullptr,
+                                                stats ? h->stage_stats : nullptr, st)) return rc;
         CK(cudaMemcpyAsync(err + off, h->stage_err[b], sizeof(double) * m, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(ndet + off, h->stage_ndet[b], sizeof(int) * m, cudaMemcpyDeviceToHost, st));
+        if (maxmag) CK(cudaMemcpyAsync(maxmag + off, h->stage_mag[b], sizeof(float) * m, cudaMemcpyDeviceToHost, st));
     }
     for (int i = 0; i < stmpm_handle::NBUF; ++i) CK(cudaStreamSynchronize(h->streams[i]));
     if (stats) CK(cudaMemcpy(stats, h->stage_stats, sizeof(double) * slen, cudaMemcpyDeviceToHost));

@@ -133,7 +133,7 @@ class TrialEngine:
         return arr, n
 
     def run_presampled(self, cols, seed: int, trial0: int = 0, precision: int = 64, want_stats: bool = False,
-                       out_err: np.ndarray | None = None, out_ndet: np.ndarray | None = None):
+                       out_err: np.ndarray | None = None, out_ndet: np.ndarray | None = None, want_maxmag: bool = False):
         """HOST buffers in, HOST buffers out (H2D, kernel, D2H inside the call) — `Simulation.run_sim`'s path.
         cols: float64 [13, n] in COLUMNS order.  Returns (err_arcsec f64 [n] with -1 = failed, n_det i32 [n][, stats])."""
         if not isinstance(cols, np.ndarray) and not isinstance(cols, (list, tuple)):
@@ -144,9 +144,16 @@ class TrialEngine:
         err = out_err if out_err is not None else np.empty(n, dtype=np.float64)
         ndet = out_ndet if out_ndet is not None else np.empty(n, dtype=np.int32)
         stats = np.zeros(self.stats_len, dtype=np.float64) if want_stats else None
-        _abi.check(self._lib.stmpm_run_presampled_host(self._h, int(precision), n, int(seed) & (2**64 - 1), int(trial0),
-                                                       ptrs, _ptr(err), _ptr(ndet), _ptr(stats)))
-        return (err, ndet, stats) if want_stats else (err, ndet)
+        maxmag = np.empty(n, dtype=np.float32) if want_maxmag else None
+        _abi.check(self._lib.stmpm_run_presampled_host_ex(self._h, int(precision), n, int(seed) & (2**64 - 1),
+                                                          int(trial0), ptrs, _ptr(err), _ptr(ndet), _ptr(maxmag),
+                                                          _ptr(stats)))
+        out = (err, ndet)
+        if want_maxmag:
+            out += (maxmag,)       # faintest detected star's catalog magnitude, -inf if none (star_mag objective)
+        if want_stats:
+            out += (stats,)
+        return out
 
     def run_presampled_device(self, cols, err, ndet, stats=None, *, seed: int, trial0: int = 0, precision: int = 64,
                               stream: int = 0) -> None:

@@ -22,6 +22,7 @@ logger = logging.getLogger(__name__)
 
 QUEST_OUTPUT = "QUATERNION_ERROR_[arcsec]"      # toolplot.py:71
 N_DET_OUTPUT = "N_STARS_DETECTED"
+MAG_OUTPUT = "MAXIMUM MAGNITUDE VISIBLE"            # toolplot.py:241
 
 _COLUMN_DEFAULT_FROM = {"RIGHT_ASCENSION": 0.0, "DECLINATION": 0.0, "ROLL": 0.0}
 
@@ -81,12 +82,13 @@ class Simulation:
                 cols[i] = _COLUMN_DEFAULT_FROM.get(name, 0.0)
         return cols
 
-    def _run_engine(self, data: pd.DataFrame):
+    def _run_engine(self, data: pd.DataFrame, want_maxmag: bool = False):
         cols = self._columns(data)
         n = cols.shape[1]
-        err, ndet = self.engine.run_presampled(cols, self._philox_seed(), self._next_trial, self.precision)
+        out = self.engine.run_presampled(cols, self._philox_seed(), self._next_trial, self.precision,
+                                         want_maxmag=want_maxmag)
         self._next_trial += n
-        return err, ndet
+        return out
 
     # ---------------------------------------------------------------- objectives (selected at driver.py:240-247)
     def quest_objective(self, data):
@@ -100,9 +102,12 @@ class Simulation:
         return err
 
     def star_mag(self, data):
-        raise NotImplementedError(
-            "star_mag (-func M, output 'MAXIMUM MAGNITUDE VISIBLE', toolplot.py:241): its body is absent from the "
-            "reference mount and it is outside the accelerated hot path (SURVEY.md §8a R9)")
+        """Magnitude objective (-func M, driver.py:246-247): catalog magnitude of the faintest star the trial detects —
+        the column 'MAXIMUM MAGNITUDE VISIBLE' that toolplot.py:241 histograms.  A by-product of the same kernel."""
+        self.output_name = MAG_OUTPUT
+        if isinstance(data, pd.Series):
+            return float(self._run_engine(data.to_frame().T, want_maxmag=True)[2][0])
+        return self._run_engine(data, want_maxmag=True)[2]
 
     def phi_model(self, data):
         raise NotImplementedError(
@@ -125,7 +130,14 @@ class Simulation:
             out[QUEST_OUTPUT] = err
             out[N_DET_OUTPUT] = ndet
             out = out[err >= 0.0]
-        elif func in (Simulation.star_mag, Simulation.phi_model):
+        elif func is Simulation.star_mag:
+            self.output_name = MAG_OUTPUT
+            err, ndet, mmag = self._run_engine(data, want_maxmag=True)
+            out = data.copy()
+            out[MAG_OUTPUT] = mmag.astype(np.float64)
+            out[N_DET_OUTPUT] = ndet
+            out = out[ndet > 0]                      # no detected star -> no magnitude: row dropped
+        elif func is Simulation.phi_model:
             obj_func(data)   # raises NotImplementedError with the explanation
             raise AssertionError("unreachable")
         else:   # a user-supplied per-row callable

@@ -13,6 +13,8 @@ class OracleEngine:
         self.xyz, self.mag = load_catalog()
         self.calls = 0
 
-    def run_presampled(self, cols, seed, trial0=0, precision=64, want_stats=False, **_):
+    def run_presampled(self, cols, seed, trial0=0, precision=64, want_stats=False, want_maxmag=False, **_):
         self.calls += 1
-        return trial.run_trials(np.asarray(cols, dtype=np.float64), self.xyz, self.mag, self.f_ideal, seed, trial0)
+        e, d, aux = trial.run_trials(np.asarray(cols, dtype=np.float64), self.xyz, self.mag, self.f_ideal, seed, trial0,
+                                     return_aux=True)
+        return (e, d, aux["maxmag"]) if want_maxmag else (e, d)

@@ -230,3 +230,15 @@ def test_custom_catalog_with_non_identity_star_ids(lib_built, catalog):
     for prec in (64, 32):
         compare(*eng.run_presampled(cols, 77, 0, precision=prec), e_ref, d_ref, prec)
     eng.close()
+
+
+def test_star_mag_output_is_bit_exact(engine, catalog):
+    """star_mag objective: faintest detected star's catalog magnitude (a max over float32 catalog values: exact)."""
+    xyz, mag = catalog
+    cols = trial.sample_params(dict(BASIC_MEAN, MAX_MAGNITUDE=4.6), BASIC_SIGMA, THERMAL_COEF, 41, 0, 8000)
+    e_ref, d_ref, aux = trial.run_trials(cols, xyz, mag, F, 41, 0, return_aux=True)
+    for prec in (64, 32):
+        e, d, m = engine.run_presampled(cols, 41, 0, precision=prec, want_maxmag=True)
+        compare(e, d, e_ref, d_ref, prec)
+        assert np.array_equal(m, aux["maxmag"])
+    assert np.isneginf(m[d_ref == 0]).all() and (d_ref == 0).any()

@@ -81,6 +81,9 @@ def test_run_sim_contract(dropin):
     assert not np.array_equal(out2[sim.output_name].to_numpy(), out[sim.output_name].to_numpy()[:10])  # new trial indices
     with pytest.raises(NotImplementedError):
         sim.run_sim(params=[], obj_func=sim.phi_model)
+    mag_out = sim.run_sim(params=[], obj_func=sim.star_mag)          # -func M (driver.py:246-247)
+    assert sim.output_name == "MAXIMUM MAGNITUDE VISIBLE" and len(mag_out) == 50   # toolplot.py:241
+    assert (mag_out[sim.output_name] <= mag_out["MAX_MAGNITUDE"] + 1e-6).all() and (mag_out[sim.output_name] > 3).all()
     assert isinstance(sim.quest_objective(sim.sim_data.iloc[30]), float)
 
 
