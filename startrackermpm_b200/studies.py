@@ -131,9 +131,72 @@ def run_segments(engine: TrialEngine, dists: Sequence[_abi.Dist], trials_per_seg
     return out
 
 
+# ---------------------------------------------------------------- run.sh study matrix
+# study name -> swept / perturbed columns, exactly run.sh:11-42's tag table
+STUDY_TAGS = {
+    "STARS": ("MAX_MAGNITUDE",),                                             # run.sh:16
+    "EPS_LAT": ("F_ARR_EPS_X", "F_ARR_EPS_Y"),                               # run.sh:12
+    "EPS_LONG": ("F_ARR_EPS_Z",),                                            # run.sh:14
+    "EPS": ("F_ARR_EPS_X", "F_ARR_EPS_Y", "F_ARR_EPS_Z"),                    # run.sh:35
+    "PHI_LAT": ("F_ARR_PHI", "F_ARR_THETA"),                                 # run.sh:11
+    "PHI_LONG": ("F_ARR_PSI",),                                              # run.sh:13
+    "PHI": ("F_ARR_PHI", "F_ARR_THETA", "F_ARR_PSI"),                        # run.sh:38
+    "FOCLEN": ("FOCAL_LENGTH", "MAX_MAGNITUDE"),                             # run.sh:15
+    "CENTROID": ("BASE_DEV_X", "BASE_DEV_Y"),                                # run.sh:17
+}
+SWEEP_POINTS, SWEEP_REPEATS = 100, 200                                        # sensitivity.py:19-20
+
+
+def study_matrix(engine: TrialEngine, means: Mapping[str, float], sigmas: Mapping[str, float], *, studies=None,
+                 mc_trials: int = 20_000, sweep_repeats: int = SWEEP_REPEATS, seed: int = 0, precision: int = 64) -> dict:
+    """The thesis' "univariate effect analysis" (run.sh:50-131) on the GPU engine, per study name:
+
+    * `mc`    — Monte Carlo with ONLY the study's parameters perturbed (their sigma from `sigmas`, everything else ideal):
+                what run.sh does with `-cam data/<STUDY>.json -sw i -n 20000` (run.sh:61-63,120).
+    * `sweep` — Sense.run_sim's 1-D diagonal sweep (sensitivity.py:39-55): 100 values, every swept column at the same
+                index: linspace(ideal - 3 sigma, ideal + 3 sigma); BASE_DEV_* linspace(0, -3 sigma) (sensitivity.py:46-47);
+                MAX_MAGNITUDE linspace(ideal - 3, ideal + 3) (sensitivity.py:49-52), or ~ N(ideal, 1) per trial when
+                swept together with FOCAL_LENGTH (sensitivity.py:61-62); all other hardware ideal and, unless swept,
+                MAX_MAGNITUDE = 20 (sensitivity.py:112).  `sweep_repeats` trials per value (200 in the reference).
+    One multi-segment launch per sweep.  Returns {study: {"mc": summary, "sweep": {"values": {...}, "mean": [...], ...}}}."""
+    out = {}
+    ideal_sig = {k: 0.0 for k in NORMAL_PARAMS}
+    for si, name in enumerate(studies or STUDY_TAGS):
+        tags = STUDY_TAGS[name]
+        s_mc = dict(ideal_sig)
+        for t in tags:
+            s_mc[t] = float(sigmas.get(t, 0.0))
+        mc = summarize(engine.run_rng(make_dist(means, s_mc, 0.0), mc_trials, seed + 2 * si, 0, precision)[0],
+                       engine.hist_log2_sub)
+        values, dists = {}, []
+        for t in tags:
+            up = 3.0 * float(sigmas.get(t, 0.0))
+            if t in ("BASE_DEV_X", "BASE_DEV_Y"):
+                values[t] = np.linspace(0.0, -up, SWEEP_POINTS)
+            elif t == "MAX_MAGNITUDE":
+                values[t] = np.linspace(means[t] - 3.0, means[t] + 3.0, SWEEP_POINTS)
+            else:
+                values[t] = np.linspace(means[t] - up, means[t] + up, SWEEP_POINTS)
+        both = "FOCAL_LENGTH" in tags and "MAX_MAGNITUDE" in tags
+        for i in range(SWEEP_POINTS):
+            m, s = dict(means), dict(ideal_sig)
+            m["MAX_MAGNITUDE"] = 20.0
+            for t in tags:
+                m[t] = float(values[t][i])
+            if both:
+                m["MAX_MAGNITUDE"], s["MAX_MAGNITUDE"] = means["MAX_MAGNITUDE"], 1.0
+            dists.append(make_dist(m, s, 0.0))
+        st = engine.run_rng(dists, sweep_repeats, seed + 2 * si + 1, 0, precision)
+        ss = summaries(st, engine.hist_log2_sub)
+        out[name] = {"mc": mc, "sweep": {"values": values, "mean": np.array([x.get("mean", np.nan) for x in ss]),
+                                         "sigma_halfnormal": np.array([x.get("sigma_halfnormal", np.nan) for x in ss]),
+                                         "fail_rate": np.array([x["fail_rate"] for x in ss]), "stats": st}}
+    return out
+
+
 def summaries(stats: np.ndarray, hist_log2_sub: int = 8) -> list[dict]:
     return [summarize(s, hist_log2_sub) for s in np.atleast_2d(stats)]
 
 
 __all__ = ["monte_carlo_converged", "grid_axes", "sensitivity_grid_dists", "sensitivity_grid", "leo_lifetime_dists",
-           "run_segments", "summaries", "NORMAL_PARAMS"]
+           "run_segments", "summaries", "study_matrix", "STUDY_TAGS", "NORMAL_PARAMS"]

@@ -75,3 +75,22 @@ def test_monte_carlo_stop_rule_matches_reference_loop(engine):
         prev = fin.std() / k
     assert count == got["count"] and got["n_ok"] == len(fin)
     assert got["sigma_halfnormal"] == pytest.approx(prev, rel=1e-10)
+
+
+@pytest.mark.gpu
+def test_run_sh_study_matrix_on_gpu(engine):
+    """run.sh's nine studies (MC + diagonal sweep each) and the analytic shapes of their sweeps."""
+    from startrackermpm_b200 import studies
+    res = studies.study_matrix(engine, BASIC_MEAN, BASIC_SIGMA, mc_trials=5000, sweep_repeats=100, seed=7)
+    assert set(res) == set(studies.STUDY_TAGS)
+    psi = res["PHI_LONG"]["sweep"]
+    assert np.allclose(psi["mean"], np.abs(psi["values"]["F_ARR_PSI"]) * 3600.0, atol=1e-6)     # pure psi -> |psi| exactly
+    lat = res["EPS_LAT"]["sweep"]
+    r = np.hypot(lat["values"]["F_ARR_EPS_X"], lat["values"]["F_ARR_EPS_Y"])
+    assert np.allclose(lat["mean"], np.arctan(r / 3500.0) * 206264.806, rtol=0.03, atol=0.5)     # README.md:13 "consistent bias"
+    cen = res["CENTROID"]["sweep"]
+    assert cen["mean"][0] < 1e-6 and np.all(np.diff(cen["mean"][::10]) > 0)                     # grows with centroid sigma
+    stars = res["STARS"]["sweep"]
+    assert stars["fail_rate"][0] > 0.9 and stars["fail_rate"][-1] == 0.0                        # mag 3 -> 9
+    assert res["EPS_LONG"]["mc"]["mean"] < res["EPS_LAT"]["mc"]["mean"]                         # vertical shift hurts less
+    assert res["PHI"]["mc"]["sigma_halfnormal"] > res["CENTROID"]["mc"]["sigma_halfnormal"]

@@ -1,7 +1,7 @@
 """Small invocation of every kernel path for compute-sanitizer (memcheck / racecheck): both modes, both precisions,
 ragged sizes, the band-scan fallback, multi-segment statistics."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root
 import numpy as np
 from oracle import trial
 from startrackermpm_b200.engine import TrialEngine, make_dist
