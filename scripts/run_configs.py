@@ -31,7 +31,7 @@ if 3 in args.configs:      # sensitivity grid 64 x 64 x 16, 1e6 trials per point
     eng = TrialEngine(local, f_ideal=F_IDEAL, hist_log2_sub=5)
     tps = max(1000, int(1e6 * args.scale))
     ea, pa, da = studies.grid_axes(BASIC_SIGMA["F_ARR_EPS_X"], BASIC_SIGMA["F_ARR_PHI"], BASIC_SIGMA["BASE_DEV_X"])
-    seg = list(sharding.shard_segments(64 * 64 * 16, rank, world))
+    seg = list(range(*sharding.shard_range(64 * 64 * 16, rank, world)))   # contiguous block: 4096 points per launch
     sync(); t = time.perf_counter()
     st = studies.sensitivity_grid(eng, BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF, ea, pa, da, tps, seed=3,
                                   precision=args.precision, segments=seg)

@@ -19,7 +19,9 @@ def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
 
 
 def shard_segments(n_segments: int, rank: int, world: int) -> range:
-    """Round-robin whole segments (grid points / orbit steps): per-segment statistics stay rank-local."""
+    """Round-robin whole segments (grid points / orbit steps): per-segment statistics stay rank-local.  Use this when the
+    cost per segment varies systematically along the index (orbit steps); for uniform sweeps prefer a contiguous block
+    `range(*shard_range(n_segments, rank, world))`, which `studies.run_segments` batches into few launches."""
     return range(rank, int(n_segments), int(world))
 
 
