@@ -50,7 +50,7 @@ struct KArgs {
 };
 
 struct SmemLayout {
-    size_t cat32, band_tab, lk_band_tab, tables, list, win, red, total;
+    size_t cat32, band_tab, lk_band_tab, tables, list, win, red, mbar, total;
 };
 constexpr size_t WIN_BYTES = WIN_MAX /*keys u8*/ + 2 * WIN_MAX /*perm u16*/ + 2 * KEY_BINS /*hist u16*/;
 static SmemLayout smem_layout(int n_stars, int n_bands, int lk_bands) {
@@ -63,6 +63,7 @@ static SmemLayout smem_layout(int n_stars, int n_bands, int lk_bands) {
     L.list = o;       o += (size_t)LIST_CAP * TPB * 2;
     L.win = o;        o += (size_t)(TPB / 32) * WIN_BYTES;
     L.red = o;        o += (size_t)(TPB / 32) * 8 * 8;
+    L.mbar = o;       o += 16;
     L.total = o;
     return L;
 }
@@ -96,6 +97,26 @@ __device__ __forceinline__ bool scan_list(const Ctx32& c, const float4* __restri
     return false;
 }
 
+// ---- TMA bulk copy (cp.async.bulk, global -> shared, completion on an mbarrier): stages the 146 KB fp32 catalog
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
 __device__ __forceinline__ int lookup_cell(const int2* __restrict__ s_lkband, int lk_bands, float lk_inv_band_h, float ra0,
                                            float dec0) {
     const int lb = min(lk_bands - 1, max(0, (int)floorf((dec0 + 1.57079633f) * lk_inv_band_h)));
@@ -109,7 +130,7 @@ __device__ __forceinline__ int lookup_cell(const int2* __restrict__ s_lkband, in
 // INSTR 2: also record the faintest detected star's magnitude (star_mag objective).
 template <int MODE, int PREC, int INSTR>
 __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const SmemLayout L) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     float4* s_cat = reinterpret_cast<float4*>(smem + L.cat32);
     int2* s_band = reinterpret_cast<int2*>(smem + L.band_tab);
     int2* s_lkband = reinterpret_cast<int2*>(smem + L.lk_band_tab);
@@ -122,17 +143,27 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
     uint16_t* w_perm = reinterpret_cast<uint16_t*>(w_key + WIN_MAX);
     uint16_t* w_hist = w_perm + WIN_MAX;
 
-    // ---- stage the catalog + grid into shared memory (once per CTA; the CTA is persistent)
+    // ---- stage the catalog + tables into shared memory (once per CTA; the CTA is persistent).  The 146 KB fp32 catalog
+    // goes through the TMA unit: one elected thread issues cp.async.bulk chunks that complete on an mbarrier while the
+    // other threads load the small tables; nobody touches s_cat before the barrier phase flips.
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L.mbar);
+    if (threadIdx.x == 0) mbar_init(s_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t total = (uint32_t)a.n_stars * 16u;
+        mbar_expect_tx(s_bar, total);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(a.cat32);
+        unsigned char* dst = reinterpret_cast<unsigned char*>(s_cat);
+        for (uint32_t off = 0; off < total; off += 32768u) bulk_g2s(dst + off, src + off, min(32768u, total - off), s_bar);
+    }
     {
-        const uint4* g = reinterpret_cast<const uint4*>(a.cat32);
-        uint4* s = reinterpret_cast<uint4*>(s_cat);
-        for (int i = threadIdx.x; i < a.n_stars; i += TPB) s[i] = __ldg(g + i);
         for (int i = threadIdx.x; i < a.n_bands; i += TPB) s_band[i] = __ldg(a.band_tab + i);
         for (int i = threadIdx.x; i < a.lk_bands; i += TPB) s_lkband[i] = __ldg(a.lk_band_tab + i);
         const double* gt = reinterpret_cast<const double*>(a.tables);
         double* stb = reinterpret_cast<double*>(smem + L.tables);
         for (int i = threadIdx.x; i < (int)(sizeof(MathTables) / 8); i += TPB) stb[i] = __ldg(gt + i);
     }
+    while (!mbar_try_wait(s_bar, 0)) {}
     __syncthreads();
 
     const uint16_t* __restrict__ g_cell = a.cell_start;   // sky-grid cell index (fallback scan only): read through L1/L2
