@@ -126,11 +126,30 @@ STMPM_HD int clz64(unsigned long long v) {
     return __builtin_clzll(v);
 #endif
 }
+// 1/sqrt(x) and 1/x for normal, positive, finite x (every use below: no zero / inf / denormal / NaN handling needed, which
+// is what libm's expansions spend their branches on): MUFU seed (~2^-22) + two Newton steps -> ~1 ulp.
 STMPM_HD double fast_rsqrt(double x) {
 #if defined(__CUDA_ARCH__)
-    return rsqrt(x);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double h = 0.5 * x;
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    return y;
 #else
     return 1.0 / sqrt(x);
+#endif
+}
+STMPM_HD double fast_div(double a, double b) {   // a / b, b normal and finite
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    r = r * fma(-b, r, 2.0);
+    r = r * fma(-b, r, 2.0);
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);              // one residual correction: correctly rounded in practice
+#else
+    return a / b;
 #endif
 }
 
@@ -338,14 +357,16 @@ __device__ __forceinline__ bool star_exact(const Ctx64& c, const MathTables* __r
     const double dn = c.NI[0] * s.x + c.NI[1] * s.y + c.NI[2] * s.z;
     const double du = c.EU[0] * s.x + c.EU[1] * s.y + c.EU[2] * s.z;
     const double dv = c.EV[0] * s.x + c.EV[1] * s.y + c.EV[2] * s.z;
-    const double lam = c.np0 / dn;
+    // pre-filter survivors have dn > 0.02 (anything else is not detectable: dn <= 0 fails the test below, and a star
+    // with 0 < dn <= 0.02 lands > 50 f from the array centre); clamp so the seed + Newton reciprocal stays in range
+    const double lam = fast_div(c.np0, fmax(dn, 1e-3));
     double z1, z2;
     box_muller_tab(T, x0, x1, z1, z2);
     const double um = fma(c.sx, z1, fma(lam, du, -c.cu));
     const double vm = fma(c.sy, z2, fma(lam, dv, -c.cv));
     const bool det = (dn > 0.0) && (fabs(um) <= half_u) && (fabs(vm) <= half_v);
     if (det) {
-        const double inv = rsqrt(um * um + vm * vm + f_ideal * f_ideal);
+        const double inv = fast_rsqrt(um * um + vm * vm + f_ideal * f_ideal);
         const double bx = um * inv, by = vm * inv, bz = f_ideal * inv;
         B[0] = fma(bx, s.x, B[0]); B[1] = fma(bx, s.y, B[1]); B[2] = fma(bx, s.z, B[2]);
         B[3] = fma(by, s.x, B[3]); B[4] = fma(by, s.y, B[4]); B[5] = fma(by, s.z, B[5]);
