@@ -513,8 +513,8 @@ static void stmpm_host_tables(MathTables* t) {
         t->log_tab[j][1] = std::log(c);
     }
     for (int k = 0; k < 34; ++k) t->k_ln2[k] = k * M_LN2;
-    for (int j = 0; j < 64; ++j) {
-        const double a = (M_PI / 2.0) * (j + 0.5) / 64.0;
+    for (int j = 0; j < 256; ++j) {
+        const double a = 2.0 * M_PI * (j + 0.5) / 256.0;
         t->sc_tab[j][0] = std::sin(a);
         t->sc_tab[j][1] = std::cos(a);
     }

@@ -95,10 +95,10 @@ STMPM_HD double u01(uint32_t w) { return ((double)w + 0.5) * TWO_M32; }
 // Evaluated to ~1e-15 absolute with integer argument reduction (no int->double conversions: those go to the XU pipe)
 // and small tables instead of libm's long polynomials: the star loop is FP64-pipe bound.
 //   ln:  2w+1 = m 2^p, m in [1,2); j = top 7 mantissa bits; r = m / c_j - 1, |r| <= 2^-8; ln m = ln c_j + log1p(r)
-//   sin/cos: quadrant = top 2 bits of w; 64 table intervals per quadrant; |d| <= pi/256 remainder by Taylor.
+//   sin/cos: 256 table intervals over the full circle (top 8 bits of w); |d| <= pi/256 remainder by Taylor.
 struct __align__(16) MathTables {
     double log_tab[128][2];                 // {1 / c_j, ln c_j},  c_j = 1 + (j + 0.5) / 128   (one 16-byte load)
-    double sc_tab[64][2];                   // {sin, cos} of (pi/2) (j + 0.5) / 64             (one 16-byte load)
+    double sc_tab[256][2];                  // {sin, cos} of 2 pi (j + 0.5) / 256: the full circle, no quadrant logic
     double k_ln2[34];                       // k * ln 2
 };
 STMPM_HD void load2(const double* p, double& a, double& b) {
@@ -169,11 +169,9 @@ STMPM_HD void box_muller_tab(const MathTables* __restrict__ T, uint32_t wa, uint
     const double ln_u = (ln_c + p) - T->k_ln2[lz - 30];   // k = 33 - p = lz - 30
     const double L = -2.0 * ln_u;
     const double R = L * fast_rsqrt(L);
-    // ---- angle 2 pi u2 = (pi/2) (q + (64-interval j2 centre) ) + d
-    const uint32_t q = wb >> 30;
-    const uint32_t w30 = wb & 0x3FFFFFFFu;
-    const int j2 = (int)(w30 >> 24);
-    const uint32_t rem = w30 & 0xFFFFFFu;
+    // ---- angle 2 pi u2 = 2 pi (j2 + 0.5) / 256 + d,  j2 = top 8 bits of wb
+    const int j2 = (int)(wb >> 24);
+    const uint32_t rem = wb & 0xFFFFFFu;
     // d = (pi/128) ((rem + 0.5) / 2^24 - 0.5), via the 2^52 magic number (exact, no conversion instruction)
     const double t = bits_to_double(0x4330000000000000ull | (unsigned long long)(2u * rem + 1u));
     const double d = (t - 4503599644147712.0) * 7.314590396335798e-10;   // (2^52 + 2^24);  pi / 128 / 2^25
@@ -182,13 +180,8 @@ STMPM_HD void box_muller_tab(const MathTables* __restrict__ T, uint32_t wa, uint
     const double cd = fma(d2, fma(d2, fma(d2, -1.0 / 720.0, 1.0 / 24.0), -0.5), 1.0);
     double S, C;
     load2(T->sc_tab[j2], S, C);
-    const double sn = fma(S, cd, C * sd);
-    const double cs = fma(C, cd, -S * sd);
-    // quadrant rotation: (cos, sin) -> q=0 (cs, sn); 1 (-sn, cs); 2 (-cs, -sn); 3 (sn, -cs)
-    const double c0 = (q & 1u) ? sn : cs;
-    const double s0 = (q & 1u) ? cs : sn;
-    const double cq = (q == 1u || q == 2u) ? -c0 : c0;
-    const double sq = (q >= 2u) ? -s0 : s0;
+    const double sq = fma(S, cd, C * sd);
+    const double cq = fma(C, cd, -S * sd);
     z1 = R * cq;
     z2 = R * sq;
 }
