@@ -507,14 +507,14 @@ struct stmpm_handle {
 
 // Tables of box_muller_tab (stmpm_device.cuh), computed with the host libm.
 static void stmpm_host_tables(MathTables* t) {
-    for (int j = 0; j < 128; ++j) {
-        const double c = 1.0 + (j + 0.5) / 128.0;
+    for (int j = 0; j < 256; ++j) {
+        const double c = 1.0 + (j + 0.5) / 256.0;
         t->log_tab[j][0] = 1.0 / c;
         t->log_tab[j][1] = std::log(c);
     }
     for (int k = 0; k < 34; ++k) t->k_ln2[k] = k * M_LN2;
-    for (int j = 0; j < 256; ++j) {
-        const double a = 2.0 * M_PI * (j + 0.5) / 256.0;
+    for (int j = 0; j < 1024; ++j) {
+        const double a = 2.0 * M_PI * (j + 0.5) / 1024.0;
         t->sc_tab[j][0] = std::sin(a);
         t->sc_tab[j][1] = std::cos(a);
     }

@@ -94,11 +94,12 @@ STMPM_HD double u01(uint32_t w) { return ((double)w + 0.5) * TWO_M32; }
 // MODEL.md §5: R = sqrt(-2 ln u1), z1 = R cos(2 pi u2), z2 = R sin(2 pi u2), u = (w + 0.5) 2^-32.
 // Evaluated to ~1e-15 absolute with integer argument reduction (no int->double conversions: those go to the XU pipe)
 // and small tables instead of libm's long polynomials: the star loop is FP64-pipe bound.
-//   ln:  2w+1 = m 2^p, m in [1,2); j = top 7 mantissa bits; r = m / c_j - 1, |r| <= 2^-8; ln m = ln c_j + log1p(r)
-//   sin/cos: 256 table intervals over the full circle (top 8 bits of w); |d| <= pi/256 remainder by Taylor.
+//   ln:  2w+1 = m 2^p, m in [1,2); j = top 8 mantissa bits; r = m / c_j - 1, |r| <= 2^-9; ln m = ln c_j + log1p(r)
+//   sin/cos: 1024 table intervals over the full circle (top 10 bits of w); |d| <= pi/1024 remainder by Taylor.
+// Dense tables keep the polynomials — i.e. the dependent fp64 chain of the star loop — short.
 struct __align__(16) MathTables {
-    double log_tab[128][2];                 // {1 / c_j, ln c_j},  c_j = 1 + (j + 0.5) / 128   (one 16-byte load)
-    double sc_tab[256][2];                  // {sin, cos} of 2 pi (j + 0.5) / 256: the full circle, no quadrant logic
+    double log_tab[256][2];                 // {1 / c_j, ln c_j},  c_j = 1 + (j + 0.5) / 256   (one 16-byte load)
+    double sc_tab[1024][2];                 // {sin, cos} of 2 pi (j + 0.5) / 1024: the full circle, no quadrant logic
     double k_ln2[34];                       // k * ln 2
 };
 STMPM_HD void load2(const double* p, double& a, double& b) {
@@ -156,28 +157,25 @@ STMPM_HD void box_muller_tab(const MathTables* __restrict__ T, uint32_t wa, uint
     const int lz = clz64(v);                                  // top bit at p = 63 - lz, u1 = m 2^(p - 33)
     const unsigned long long frac = ((v << lz) << 1) >> 12;   // 52 mantissa bits of m (lz + 1 can be 64)
     const double m = bits_to_double(0x3FF0000000000000ull | frac);
-    const int j = (int)(frac >> 45);
+    const int j = (int)(frac >> 44);
     double inv_c, ln_c;
     load2(T->log_tab[j], inv_c, ln_c);
     const double r = fma(m, inv_c, -1.0);
-    // log1p(r) = r - r^2/2 + r^3/3 - r^4/4 + r^5/5 - r^6/6, |r| <= 2^-8 (truncation < 2e-18), Estrin form (depth 4)
+    // log1p(r) = r - r^2/2 + r^3/3 - r^4/4 + r^5/5, |r| <= 2^-9 (truncation r^6/6 < 1e-17), Estrin form: depth 3
     const double r2 = r * r;
-    const double pa = fma(r, 1.0 / 3.0, -0.5);
-    const double pb = fma(r, 0.2, -0.25);
-    const double pc = fma(r2, -1.0 / 6.0, pb);
-    const double p = fma(r2, fma(r2, pc, pa), r);
+    const double p = fma(r2, fma(r2, fma(r, 0.2, -0.25), fma(r, 1.0 / 3.0, -0.5)), r);
     const double ln_u = (ln_c + p) - T->k_ln2[lz - 30];   // k = 33 - p = lz - 30
     const double L = -2.0 * ln_u;
     const double R = L * fast_rsqrt(L);
-    // ---- angle 2 pi u2 = 2 pi (j2 + 0.5) / 256 + d,  j2 = top 8 bits of wb
-    const int j2 = (int)(wb >> 24);
-    const uint32_t rem = wb & 0xFFFFFFu;
-    // d = (pi/128) ((rem + 0.5) / 2^24 - 0.5), via the 2^52 magic number (exact, no conversion instruction)
+    // ---- angle 2 pi u2 = 2 pi (j2 + 0.5) / 1024 + d,  j2 = top 10 bits of wb
+    const int j2 = (int)(wb >> 22);
+    const uint32_t rem = wb & 0x3FFFFFu;
+    // d = (pi/512) ((rem + 0.5) / 2^22 - 0.5), |d| <= pi/1024, via the 2^52 magic number (exact, no conversion instruction)
     const double t = bits_to_double(0x4330000000000000ull | (unsigned long long)(2u * rem + 1u));
-    const double d = (t - 4503599644147712.0) * 7.314590396335798e-10;   // (2^52 + 2^24);  pi / 128 / 2^25
+    const double d = (t - 4503599631564800.0) * 7.314590396335798e-10;   // (2^52 + 2^22);  pi / 512 / 2^23
     const double d2 = d * d;
-    const double sd = fma(d * d2, fma(d2, 1.0 / 120.0, -1.0 / 6.0), d);
-    const double cd = fma(d2, fma(d2, fma(d2, -1.0 / 720.0, 1.0 / 24.0), -0.5), 1.0);
+    const double sd = fma(d * d2, -1.0 / 6.0, d);                        // truncation d^5/120 < 2.3e-15
+    const double cd = fma(d2, fma(d2, 1.0 / 24.0, -0.5), 1.0);           // truncation d^6/720 < 1.2e-18
     double S, C;
     load2(T->sc_tab[j2], S, C);
     const double sq = fma(S, cd, C * sd);
