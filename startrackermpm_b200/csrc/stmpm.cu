@@ -49,24 +49,20 @@ struct KArgs {
     unsigned long long* counters;   // INSTR only: [visits, mag_pass, survivors, detected]
 };
 
-struct SmemLayout {
-    size_t cat32, band_tab, lk_band_tab, tables, list, win, red, mbar, total;
-};
+// Shared-memory layout: every region at a COMPILE-TIME offset (fixed-size regions first, the variable-size catalog
+// last), so ptxas addresses them as [reg + immediate] instead of re-deriving bases from kernel parameters per access.
 constexpr size_t WIN_BYTES = WIN_MAX /*keys u8*/ + 2 * WIN_MAX /*perm u16*/ + 2 * KEY_BINS /*hist u16*/;
-static SmemLayout smem_layout(int n_stars, int n_bands, int lk_bands) {
-    SmemLayout L;
-    size_t o = 0;
-    L.cat32 = o;      o += (size_t)n_stars * 16;
-    L.band_tab = o;   o += (((size_t)n_bands * 8) + 15) / 16 * 16;
-    L.lk_band_tab = o; o += (((size_t)lk_bands * 8) + 15) / 16 * 16;
-    L.tables = o;     o += (sizeof(MathTables) + 15) / 16 * 16;
-    L.list = o;       o += (size_t)LIST_CAP * TPB * 2;
-    L.win = o;        o += (size_t)(TPB / 32) * WIN_BYTES;
-    L.red = o;        o += (size_t)(TPB / 32) * 8 * 8;
-    L.mbar = o;       o += 16;
-    L.total = o;
-    return L;
-}
+constexpr int LK_BANDS = 180;          // 1-degree lookup grid
+constexpr int MAX_BANDS = 256;         // sky-grid declination bands (fallback scan)
+constexpr size_t OFF_LIST = 0;
+constexpr size_t OFF_WIN = OFF_LIST + (size_t)LIST_CAP * TPB * 2;
+constexpr size_t OFF_TAB = OFF_WIN + (size_t)(TPB / 32) * WIN_BYTES;
+constexpr size_t OFF_RED = OFF_TAB + (sizeof(MathTables) + 15) / 16 * 16;
+constexpr size_t OFF_MBAR = OFF_RED + (size_t)(TPB / 32) * 8 * 8;
+constexpr size_t OFF_LKBAND = OFF_MBAR + 16;
+constexpr size_t OFF_BAND = OFF_LKBAND + (size_t)LK_BANDS * 8;
+constexpr size_t OFF_CAT = (OFF_BAND + (size_t)MAX_BANDS * 8 + 127) / 128 * 128;
+static size_t smem_total(int n_stars) { return OFF_CAT + (size_t)n_stars * 16; }
 
 // Walks the magnitude-sorted candidate list of the boresight's lookup cell from position lk on, pushing pre-filter
 // survivors to row[cnt * TPB]; the first star fainter than MAX_MAGNITUDE ends the scan (returns true).  Returns false
@@ -129,24 +125,24 @@ __device__ __forceinline__ int lookup_cell(const int2* __restrict__ s_lkband, in
 // INSTR 1: also count candidate visits / magnitude passes / pre-filter survivors (work-model calibration, not timed).
 // INSTR 2: also record the faintest detected star's magnitude (star_mag objective).
 template <int MODE, int PREC, int INSTR>
-__global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const SmemLayout L) {
+__global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    float4* s_cat = reinterpret_cast<float4*>(smem + L.cat32);
-    int2* s_band = reinterpret_cast<int2*>(smem + L.band_tab);
-    int2* s_lkband = reinterpret_cast<int2*>(smem + L.lk_band_tab);
-    const MathTables* s_tab = reinterpret_cast<const MathTables*>(smem + L.tables);
-    uint16_t* s_list = reinterpret_cast<uint16_t*>(smem + L.list) + threadIdx.x;   // entry j at s_list[j * TPB]
-    double* s_red = reinterpret_cast<double*>(smem + L.red);
+    float4* s_cat = reinterpret_cast<float4*>(smem + OFF_CAT);
+    int2* s_band = reinterpret_cast<int2*>(smem + OFF_BAND);
+    int2* s_lkband = reinterpret_cast<int2*>(smem + OFF_LKBAND);
+    const MathTables* s_tab = reinterpret_cast<const MathTables*>(smem + OFF_TAB);
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(smem + OFF_LIST) + threadIdx.x;   // entry j at s_list[j * TPB]
+    double* s_red = reinterpret_cast<double*>(smem + OFF_RED);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // this warp's sort window: keys, permutation, bin counters
-    uint8_t* w_key = smem + L.win + (size_t)warp * WIN_BYTES;
+    uint8_t* w_key = smem + OFF_WIN + (size_t)warp * WIN_BYTES;
     uint16_t* w_perm = reinterpret_cast<uint16_t*>(w_key + WIN_MAX);
     uint16_t* w_hist = w_perm + WIN_MAX;
 
     // ---- stage the catalog + tables into shared memory (once per CTA; the CTA is persistent).  The 146 KB fp32 catalog
     // goes through the TMA unit: one elected thread issues cp.async.bulk chunks that complete on an mbarrier while the
     // other threads load the small tables; nobody touches s_cat before the barrier phase flips.
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L.mbar);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + OFF_MBAR);
     if (threadIdx.x == 0) mbar_init(s_bar, 1);
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -160,7 +156,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a, const Sme
         for (int i = threadIdx.x; i < a.n_bands; i += TPB) s_band[i] = __ldg(a.band_tab + i);
         for (int i = threadIdx.x; i < a.lk_bands; i += TPB) s_lkband[i] = __ldg(a.lk_band_tab + i);
         const double* gt = reinterpret_cast<const double*>(a.tables);
-        double* stb = reinterpret_cast<double*>(smem + L.tables);
+        double* stb = reinterpret_cast<double*>(smem + OFF_TAB);
         for (int i = threadIdx.x; i < (int)(sizeof(MathTables) / 8); i += TPB) stb[i] = __ldg(gt + i);
     }
     while (!mbar_try_wait(s_bar, 0)) {}
@@ -510,9 +506,9 @@ static void stmpm_host_tables(MathTables* t) {
     for (int j = 0; j < 256; ++j) {
         const double c = 1.0 + (j + 0.5) / 256.0;
         t->log_tab[j][0] = 1.0 / c;
-        t->log_tab[j][1] = std::log(c);
+        t->log_tab[j][1] = -2.0 * std::log(c);
     }
-    for (int k = 0; k < 34; ++k) t->k_ln2[k] = k * M_LN2;
+    for (int k = 0; k < 34; ++k) t->k_ln2[k] = 2.0 * k * M_LN2;
     for (int j = 0; j < 1024; ++j) {
         const double a = 2.0 * M_PI * (j + 0.5) / 1024.0;
         t->sc_tab[j][0] = std::sin(a);
@@ -537,7 +533,7 @@ static int rebuild_lists(stmpm_handle* h) {
     for (int i = 0; i < S; ++i) {
         sx[i] = h->h_xyzf[3 * order[i]]; sy[i] = h->h_xyzf[3 * order[i] + 1]; sz[i] = h->h_xyzf[3 * order[i] + 2];
     }
-    const int nb = 180;
+    const int nb = LK_BANDS;
     const double bh = M_PI / nb;
     std::vector<int2> bt(nb);
     long long n_cells = 0;
@@ -783,17 +779,18 @@ extern "C" int stmpm_stats_finalize(int32_t hist_log2_sub, const double* s, stmp
 // ------------------------------------------------------------------------------------------------ launch helper
 template <int MODE, int PREC, int INSTR = 0>
 static int launch_trials(stmpm_handle* h, KArgs& a, cudaStream_t st) {
-    const SmemLayout L = smem_layout(a.n_stars, a.n_bands, a.lk_bands);
-    if (L.total > (size_t)h->prop.sharedMemPerBlockOptin)
-        return fail(STMPM_E_ARG, "catalog too large for shared-memory staging (" + std::to_string(L.total) + " B)");
+    const size_t smem_bytes = smem_total(a.n_stars);
+    if (smem_bytes > (size_t)h->prop.sharedMemPerBlockOptin)
+        return fail(STMPM_E_ARG, "catalog too large for shared-memory staging (" + std::to_string(smem_bytes) + " B)");
+    if (a.n_bands > MAX_BANDS || a.lk_bands != LK_BANDS) return fail(STMPM_E_ARG, "sky grid has too many declination bands");
     auto kern = trials_kernel<MODE, PREC, INSTR>;
     size_t& cached = h->smem_attr_set[MODE][PREC == 64 ? 0 : 1][INSTR];
-    if (cached < L.total) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    if (cached < smem_bytes) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         // leave the rest of the unified array to L1: register spills and the permuted input gathers live there
-        const int pct = (int)std::min<size_t>(100, (L.total + 1024) * 100 / (size_t)h->prop.sharedMemPerMultiprocessor + 1);
+        const int pct = (int)std::min<size_t>(100, (smem_bytes + 1024) * 100 / (size_t)h->prop.sharedMemPerMultiprocessor + 1);
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-        cached = L.total;
+        cached = smem_bytes;
     }
     const int n_sm = h->prop.multiProcessorCount;
     // work units: (segment, part).  Inside a unit each warp sorts + runs windows of `win` trials; small launches shrink
@@ -816,7 +813,7 @@ static int launch_trials(stmpm_handle* h, KArgs& a, cudaStream_t st) {
     const long long n_units = a.n_segments * parts;
     const int grid = (int)std::min<long long>(n_units, n_sm);
     if (grid <= 0) return 0;
-    kern<<<grid, TPB, L.total, st>>>(a, L);
+    kern<<<grid, TPB, smem_bytes, st>>>(a);
     CK(cudaGetLastError());
     ++h->launches;
     return 0;

@@ -98,9 +98,9 @@ STMPM_HD double u01(uint32_t w) { return ((double)w + 0.5) * TWO_M32; }
 //   sin/cos: 1024 table intervals over the full circle (top 10 bits of w); |d| <= pi/1024 remainder by Taylor.
 // Dense tables keep the polynomials — i.e. the dependent fp64 chain of the star loop — short.
 struct __align__(16) MathTables {
-    double log_tab[256][2];                 // {1 / c_j, ln c_j},  c_j = 1 + (j + 0.5) / 256   (one 16-byte load)
+    double log_tab[256][2];                 // {1 / c_j, -2 ln c_j},  c_j = 1 + (j + 0.5) / 256   (one 16-byte load)
     double sc_tab[1024][2];                 // {sin, cos} of 2 pi (j + 0.5) / 1024: the full circle, no quadrant logic
-    double k_ln2[34];                       // k * ln 2
+    double k_ln2[34];                       // 2 k ln 2
 };
 STMPM_HD void load2(const double* p, double& a, double& b) {
 #if defined(__CUDA_ARCH__)
@@ -118,6 +118,15 @@ STMPM_HD double bits_to_double(unsigned long long b) {
     double d;
     memcpy(&d, &b, 8);
     return d;
+#endif
+}
+STMPM_HD unsigned long long double_to_bits(double d) {
+#if defined(__CUDA_ARCH__)
+    return (unsigned long long)__double_as_longlong(d);
+#else
+    unsigned long long b;
+    memcpy(&b, &d, 8);
+    return b;
 #endif
 }
 STMPM_HD int clz64(unsigned long long v) {
@@ -151,22 +160,36 @@ STMPM_HD double fast_div(double a, double b) {
 #endif
 }
 
+STMPM_HD double seed_rsqrt(double x) {   // ~2^-22 relative; x normal, positive, finite
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+#else
+    return (double)(float)(1.0 / sqrt(x));
+#endif
+}
+
 STMPM_HD void box_muller_tab(const MathTables* __restrict__ T, uint32_t wa, uint32_t wb, double& z1, double& z2) {
-    // ---- L = -2 ln u1,  u1 = (2 wa + 1) 2^-33
-    const unsigned long long v = 2ull * wa + 1ull;            // 33-bit odd integer
-    const int lz = clz64(v);                                  // top bit at p = 63 - lz, u1 = m 2^(p - 33)
-    const unsigned long long frac = ((v << lz) << 1) >> 12;   // 52 mantissa bits of m (lz + 1 can be 64)
-    const double m = bits_to_double(0x3FF0000000000000ull | frac);
-    const int j = (int)(frac >> 44);
-    double inv_c, ln_c;
-    load2(T->log_tab[j], inv_c, ln_c);
+    // ---- L = -2 ln u1,  u1 = (2 wa + 1) 2^-33.  Exact int -> double through the 2^52 magic number (one DADD, no
+    // conversion instruction, no clz / shift normalisation); exponent and mantissa then come from the bit pattern.
+    const unsigned long long v = 2ull * wa + 1ull;                         // 33-bit odd integer
+    const double tv = bits_to_double(0x4330000000000000ull | v) - 4503599627370496.0;   // == (double)v
+    const unsigned long long tb = double_to_bits(tv);
+    const int k = 1056 - (int)(tb >> 52);                                  // 33 - unbiased exponent, in [1, 33]
+    const double m = bits_to_double((tb & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull);   // mantissa in [1, 2)
+    const int j = (int)(tb >> 44) & 0xFF;                                  // top 8 mantissa bits
+    double inv_c, m2ln_c;
+    load2(T->log_tab[j], inv_c, m2ln_c);                                   // {1 / c_j, -2 ln c_j}
     const double r = fma(m, inv_c, -1.0);
     // log1p(r) = r - r^2/2 + r^3/3 - r^4/4 + r^5/5, |r| <= 2^-9 (truncation r^6/6 < 1e-17), Estrin form: depth 3
     const double r2 = r * r;
     const double p = fma(r2, fma(r2, fma(r, 0.2, -0.25), fma(r, 1.0 / 3.0, -0.5)), r);
-    const double ln_u = (ln_c + p) - T->k_ln2[lz - 30];   // k = 33 - p = lz - 30
-    const double L = -2.0 * ln_u;
-    const double R = L * fast_rsqrt(L);
+    const double L = fma(-2.0, p, m2ln_c) + T->k_ln2[k];                   // -2 ln m + 2 k ln 2  (tables hold the factor 2)
+    // R = sqrt(L): seed y ~ 1/sqrt(L), R0 = L y, one Newton step on the square root: R = R0 + (L - R0^2) y / 2
+    const double y = seed_rsqrt(L);
+    const double R0 = L * y;
+    const double R = fma(fma(-R0, R0, L), 0.5 * y, R0);
     // ---- angle 2 pi u2 = 2 pi (j2 + 0.5) / 1024 + d,  j2 = top 10 bits of wb
     const int j2 = (int)(wb >> 22);
     const uint32_t rem = wb & 0x3FFFFFu;
@@ -332,7 +355,9 @@ __device__ __forceinline__ bool setup32(const TrialParams& p, float half_u, floa
 // fp32 conservative geometric pre-filter on one shared-memory catalog entry (x, y, z, mag); magnitude tested by caller
 __device__ __forceinline__ bool prefilter_geom(const Ctx32& c, const float4 s) {
     const float dn = c.NI[0] * s.x + c.NI[1] * s.y + c.NI[2] * s.z;
-    const float rl = __fdividef(c.np0, dn);
+    float rcp_dn;                                   // bare MUFU.RCP: dn is in (0.02, 1] when it matters (no range fix-ups)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp_dn) : "f"(dn));
+    const float rl = c.np0 * rcp_dn;
     const float u = fmaf(rl, c.EU[0] * s.x + c.EU[1] * s.y + c.EU[2] * s.z, -c.cu);
     const float v = fmaf(rl, c.EV[0] * s.x + c.EV[1] * s.y + c.EV[2] * s.z, -c.cv);
     return dn > 0.02f && fabsf(u) <= c.limu && fabsf(v) <= c.limv;
@@ -355,8 +380,11 @@ __device__ __forceinline__ bool star_exact(const Ctx64& c, const MathTables* __r
     const double vm = fma(c.sy, z2, fma(lam, dv, -c.cv));
     const bool det = (dn > 0.0) && (fabs(um) <= half_u) && (fabs(vm) <= half_v);
     if (det) {
-        const double inv = fast_rsqrt(um * um + vm * vm + f_ideal * f_ideal);
-        const double bx = um * inv, by = vm * inv, bz = f_ideal * inv;
+        // b = (um, vm, f) / |.|: seed y ~ 1/|.|, one Newton factor w; (um y), (vm y), (f y) run beside the Newton chain
+        const double n2 = fma(vm, vm, fma(um, um, f_ideal * f_ideal));
+        const double y = seed_rsqrt(n2);
+        const double w = fma(-0.5 * n2 * y, y, 1.5);
+        const double bx = (um * y) * w, by = (vm * y) * w, bz = (f_ideal * y) * w;
         B[0] = fma(bx, s.x, B[0]); B[1] = fma(bx, s.y, B[1]); B[2] = fma(bx, s.z, B[2]);
         B[3] = fma(by, s.x, B[3]); B[4] = fma(by, s.y, B[4]); B[5] = fma(by, s.z, B[5]);
         B[6] = fma(bz, s.x, B[6]); B[7] = fma(bz, s.y, B[7]); B[8] = fma(bz, s.z, B[8]);
