@@ -68,9 +68,8 @@ static size_t smem_total(int n_stars) { return OFF_CAT + (size_t)n_stars * 16; }
 // survivors to row[cnt * TPB]; the first star fainter than MAX_MAGNITUDE ends the scan (returns true).  Returns false
 // while candidates remain and fewer than 8 row slots are free: the caller drains the row and calls again.
 template <int INSTR>
-__device__ __forceinline__ bool scan_list(const Ctx32& c, const float4* __restrict__ s_cat, const uint16_t* __restrict__ lp,
-                                          int lk_len, int& lk, uint16_t* __restrict__ row, int& cnt,
-                                          unsigned long long* ins) {
+__device__ __forceinline__ bool scan_list(const Ctx32& c, uint32_t sb_cat, const uint16_t* __restrict__ lp, int lk_len, int& lk,
+                                          uint32_t sb_row, int& cnt, unsigned long long* ins) {
     if (lk >= lk_len) return true;
     uint4 pk_next = __ldg(reinterpret_cast<const uint4*>(lp + lk));
     while (cnt <= LIST_CAP - 8) {
@@ -82,11 +81,11 @@ __device__ __forceinline__ bool scan_list(const Ctx32& c, const float4* __restri
         for (int e = 0; e < 8; ++e) {
             const uint32_t idx = (w4[e >> 1] >> (16 * (e & 1))) & 0xffffu;
             if (idx == 0xffffu) return true;
-            const float4 sc = s_cat[idx];
+            const float4 sc = lds_f4(sb_cat + idx * 16u);
             if (INSTR == 1) ++ins[0];
             if (!(sc.w <= c.magf)) return true;          // sorted by magnitude: every later star is fainter still
             if (INSTR == 1) ++ins[1];
-            if (prefilter_geom(c, sc)) { row[cnt * TPB] = (uint16_t)idx; ++cnt; if (INSTR == 1) ++ins[2]; }
+            if (prefilter_geom(c, sc)) { sts_u16(sb_row + (uint32_t)cnt * (TPB * 2u), idx); ++cnt; if (INSTR == 1) ++ins[2]; }
         }
         if (lk >= lk_len) return true;
     }
@@ -133,6 +132,10 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
     const MathTables* s_tab = reinterpret_cast<const MathTables*>(smem + OFF_TAB);
     uint16_t* s_list = reinterpret_cast<uint16_t*>(smem + OFF_LIST) + threadIdx.x;   // entry j at s_list[j * TPB]
     double* s_red = reinterpret_cast<double*>(smem + OFF_RED);
+    // 32-bit shared-memory addresses of the hot regions, kept in registers (see lds_f4 / TabSmem)
+    const uint32_t sb = smem_u32(smem);
+    const uint32_t sb_cat = sb + (uint32_t)OFF_CAT, sb_row = sb + (uint32_t)OFF_LIST + threadIdx.x * 2u;
+    const TabSmem tabs{sb + (uint32_t)OFF_TAB};
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // this warp's sort window: keys, permutation, bin counters
     uint8_t* w_key = smem + OFF_WIN + (size_t)warp * WIN_BYTES;
@@ -292,7 +295,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                 do {
                     if (scanning) {
                         if (use_list) {
-                            if (scan_list<INSTR>(cf, s_cat, lp, lk_len, lk, s_list, cnt, ins)) scanning = false;
+                            if (scan_list<INSTR>(cf, sb_cat, lp, lk_len, lk, sb_row, cnt, ins)) scanning = false;
                         } else {
                             // sky-grid band walk (fp32, conservative): cells overlapping the scan cone
                             while (scanning && cnt < LIST_CAP) {
@@ -331,7 +334,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                     // Software-pipelined: the 32-byte record of star j+1 is in flight while star j is evaluated.
                     double2 r_lo = make_double2(0.0, 0.0), r_hi = make_double2(0.0, 0.0);
                     if (cnt > 0) {
-                        const double2* g = reinterpret_cast<const double2*>(a.cat64 + s_list[0]);
+                        const double2* g = reinterpret_cast<const double2*>(a.cat64 + lds_u16(sb_row));
                         r_lo = __ldg(g); r_hi = __ldg(g + 1);
                     }
                     for (int j = 0; j < cnt; ++j) {
@@ -340,7 +343,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                         s.star_id = (uint32_t)(__double_as_longlong(r_hi.y) & 0xffffffffll);
                         if (INSTR == 2) s.mag = __int_as_float((int)(__double_as_longlong(r_hi.y) >> 32));
                         if (j + 1 < cnt) {
-                            const double2* g = reinterpret_cast<const double2*>(a.cat64 + s_list[(j + 1) * TPB]);
+                            const double2* g = reinterpret_cast<const double2*>(a.cat64 + lds_u16(sb_row + (uint32_t)(j + 1) * (TPB * 2u)));
                             r_lo = __ldg(g); r_hi = __ldg(g + 1);
                         }
                         // (hand-pipelining Philox one star ahead, or two stars per iteration, both measured slower:
@@ -348,8 +351,8 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                         uint32_t x0, x1;
                         philox2x32_10(s.star_id, kb, ka, x0, x1);
                         bool det;
-                        if (PREC == 64) det = star_exact(c, s_tab, s, x0, x1, a.f_ideal, a.half_u, a.half_v, B);
-                        else det = star_f32(c, cf, s_tab, s, x0, x1, a.f_ideal, a.half_u, a.half_v, B);
+                        if (PREC == 64) det = star_exact(c, tabs, s, x0, x1, a.f_ideal, a.half_u, a.half_v, B);
+                        else det = star_f32(c, cf, tabs, s, x0, x1, a.f_ideal, a.half_u, a.half_v, B);
                         n_det += det ? 1 : 0;
                         if (INSTR == 2 && det) mag_faintest = fmaxf(mag_faintest, s.mag);
                     }

@@ -170,7 +170,33 @@ STMPM_HD double seed_rsqrt(double x) {   // ~2^-22 relative; x normal, positive,
 #endif
 }
 
-STMPM_HD void box_muller_tab(const MathTables* __restrict__ T, uint32_t wa, uint32_t wb, double& z1, double& z2) {
+// Table accessors: a plain pointer (host build, global memory) or a 32-bit shared-memory address (the trial kernel: explicit
+// ld.shared on a base kept in a register, so ptxas does not rebuild the shared-window base inside the star loop).
+struct TabPtr {
+    const MathTables* T;
+    STMPM_HD void log(int j, double& a, double& b) const { load2(T->log_tab[j], a, b); }
+    STMPM_HD void sc(int j, double& a, double& b) const { load2(T->sc_tab[j], a, b); }
+    STMPM_HD double k2(int k) const { return T->k_ln2[k]; }
+};
+#if defined(__CUDACC__)
+__device__ __forceinline__ void lds_d2(uint32_t addr, double& a, double& b) {
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
+struct TabSmem {
+    uint32_t base;   // shared address of the MathTables copy
+    __device__ __forceinline__ void log(int j, double& a, double& b) const { lds_d2(base + (uint32_t)j * 16u, a, b); }
+    __device__ __forceinline__ void sc(int j, double& a, double& b) const { lds_d2(base + 4096u + (uint32_t)j * 16u, a, b); }
+    __device__ __forceinline__ double k2(int k) const {
+        double v;
+        asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + 4096u + 16384u + (uint32_t)k * 8u));
+        return v;
+    }
+};
+#endif
+STMPM_HD void box_muller_tab(const MathTables* __restrict__ T, uint32_t wa, uint32_t wb, double& z1, double& z2);
+
+template <class Tab>
+STMPM_HD void box_muller_t(const Tab T, uint32_t wa, uint32_t wb, double& z1, double& z2) {
     // ---- L = -2 ln u1,  u1 = (2 wa + 1) 2^-33.  Exact int -> double through the 2^52 magic number (one DADD, no
     // conversion instruction, no clz / shift normalisation); exponent and mantissa then come from the bit pattern.
     const unsigned long long v = 2ull * wa + 1ull;                         // 33-bit odd integer
@@ -180,12 +206,12 @@ STMPM_HD void box_muller_tab(const MathTables* __restrict__ T, uint32_t wa, uint
     const double m = bits_to_double((tb & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull);   // mantissa in [1, 2)
     const int j = (int)(tb >> 44) & 0xFF;                                  // top 8 mantissa bits
     double inv_c, m2ln_c;
-    load2(T->log_tab[j], inv_c, m2ln_c);                                   // {1 / c_j, -2 ln c_j}
+    T.log(j, inv_c, m2ln_c);                                               // {1 / c_j, -2 ln c_j}
     const double r = fma(m, inv_c, -1.0);
     // log1p(r) = r - r^2/2 + r^3/3 - r^4/4 + r^5/5, |r| <= 2^-9 (truncation r^6/6 < 1e-17), Estrin form: depth 3
     const double r2 = r * r;
     const double p = fma(r2, fma(r2, fma(r, 0.2, -0.25), fma(r, 1.0 / 3.0, -0.5)), r);
-    const double L = fma(-2.0, p, m2ln_c) + T->k_ln2[k];                   // -2 ln m + 2 k ln 2  (tables hold the factor 2)
+    const double L = fma(-2.0, p, m2ln_c) + T.k2(k);                   // -2 ln m + 2 k ln 2  (tables hold the factor 2)
     // R = sqrt(L): seed y ~ 1/sqrt(L), R0 = L y, one Newton step on the square root: R = R0 + (L - R0^2) y / 2
     const double y = seed_rsqrt(L);
     const double R0 = L * y;
@@ -200,11 +226,14 @@ STMPM_HD void box_muller_tab(const MathTables* __restrict__ T, uint32_t wa, uint
     const double sd = fma(d * d2, -1.0 / 6.0, d);                        // truncation d^5/120 < 2.3e-15
     const double cd = fma(d2, fma(d2, 1.0 / 24.0, -0.5), 1.0);           // truncation d^6/720 < 1.2e-18
     double S, C;
-    load2(T->sc_tab[j2], S, C);
+    T.sc(j2, S, C);
     const double sq = fma(S, cd, C * sd);
     const double cq = fma(C, cd, -S * sd);
     z1 = R * cq;
     z2 = R * sq;
+}
+STMPM_HD void box_muller_tab(const MathTables* __restrict__ T, uint32_t wa, uint32_t wb, double& z1, double& z2) {
+    box_muller_t(TabPtr{T}, wa, wb, z1, z2);
 }
 
 #if defined(__CUDACC__)
@@ -352,6 +381,20 @@ __device__ __forceinline__ bool setup32(const TrialParams& p, float half_u, floa
     return true;
 }
 
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {            // read-only shared data (catalog)
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {         // survivor list (written by this thread)
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 // fp32 conservative geometric pre-filter on one shared-memory catalog entry (x, y, z, mag); magnitude tested by caller
 __device__ __forceinline__ bool prefilter_geom(const Ctx32& c, const float4 s) {
     const float dn = c.NI[0] * s.x + c.NI[1] * s.y + c.NI[2] * s.z;
@@ -365,7 +408,8 @@ __device__ __forceinline__ bool prefilter_geom(const Ctx32& c, const float4 s) {
 
 // Exact (fp64) star evaluation: MODEL.md §2-§4. Returns detected?; on detection adds b s^T into B.
 // (x0, x1) = the star's Philox2x32-10 words (MODEL.md §5), computed by the caller.
-__device__ __forceinline__ bool star_exact(const Ctx64& c, const MathTables* __restrict__ T, const StarRec& s,
+template <class Tab>
+__device__ __forceinline__ bool star_exact(const Ctx64& c, const Tab T, const StarRec& s,
                                            uint32_t x0, uint32_t x1, double f_ideal, double half_u, double half_v,
                                            double* __restrict__ B) {
     const double dn = c.NI[0] * s.x + c.NI[1] * s.y + c.NI[2] * s.z;
@@ -375,7 +419,7 @@ __device__ __forceinline__ bool star_exact(const Ctx64& c, const MathTables* __r
     // with 0 < dn <= 0.02 lands > 50 f from the array centre); clamp so the seed + Newton reciprocal stays in range
     const double lam = fast_div(c.np0, fmax(dn, 1e-3));
     double z1, z2;
-    box_muller_tab(T, x0, x1, z1, z2);
+    box_muller_t(T, x0, x1, z1, z2);
     const double um = fma(c.sx, z1, fma(lam, du, -c.cu));
     const double vm = fma(c.sy, z2, fma(lam, dv, -c.cv));
     const bool det = (dn > 0.0) && (fabs(um) <= half_u) && (fabs(vm) <= half_v);
@@ -397,7 +441,8 @@ __device__ __forceinline__ bool star_exact(const Ctx64& c, const MathTables* __r
 // centroid lies inside a guard band around the array edge, so detection counts stay bit-exact with the fp64 oracle;
 // (b) B is accumulated in fp64 against the fp64 reference vector — roll about the boresight is ~1/sin(FOV/2) less
 // observable than pointing, and fp32 partial sums of B (ulp ~1e-6 at |B| ~ 16) would cost ~1e-6 rad of roll.
-__device__ __forceinline__ bool star_f32(const Ctx64& c, const Ctx32& cf, const MathTables* __restrict__ T,
+template <class Tab>
+__device__ __forceinline__ bool star_f32(const Ctx64& c, const Ctx32& cf, const Tab T,
                                          const StarRec& s, uint32_t x0, uint32_t x1, double f_ideal, double half_u,
                                          double half_v, double* __restrict__ B) {
     const float sx = (float)s.x, sy = (float)s.y, sz = (float)s.z;
