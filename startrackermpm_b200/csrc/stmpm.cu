@@ -134,7 +134,9 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
     double* s_red = reinterpret_cast<double*>(smem + OFF_RED);
     // 32-bit shared-memory addresses of the hot regions, kept in registers (see lds_f4 / TabSmem)
     const uint32_t sb = smem_u32(smem);
-    const uint32_t sb_cat = sb + (uint32_t)OFF_CAT, sb_row = sb + (uint32_t)OFF_LIST + threadIdx.x * 2u;
+    const uint32_t sb_cat = sb + (uint32_t)OFF_CAT;
+    uint32_t sb_row = sb + (uint32_t)OFF_LIST + threadIdx.x * 2u;
+    asm volatile("" : "+r"(sb_row));   // keep it: ptxas otherwise re-reads %tid.x and re-adds at every list push
     const TabSmem tabs{sb + (uint32_t)OFF_TAB};
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // this warp's sort window: keys, permutation, bin counters
