@@ -62,32 +62,32 @@ constexpr size_t OFF_MBAR = OFF_RED + (size_t)(TPB / 32) * 8 * 8;
 constexpr size_t OFF_LKBAND = OFF_MBAR + 16;
 constexpr size_t OFF_BAND = OFF_LKBAND + (size_t)LK_BANDS * 8;
 constexpr size_t OFF_CAT = (OFF_BAND + (size_t)MAX_BANDS * 8 + 127) / 128 * 128;
-static size_t smem_total(int n_stars) { return OFF_CAT + (size_t)n_stars * 16; }
+static size_t smem_total(int n_stars) { return OFF_CAT + (size_t)(n_stars + 1) * 16; }   // + the +inf terminator star
 
 // Walks the magnitude-sorted candidate list of the boresight's lookup cell from position lk on, pushing pre-filter
 // survivors to row[cnt * TPB]; the first star fainter than MAX_MAGNITUDE ends the scan (returns true).  Returns false
 // while candidates remain and fewer than 8 row slots are free: the caller drains the row and calls again.
+// Every list ends with at least one entry that points at a dummy catalog star of magnitude +inf (index n_stars), so the
+// magnitude test alone terminates the walk: no per-entry sentinel or bounds check, and the next pack can always be
+// prefetched (the list array is padded by one pack).
 template <int INSTR>
-__device__ __forceinline__ bool scan_list(const Ctx32& c, uint32_t sb_cat, const uint16_t* __restrict__ lp, int lk_len, int& lk,
-                                          uint32_t sb_row, int& cnt, unsigned long long* ins) {
-    if (lk >= lk_len) return true;
-    uint4 pk_next = __ldg(reinterpret_cast<const uint4*>(lp + lk));
+__device__ __forceinline__ bool scan_list(const Ctx32& c, uint32_t sb_cat, const uint16_t* __restrict__& lp, uint32_t sb_row,
+                                          int& cnt, unsigned long long* ins) {
+    uint4 pk_next = __ldg(reinterpret_cast<const uint4*>(lp));
     while (cnt <= LIST_CAP - 8) {
         const uint4 pk = pk_next;
-        lk += 8;
-        if (lk < lk_len) pk_next = __ldg(reinterpret_cast<const uint4*>(lp + lk));   // prefetch the next 8 candidates
+        lp += 8;
+        pk_next = __ldg(reinterpret_cast<const uint4*>(lp));                          // prefetch the next 8 candidates
         const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const uint32_t idx = (w4[e >> 1] >> (16 * (e & 1))) & 0xffffu;
-            if (idx == 0xffffu) return true;
             const float4 sc = lds_f4(sb_cat + idx * 16u);
             if (INSTR == 1) ++ins[0];
             if (!(sc.w <= c.magf)) return true;          // sorted by magnitude: every later star is fainter still
             if (INSTR == 1) ++ins[1];
             if (prefilter_geom(c, sc)) { sts_u16(sb_row + (uint32_t)cnt * (TPB * 2u), idx); ++cnt; if (INSTR == 1) ++ins[2]; }
         }
-        if (lk >= lk_len) return true;
     }
     return false;
 }
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
     if (threadIdx.x == 0) mbar_init(s_bar, 1);
     __syncthreads();
     if (threadIdx.x == 0) {
-        const uint32_t total = (uint32_t)a.n_stars * 16u;
+        const uint32_t total = (uint32_t)(a.n_stars + 1) * 16u;
         mbar_expect_tx(s_bar, total);
         const unsigned char* src = reinterpret_cast<const unsigned char*>(a.cat32);
         unsigned char* dst = reinterpret_cast<unsigned char*>(s_cat);
@@ -274,15 +274,12 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                 // ---- phase-A state.  Fast path: the magnitude-sorted candidate list of the boresight's lookup cell.
                 // Fallback (scan cone wider than the lists were built for): walk the sky-grid bands.
                 const bool use_list = cf.cone <= a.lk_cone;
-                const uint16_t* lp = a.lk_list;
-                int lk = 0, lk_len = 0;
+                const uint16_t* __restrict__ lp = a.lk_list;
                 int b = 0, b_hi = -1, i = 0, i_end = 0, pi = 0, p_end = 0;
                 float dalpha = -1.0f;
                 if (use_list) {
                     const int cell = lookup_cell(s_lkband, a.lk_bands, a.lk_inv_band_h, cf.ra0, cf.dec0);
-                    const uint32_t o0 = __ldg(a.lk_off + cell), o1 = __ldg(a.lk_off + cell + 1);
-                    lp += o0;
-                    lk_len = (int)(o1 - o0);
+                    lp += __ldg(a.lk_off + cell);
                 } else {
                     b = max(0, (int)floorf((cf.dec0 - cf.cone + 1.57079633f) * a.inv_band_h));
                     b_hi = min(a.n_bands - 1, (int)floorf((cf.dec0 + cf.cone + 1.57079633f) * a.inv_band_h));
@@ -297,7 +294,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                 do {
                     if (scanning) {
                         if (use_list) {
-                            if (scan_list<INSTR>(cf, sb_cat, lp, lk_len, lk, sb_row, cnt, ins)) scanning = false;
+                            if (scan_list<INSTR>(cf, sb_cat, lp, sb_row, cnt, ins)) scanning = false;
                         } else {
                             // sky-grid band walk (fp32, conservative): cells overlapping the scan cone
                             while (scanning && cnt < LIST_CAP) {
@@ -590,12 +587,13 @@ static int rebuild_lists(stmpm_handle* h) {
                 }
                 while (lev < KEY_LEVELS) kt[lev++] = (uint8_t)std::min(n_in, 255);
             }
-            while ((list.size() - start) % 8) list.push_back((uint16_t)0xffff);
+            list.push_back((uint16_t)S);                                    // terminator: the +inf dummy star
+            while ((list.size() - start) % 8) list.push_back((uint16_t)S);
             if (list.size() > 0xfffffff0ull) return fail(STMPM_E_ARG, "candidate lists exceed 2^32 entries: field of view too wide");
             off[bt[b].x + rc + 1] = (uint32_t)list.size();
         }
     }
-    if (list.empty()) list.resize(8, (uint16_t)0xffff);
+    for (int k = 0; k < 8; ++k) list.push_back((uint16_t)S);              // one pack of slack for the unconditional prefetch
     cudaFree(h->lk_band_tab); cudaFree(h->lk_off); cudaFree(h->lk_list);
     h->lk_band_tab = nullptr; h->lk_off = nullptr; h->lk_list = nullptr;
     CK(cudaMalloc(&h->lk_band_tab, sizeof(int2) * nb));
@@ -672,8 +670,8 @@ extern "C" int stmpm_device_info(stmpm_t* h, int32_t* sm_count, int64_t* smem_pe
 extern "C" int stmpm_set_catalog(stmpm_t* h, const double* xyz, const float* mag, const int32_t* star_id,
                                  int32_t n_stars, int32_t n_bands, const int32_t* n_ra, const int32_t* cell_start) {
     if (!h || !xyz || !mag || !star_id || !n_ra || !cell_start) return fail(STMPM_E_ARG, "stmpm_set_catalog: null");
-    if (n_stars <= 0 || n_stars > 65535)
-        return fail(STMPM_E_ARG, "stmpm_set_catalog: n_stars must be in [1, 65535] (16-bit shared-memory cell index)");
+    if (n_stars <= 0 || n_stars > 65534)
+        return fail(STMPM_E_ARG, "stmpm_set_catalog: n_stars must be in [1, 65534] (16-bit candidate indices + one terminator)");
     if (n_bands <= 0 || n_bands > 4096) return fail(STMPM_E_ARG, "stmpm_set_catalog: bad n_bands");
     CK(cudaSetDevice(h->device));
     long long n_cells = 0;
@@ -691,7 +689,8 @@ extern "C" int stmpm_set_catalog(stmpm_t* h, const double* xyz, const float* mag
         if (c && cell_start[c] < cell_start[c - 1]) return fail(STMPM_E_ARG, "stmpm_set_catalog: cell_start not sorted");
         cs[c] = (uint16_t)cell_start[c];
     }
-    std::vector<float4> c32(n_stars);
+    std::vector<float4> c32(n_stars + 1);
+    c32[n_stars] = make_float4(0.0f, 0.0f, 1.0f, INFINITY);                // dummy list terminator: never passes a magnitude test
     std::vector<StarRec> c64(n_stars);
     for (int i = 0; i < n_stars; ++i) {
         c32[i] = make_float4((float)xyz[3 * i], (float)xyz[3 * i + 1], (float)xyz[3 * i + 2], mag[i]);
@@ -700,11 +699,11 @@ extern "C" int stmpm_set_catalog(stmpm_t* h, const double* xyz, const float* mag
     }
     cudaFree(h->cat32); cudaFree(h->cat64); cudaFree(h->cell_start); cudaFree(h->band_tab);
     h->cat32 = nullptr; h->cat64 = nullptr; h->cell_start = nullptr; h->band_tab = nullptr;
-    CK(cudaMalloc(&h->cat32, sizeof(float4) * n_stars));
+    CK(cudaMalloc(&h->cat32, sizeof(float4) * (n_stars + 1)));
     CK(cudaMalloc(&h->cat64, sizeof(StarRec) * n_stars));
     CK(cudaMalloc(&h->cell_start, sizeof(uint16_t) * n_pad));
     CK(cudaMalloc(&h->band_tab, sizeof(int2) * n_bands));
-    CK(cudaMemcpy(h->cat32, c32.data(), sizeof(float4) * n_stars, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->cat32, c32.data(), sizeof(float4) * (n_stars + 1), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->cat64, c64.data(), sizeof(StarRec) * n_stars, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->cell_start, cs.data(), sizeof(uint16_t) * n_pad, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->band_tab, bt.data(), sizeof(int2) * n_bands, cudaMemcpyHostToDevice));

@@ -320,7 +320,9 @@ __device__ __forceinline__ void window_and_cone(const TrialParams& p, float half
     const float noise = 6.8f * fmaxf(fabsf((float)p.devx), fabsf((float)p.devy)) + 0.05f + 1e-5f * ff;
     c.limu = opaque(half_u + noise);
     c.limv = opaque(half_v + noise);
-    c.magf = opaque(__double2float_rd(p.maxmag));   // (double)mag <= maxmag  <=>  mag <= round-down-to-float(maxmag)
+    // (double)mag <= maxmag  <=>  mag <= round-down-to-float(maxmag); clamped to a finite value so that the +inf
+    // magnitude of the candidate lists' terminator entry never passes
+    c.magf = opaque(fminf(__double2float_rd(p.maxmag), 3.0e38f));
     const float reach = 1.41421357f * (fmaxf(half_u, half_v) + noise) + hypotf((float)p.ex, (float)p.ey) + 1.0f;
     const float tilt = fminf((fabsf((float)p.phi) + fabsf((float)p.theta)) * 0.0174532925f, 0.5f);
     const float depth = (float)p.f + (float)p.ez - reach * tilt;

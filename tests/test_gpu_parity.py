@@ -64,6 +64,7 @@ def test_stress_configs(engine, catalog, prec):
         "neg_dev": trial.sample_params(dict(BASIC_MEAN, BASE_DEV_X=-0.3, BASE_DEV_Y=-0.2), ZERO_SIGMA, 0.0, 5, 0, 600),
         # tilts beyond the small-angle series (> 0.1 rad) and beyond the candidate lists' cone -> sky-grid band scan
         "big_tilt": trial.sample_params(dict(BASIC_MEAN, F_ARR_PHI=7.0, F_ARR_THETA=-6.5, F_ARR_PSI=30.0), BASIC_SIGMA, 0.0, 5, 0, 400),
+        "inf_mag": trial.sample_params(dict(BASIC_MEAN, MAX_MAGNITUDE=np.inf), ZERO_SIGMA, 0.0, 5, 0, 200),
         "big_shift": trial.sample_params(dict(BASIC_MEAN, F_ARR_EPS_X=60.0, F_ARR_EPS_Y=-45.0), BASIC_SIGMA, 0.0, 5, 0, 400),
     }
     polar = trial.sample_params(BASIC_MEAN, BASIC_SIGMA, 0.0, 5, 0, 720)
