@@ -319,9 +319,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--trials", type=float, default=1e8, help="trials per GPU per step (configs[1]: 1e8)")
     ap.add_argument("--e2e-trials", type=float, default=1e8, help="trials per GPU per e2e step")
-    ap.add_argument("--cpu-trials-per-core", type=int, default=16384)
+    ap.add_argument("--cpu-trials-per-core", type=int, default=None,
+                    help="oracle-port trials per host process: default 131072 for the cpu_baseline leg (~13 s), 32768 per step "
+                         "for --impl reference (~3 s per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.cpu_trials_per_core is None:
+        args.cpu_trials_per_core = 32768 if args.impl == "reference" else 131072
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_ours(args)
