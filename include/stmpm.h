@@ -68,6 +68,13 @@ typedef struct {
     double mean_ndet;
 } stmpm_summary;
 
+/* toolplot.py:82-99 (mode 'm'): RMS about 0, 6-sigma clip, bins-bin density histogram over [min, max] of the kept values,
+ * mode = left edge of the fullest bin, sigma about the mode. */
+typedef struct {
+    double n, rms, n_kept, kept_min, kept_max, mode, sigma_about_mode;
+    int32_t mode_bin, reserved;
+} stmpm_toolplot;
+
 const char* stmpm_last_error(void);
 int stmpm_version(void);
 
@@ -129,6 +136,11 @@ int stmpm_run_presampled_host_ex(stmpm_t* h, int precision, int64_t n, uint64_t 
 int stmpm_run_rng_host(stmpm_t* h, int precision, int64_t n_segments, int64_t trials_per_segment, uint64_t seed,
                        int64_t trial0, const stmpm_dist* dists_host, double* err_arcsec_host, int32_t* n_det_host,
                        double* stats_host);
+
+/* toolplot.py's reductions on the device from n per-trial error records (err < 0 = failed trial = a row the reference
+ * dropped).  density_host (optional) receives the `bins` values of np.histogram(kept, bins, density=True)[0]. */
+int stmpm_toolplot_reduce(stmpm_t* h, const double* err_arcsec_dev, int64_t n, int32_t bins, stmpm_toolplot* out,
+                          double* density_host, void* stream);
 
 /* FMA-chain microbenchmark: measured FP64 / FP32 FMA peak of this GPU in TFLOP/s (roofline denominator). */
 int stmpm_fma_peak(stmpm_t* h, int precision, double* tflops);

@@ -84,9 +84,12 @@ def toolplot_reductions(x, bins: int = 50):
     """toolplot.py:82-99 on an error sample: RMS, 6-sigma clip, density histogram, mode (left edge of the fullest bin),
     sigma about the mode."""
     x = np.asarray(x, dtype=np.float64)
-    rms = np.sqrt((x ** 2).sum() / x.size)
-    kept = x[x <= 6 * rms]
-    h = np.histogram(kept, bins=bins, density=True)
-    mode = h[1][np.argmax(h[0])]
-    newsig = np.sqrt(((kept - mode) ** 2).sum() / kept.size)
-    return {"rms": rms, "n_kept": kept.size, "mode": mode, "sigma_about_mode": newsig}
+    x = x[x >= 0.0]                                         # failed trials are rows the reference dropped (driver.py:321)
+    rms = np.sqrt((x ** 2).sum() / x.size)                  # toolplot.py:82
+    kept = x[x <= 6 * rms]                                  # toolplot.py:83
+    h = np.histogram(kept, bins=bins, density=True)         # toolplot.py:89
+    hmax = int(np.argmax(h[0]))                             # toolplot.py:90
+    mode = h[1][hmax]                                       # toolplot.py:96
+    newsig = np.sqrt(((kept - mode) ** 2).sum() / kept.size)  # toolplot.py:99
+    return {"n": x.size, "rms": rms, "n_kept": kept.size, "kept_min": kept.min(), "kept_max": kept.max(), "mode": mode,
+            "mode_bin": hmax, "sigma_about_mode": newsig, "density": h[0]}

@@ -24,7 +24,7 @@ NORMAL_PARAMS = ("FOCAL_LENGTH", "F_ARR_EPS_X", "F_ARR_EPS_Y", "F_ARR_EPS_Z", "F
 EXPORTS = ("stmpm_last_error", "stmpm_version", "stmpm_create", "stmpm_destroy", "stmpm_device_info",
            "stmpm_set_catalog", "stmpm_set_sensor", "stmpm_stats_len", "stmpm_stats_finalize",
            "stmpm_trials_presampled", "stmpm_trials_presampled_ex", "stmpm_trials_rng", "stmpm_fill_presampled", "stmpm_run_presampled_host", "stmpm_run_presampled_host_ex",
-           "stmpm_run_rng_host", "stmpm_fma_peak", "stmpm_work_counters", "stmpm_debug_box_muller", "stmpm_launch_count")
+           "stmpm_run_rng_host", "stmpm_toolplot_reduce", "stmpm_fma_peak", "stmpm_work_counters", "stmpm_debug_box_muller", "stmpm_launch_count")
 
 
 class SensorCfg(C.Structure):
@@ -39,6 +39,11 @@ class Dist(C.Structure):
 class Summary(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("n_ok", "n_fail", "fail_rate", "mean", "std", "rms", "sigma_halfnormal",
                                           "mean_halfnormal", "p50", "p90", "p99", "p999", "x_max", "mean_ndet")]
+
+
+class Toolplot(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("n", "rms", "n_kept", "kept_min", "kept_max", "mode", "sigma_about_mode")] + \
+               [("mode_bin", C.c_int32), ("reserved", C.c_int32)]
 
 
 class StmpmError(RuntimeError):
@@ -76,6 +81,7 @@ def load():
     lib.stmpm_fill_presampled.argtypes = [vp, i64, u64, i64, P(Dist), P(vp), vp]
     lib.stmpm_run_presampled_host.argtypes = [vp, C.c_int, i64, u64, i64, P(vp), vp, vp, vp]
     lib.stmpm_run_rng_host.argtypes = [vp, C.c_int, i64, i64, u64, i64, P(Dist), vp, vp, vp]
+    lib.stmpm_toolplot_reduce.argtypes = [vp, vp, i64, i32, P(Toolplot), vp, vp]
     lib.stmpm_fma_peak.argtypes = [vp, C.c_int, P(dbl)]
     lib.stmpm_work_counters.argtypes = [vp, i64, u64, i64, P(Dist), P(dbl)]
     lib.stmpm_debug_box_muller.argtypes = [vp, vp, i64, vp, vp]

@@ -437,6 +437,62 @@ __global__ void __launch_bounds__(256) fill_presampled_kernel(long long n, long 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ toolplot reductions
+// toolplot.py:82-99 on the device, from the per-trial error records (failed trials, err < 0, are the rows the reference
+// dropped).  acc layout (doubles): [0] n, [1] sum x^2 | [2] n_kept, [3] sum x, [4] sum x^2, [5] min bits, [6] max bits.
+__global__ void __launch_bounds__(256) toolplot_pass1(const double* __restrict__ x, long long n, double* acc) {
+    double c = 0.0, s2 = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = __ldcs(x + i);
+        if (v >= 0.0) { c += 1.0; s2 = fma(v, v, s2); }
+    }
+    for (int off = 16; off > 0; off >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, off); s2 += __shfl_xor_sync(0xffffffffu, s2, off); }
+    if ((threadIdx.x & 31) == 0 && c > 0.0) { atomicAdd(acc + 0, c); atomicAdd(acc + 1, s2); }
+}
+__global__ void __launch_bounds__(256) toolplot_pass2(const double* __restrict__ x, long long n, double* acc) {
+    const double clip = 6.0 * sqrt(acc[1] / acc[0]);                       // toolplot.py:82-83
+    double c = 0.0, s1 = 0.0, s2 = 0.0, mn = INFINITY, mx = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = __ldcs(x + i);
+        if (v >= 0.0 && v <= clip) { c += 1.0; s1 += v; s2 = fma(v, v, s2); mn = fmin(mn, v); mx = fmax(mx, v); }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        c += __shfl_xor_sync(0xffffffffu, c, off); s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, off)); mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    }
+    if ((threadIdx.x & 31) == 0 && c > 0.0) {
+        atomicAdd(acc + 2, c); atomicAdd(acc + 3, s1); atomicAdd(acc + 4, s2);
+        atomicMin(reinterpret_cast<unsigned long long*>(acc + 5), (unsigned long long)__double_as_longlong(mn));   // x >= 0:
+        atomicMax(reinterpret_cast<unsigned long long*>(acc + 6), (unsigned long long)__double_as_longlong(mx));   // bit order == value order
+    }
+}
+__global__ void __launch_bounds__(256) toolplot_pass3(const double* __restrict__ x, long long n, const double* acc, int bins,
+                                                      unsigned long long* hist) {
+    extern __shared__ unsigned int s_h[];
+    for (int i = threadIdx.x; i < bins; i += blockDim.x) s_h[i] = 0u;
+    __syncthreads();
+    const double clip = 6.0 * sqrt(acc[1] / acc[0]);
+    const double lo = __longlong_as_double((long long)reinterpret_cast<const unsigned long long*>(acc)[5]);
+    const double hi = __longlong_as_double((long long)reinterpret_cast<const unsigned long long*>(acc)[6]);
+    const double step = (hi - lo) / (double)bins;                          // numpy.linspace(lo, hi, bins + 1)
+    const double norm = hi > lo ? (double)bins / (hi - lo) : 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = __ldcs(x + i);
+        if (v >= 0.0 && v <= clip) {
+            // numpy.histogram: provisional index from the scaled position, then corrected against the actual edges
+            int b = (int)((v - lo) * norm);
+            if (b >= bins) b = bins - 1;
+            const double e0 = lo + (double)b * step, e1 = (b + 1 == bins) ? hi : lo + (double)(b + 1) * step;
+            if (v < e0 && b > 0) --b;
+            else if (v >= e1 && b != bins - 1) ++b;
+            atomicAdd(&s_h[b], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < bins; i += blockDim.x) if (s_h[i]) atomicAdd(hist + i, (unsigned long long)s_h[i]);
+}
+
 // ------------------------------------------------------------------------------------------------ FMA peak kernels
 template <typename T>
 __global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T b) {
@@ -1079,6 +1135,53 @@ extern "C" int stmpm_debug_box_muller(const uint32_t* wa, const uint32_t* wb, in
     MathTables mt;
     stmpm_host_tables(&mt);
     for (int64_t i = 0; i < n; ++i) box_muller_tab(&mt, wa[i], wb[i], z1[i], z2[i]);
+    return 0;
+}
+
+extern "C" int stmpm_toolplot_reduce(stmpm_t* h, const double* err_dev, int64_t n, int32_t bins, stmpm_toolplot* out,
+                                     double* density_host, void* stream) {
+    if (!h || !err_dev || !out || n <= 0 || bins < 1 || bins > 4096)
+        return fail(STMPM_E_ARG, "stmpm_toolplot_reduce: bad arguments");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    double* acc = nullptr;
+    CK(cudaMalloc(&acc, sizeof(double) * 8 + sizeof(unsigned long long) * bins));
+    unsigned long long* hist = reinterpret_cast<unsigned long long*>(acc + 8);
+    CK(cudaMemsetAsync(acc, 0, sizeof(double) * 8 + sizeof(unsigned long long) * bins, st));
+    const unsigned long long inf_bits = 0x7FF0000000000000ull;
+    CK(cudaMemcpyAsync(acc + 5, &inf_bits, 8, cudaMemcpyHostToDevice, st));
+    const int grid = (int)std::min<long long>((n + 255) / 256, (long long)h->prop.multiProcessorCount * 16);
+    toolplot_pass1<<<grid, 256, 0, st>>>(err_dev, n, acc);
+    toolplot_pass2<<<grid, 256, 0, st>>>(err_dev, n, acc);
+    toolplot_pass3<<<grid, 256, sizeof(unsigned int) * bins, st>>>(err_dev, n, acc, bins, hist);
+    CK(cudaGetLastError());
+    h->launches += 3;
+    std::vector<double> a(8);
+    std::vector<unsigned long long> hh(bins);
+    CK(cudaMemcpyAsync(a.data(), acc, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hh.data(), hist, sizeof(unsigned long long) * bins, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(acc);
+    std::memset(out, 0, sizeof(*out));
+    out->n = a[0];
+    if (a[0] <= 0) return 0;
+    out->rms = std::sqrt(a[1] / a[0]);                                     // toolplot.py:82
+    out->n_kept = a[2];
+    if (a[2] <= 0) return 0;
+    double lo, hi;
+    std::memcpy(&lo, &a[5], 8); std::memcpy(&hi, &a[6], 8);
+    out->kept_min = lo; out->kept_max = hi;
+    int arg = 0;
+    for (int i = 1; i < bins; ++i) if (hh[i] > hh[arg]) arg = i;          // numpy.argmax: first maximum
+    out->mode_bin = arg;
+    const double step = (hi - lo) / (double)bins;
+    out->mode = lo + arg * step;                                           // h[1][hmax]: left edge (toolplot.py:90,96)
+    const double m = out->mode;
+    out->sigma_about_mode = std::sqrt(std::max(0.0, (a[4] - 2.0 * m * a[3] + a[2] * m * m) / a[2]));   // toolplot.py:99
+    if (density_host) {
+        const double w = hi > lo ? step : 1.0;
+        for (int i = 0; i < bins; ++i) density_host[i] = (double)hh[i] / (a[2] * w);
+    }
     return 0;
 }
 

@@ -197,6 +197,17 @@ class TrialEngine:
                                               int(seed) & (2**64 - 1), int(trial0), arr, _ptr(err), _ptr(ndet),
                                               _ptr(stats), int(stream)))
 
+    def toolplot_reduce(self, err, bins: int = 50, stream: int = 0) -> dict:
+        """toolplot.py:82-99 on the device: `err` is a float64 CUDA tensor of per-trial errors [arcsec] (-1 = failed).
+        Returns rms, n_kept (<= 6 rms), mode (left edge of the fullest of `bins` bins), sigma_about_mode, density[bins]."""
+        n = int(err.shape[0])
+        out = _abi.Toolplot()
+        dens = np.empty(int(bins), dtype=np.float64)
+        _abi.check(self._lib.stmpm_toolplot_reduce(self._h, _ptr(err), n, int(bins), C.byref(out), _ptr(dens), int(stream)))
+        d = {k: getattr(out, k) for k, _ in _abi.Toolplot._fields_ if k != "reserved"}
+        d["density"] = dens
+        return d
+
     # ---------------------------------------------------------------- statistics
     def summarize(self, stats: np.ndarray) -> dict:
         return summarize(stats, self.hist_log2_sub)

@@ -243,3 +243,27 @@ def test_star_mag_output_is_bit_exact(engine, catalog):
         compare(e, d, e_ref, d_ref, prec)
         assert np.array_equal(m, aux["maxmag"])
     assert np.isneginf(m[d_ref == 0]).all() and (d_ref == 0).any()
+
+
+def test_toolplot_reductions_on_device(engine):
+    """toolplot.py:82-99 (RMS, 6-sigma clip, 50-bin density histogram, mode, sigma about the mode) from device records."""
+    n = 400_000
+    dist = make_dist(BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF)
+    err = torch.empty(n, dtype=torch.float64, device="cuda")
+    ndet = torch.empty(n, dtype=torch.int32, device="cuda")
+    stats = torch.zeros(engine.stats_len, dtype=torch.float64, device="cuda")
+    engine.run_rng_device(dist, n, stats, err, ndet, seed=8)
+    torch.cuda.synchronize()
+    x = err.cpu().numpy()
+    x[:50] = 1e5                                                       # outliers beyond the 6-sigma clip
+    x[50:60] = -1.0
+    err.copy_(torch.from_numpy(x))
+    for bins in (50, 7):
+        got = engine.toolplot_reduce(err, bins=bins)
+        want = ostats.toolplot_reductions(x, bins=bins)
+        assert got["n"] == want["n"] and got["n_kept"] == want["n_kept"] and got["n_kept"] < got["n"]
+        assert got["kept_min"] == want["kept_min"] and got["kept_max"] == want["kept_max"]
+        assert got["mode_bin"] == want["mode_bin"] and got["mode"] == pytest.approx(want["mode"], rel=1e-14)
+        assert got["rms"] == pytest.approx(want["rms"], rel=1e-12)
+        assert got["sigma_about_mode"] == pytest.approx(want["sigma_about_mode"], rel=1e-10)
+        assert np.allclose(got["density"], want["density"], rtol=1e-12, atol=0)      # identical bin counts
