@@ -210,24 +210,26 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                     decf = fminf(fmaxf(decf, -1.57079633f), 1.57079633f);
                     const int cell = lookup_cell(s_lkband, a.lk_bands, a.lk_inv_band_h, raf, decf);
                     const int lev = min(KEY_LEVELS - 1, (int)floorf(((float)mm - KEY_M0) * 16.0f));
-                    key = lev < 0 ? 0 : (int)(__ldg(a.lk_key + (size_t)cell * KEY_LEVELS + lev) >> 2);
+                    key = lev < 0 ? 0 : (int)(__ldg(a.lk_key + (size_t)cell * KEY_LEVELS + lev) >> 1);
                 }
                 w_key[r] = (uint8_t)key;
                 atomicAdd(reinterpret_cast<unsigned int*>(w_hist) + (key >> 1), (key & 1) ? 0x10000u : 1u);
             }
             __syncwarp();
-            {   // exclusive scan of the 64 bins: 2 per lane
-                const uint32_t h0 = w_hist[2 * lane], h1 = w_hist[2 * lane + 1];
-                uint32_t incl = h0 + h1;
+            {   // exclusive scan of the 128 bins: 4 per lane
+                uint32_t hv[4], tot = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { hv[q] = w_hist[4 * lane + q]; tot += hv[q]; }
+                uint32_t incl = tot;
 #pragma unroll
                 for (int off = 1; off < 32; off <<= 1) {
                     const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
                     if (lane >= off) incl += o;
                 }
-                const uint32_t excl = incl - (h0 + h1);
+                uint32_t run = incl - tot;
                 __syncwarp();
-                w_hist[2 * lane] = (uint16_t)excl;
-                w_hist[2 * lane + 1] = (uint16_t)(excl + h0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { w_hist[4 * lane + q] = (uint16_t)run; run += hv[q]; }
             }
             __syncwarp();
             for (int r = lane; r < win; r += 32) {
