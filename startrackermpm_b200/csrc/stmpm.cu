@@ -51,7 +51,8 @@ struct KArgs {
 
 // Shared-memory layout: every region at a COMPILE-TIME offset (fixed-size regions first, the variable-size catalog
 // last), so ptxas addresses them as [reg + immediate] instead of re-deriving bases from kernel parameters per access.
-constexpr size_t WIN_BYTES = WIN_MAX /*keys u8*/ + 2 * WIN_MAX /*perm u16*/ + 2 * KEY_BINS /*hist u16*/;
+constexpr size_t WIN_BYTES = WIN_MAX /*keys u8*/ + 2 * WIN_MAX /*perm u16*/ + KEY_BINS /*bin counters u8*/;
+static_assert(WIN_MAX <= 128 && KEY_BINS == 256, "byte-wide bin counters: counts and offsets must stay below 256");
 constexpr int LK_BANDS = 180;          // 1-degree lookup grid
 constexpr int MAX_BANDS = 256;         // sky-grid declination bands (fallback scan)
 constexpr size_t OFF_LIST = 0;
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
     // this warp's sort window: keys, permutation, bin counters
     uint8_t* w_key = smem + OFF_WIN + (size_t)warp * WIN_BYTES;
     uint16_t* w_perm = reinterpret_cast<uint16_t*>(w_key + WIN_MAX);
-    uint16_t* w_hist = w_perm + WIN_MAX;
+    unsigned int* w_hist = reinterpret_cast<unsigned int*>(w_perm + WIN_MAX);   // 256 byte-wide counters, 4 per word
 
     // ---- stage the catalog + tables into shared memory (once per CTA; the CTA is persistent).  The 146 KB fp32 catalog
     // goes through the TMA unit: one elected thread issues cp.async.bulk chunks that complete on an mbarrier while the
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
             const long long rec0 = seg * a.trials_per_segment + wb;
 
             // ================= key pass: work key per trial, warp-local counting sort
-            for (int i = lane; i < KEY_BINS; i += 32) w_hist[i] = 0;
+            w_hist[lane] = 0u; w_hist[lane + 32] = 0u;
             __syncwarp();
             for (int r = lane; r < win; r += 32) {
                 int key = KEY_BINS - 1;                               // padding slots sort last
@@ -210,33 +211,38 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                     decf = fminf(fmaxf(decf, -1.57079633f), 1.57079633f);
                     const int cell = lookup_cell(s_lkband, a.lk_bands, a.lk_inv_band_h, raf, decf);
                     const int lev = min(KEY_LEVELS - 1, (int)floorf(((float)mm - KEY_M0) * 16.0f));
-                    key = lev < 0 ? 0 : (int)(__ldg(a.lk_key + (size_t)cell * KEY_LEVELS + lev) >> 1);
+                    key = lev < 0 ? 0 : (int)__ldg(a.lk_key + (size_t)cell * KEY_LEVELS + lev);
                 }
                 w_key[r] = (uint8_t)key;
-                atomicAdd(reinterpret_cast<unsigned int*>(w_hist) + (key >> 1), (key & 1) ? 0x10000u : 1u);
+                atomicAdd(w_hist + (key >> 2), 1u << (8 * (key & 3)));
             }
             __syncwarp();
-            {   // exclusive scan of the 128 bins: 4 per lane
-                uint32_t hv[4], tot = 0;
+            {   // exclusive scan of the 256 byte counters: lane owns bins 8 lane .. 8 lane + 7 (two words)
+                const uint32_t w0 = w_hist[2 * lane], w1 = w_hist[2 * lane + 1];
+                uint32_t hv[8], tot = 0;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { hv[q] = w_hist[4 * lane + q]; tot += hv[q]; }
+                for (int q = 0; q < 4; ++q) { hv[q] = (w0 >> (8 * q)) & 0xffu; hv[4 + q] = (w1 >> (8 * q)) & 0xffu; }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) tot += hv[q];
                 uint32_t incl = tot;
 #pragma unroll
                 for (int off = 1; off < 32; off <<= 1) {
                     const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
                     if (lane >= off) incl += o;
                 }
-                uint32_t run = incl - tot;
-                __syncwarp();
+                uint32_t run = incl - tot, o0 = 0, o1 = 0;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { w_hist[4 * lane + q] = (uint16_t)run; run += hv[q]; }
+                for (int q = 0; q < 4; ++q) { o0 |= (run & 0xffu) << (8 * q); run += hv[q]; }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { o1 |= (run & 0xffu) << (8 * q); run += hv[4 + q]; }
+                __syncwarp();
+                w_hist[2 * lane] = o0; w_hist[2 * lane + 1] = o1;
             }
             __syncwarp();
             for (int r = lane; r < win; r += 32) {
                 const int key = w_key[r];
-                const unsigned int old = atomicAdd(reinterpret_cast<unsigned int*>(w_hist) + (key >> 1),
-                                                   (key & 1) ? 0x10000u : 1u);
-                w_perm[(key & 1) ? (old >> 16) : (old & 0xffffu)] = (uint16_t)r;
+                const unsigned int old = atomicAdd(w_hist + (key >> 2), 1u << (8 * (key & 3)));
+                w_perm[(old >> (8 * (key & 3))) & 0xffu] = (uint16_t)r;
             }
             __syncwarp();
 

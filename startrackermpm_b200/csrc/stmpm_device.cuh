@@ -26,7 +26,7 @@ constexpr int WIN_MAX = 128;      // largest warp-local sort window (trials)
 constexpr int WIN_DEFAULT = 128;  // default: 128 x 16 warps x 148 SMs x 104 B of permuted inputs stays L2-resident
 constexpr int KEY_LEVELS = 128;   // work-key table: candidate visits per lookup cell at magnitude levels KEY_M0 + (k+1)/16
 constexpr float KEY_M0 = 1.0f;
-constexpr int KEY_BINS = 128;     // sort bins (visits / 2)
+constexpr int KEY_BINS = 256;     // sort bins (= candidate visits, saturated)
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u, PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
 constexpr uint32_t PHILOX2_M = 0xD256D193u;
 constexpr uint32_t TAG_STAR = 0x53544152u, TAG_PARA = 0x50415241u;
