@@ -1033,10 +1033,17 @@ extern "C" int stmpm_run_presampled_host_ex(stmpm_t* h, int precision, int64_t n
         const long long m = std::min<long long>(chunk, n - off);
         cudaStream_t st = h->streams[b];
         const double* dcols[STMPM_NCOLS];
-        for (int c = 0; c < STMPM_NCOLS; ++c) {
-            double* dst = h->stage_cols[b] + (long long)c * h->stage_cap;
-            CK(cudaMemcpyAsync(dst, cols[c] + off, sizeof(double) * m, cudaMemcpyHostToDevice, st));
-            dcols[c] = dst;
+        bool contiguous = (off == 0 && m == n);            // one [13, n] block (what Simulation.run_sim passes): one copy
+        for (int c = 1; c < STMPM_NCOLS && contiguous; ++c) contiguous = cols[c] == cols[0] + (long long)c * n;
+        if (contiguous) {
+            CK(cudaMemcpyAsync(h->stage_cols[b], cols[0], sizeof(double) * STMPM_NCOLS * m, cudaMemcpyHostToDevice, st));
+            for (int c = 0; c < STMPM_NCOLS; ++c) dcols[c] = h->stage_cols[b] + (long long)c * m;
+        } else {
+            for (int c = 0; c < STMPM_NCOLS; ++c) {
+                double* dst = h->stage_cols[b] + (long long)c * h->stage_cap;
+                CK(cudaMemcpyAsync(dst, cols[c] + off, sizeof(double) * m, cudaMemcpyHostToDevice, st));
+                dcols[c] = dst;
+            }
         }
         if (int rc = stmpm_trials_presampled_ex(h, precision, m, seed, trial0 + off, dcols, h->stage_err[b],
                                                 h->stage_ndet[b], maxmag ? h->stage_mag[b] : nullptr,
