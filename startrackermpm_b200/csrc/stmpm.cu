@@ -873,7 +873,7 @@ static int launch_trials(stmpm_handle* h, KArgs& a, cudaStream_t st) {
     const long long cta_round = win * (TPB / 32);                    // trials one CTA covers per sweep of its warps
     const long long rounds_per_seg = (tps + cta_round - 1) / cta_round;
     long long parts = 1;
-    if (a.n_segments < 4LL * n_sm) parts = std::max(1LL, std::min(rounds_per_seg, (4LL * n_sm + a.n_segments - 1) / a.n_segments));
+    if (a.n_segments < 8LL * n_sm) parts = std::max(1LL, std::min(rounds_per_seg, (8LL * n_sm + a.n_segments - 1) / a.n_segments));   // 8 units per CTA, strided: inputs with a trend still balance
     const long long rounds_per_part = (rounds_per_seg + parts - 1) / parts;
     parts = (rounds_per_seg + rounds_per_part - 1) / rounds_per_part;
     a.parts_per_segment = (int)parts;
