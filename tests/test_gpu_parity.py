@@ -267,3 +267,27 @@ def test_toolplot_reductions_on_device(engine):
         assert got["rms"] == pytest.approx(want["rms"], rel=1e-12)
         assert got["sigma_about_mode"] == pytest.approx(want["sigma_about_mode"], rel=1e-10)
         assert np.allclose(got["density"], want["density"], rtol=1e-12, atol=0)      # identical bin counts
+
+
+@pytest.mark.timeout(120)
+def test_garbage_inputs_do_not_hang_or_fault(engine):
+    """NaN / inf / absurd magnitudes in any column: the kernel must return (no hang, no fault); such trials simply fail
+    or produce non-finite errors.  Good rows in the same launch are unaffected."""
+    n = 4096
+    good = trial.sample_params(BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF, 13, 0, n)
+    e_good, d_good = engine.run_presampled(good, 13, 0)
+    bad = good.copy()
+    vals = [np.nan, np.inf, -np.inf, 1e300, -1e300, 1e-300, 1e9, -1e9]
+    rng = np.random.default_rng(0)
+    rows = rng.choice(n, 1200, replace=False)
+    for k, r in enumerate(rows):
+        bad[k % 13, r] = vals[(k // 13) % len(vals)]
+    for prec in (64, 32):
+        e, d = engine.run_presampled(bad, 13, 0, precision=prec)
+        assert e.shape == (n,) and d.shape == (n,)
+        keep = np.ones(n, bool); keep[rows] = False
+        assert np.array_equal(d[keep], d_good[keep])
+        if prec == 64:
+            assert np.array_equal(e[keep], e_good[keep])
+    st = engine.run_rng(make_dist(dict(BASIC_MEAN, FOCAL_LENGTH=np.nan), BASIC_SIGMA, 0.0), 2048, 1)   # NaN distribution
+    assert st[0][0] + st[0][1] == 2048
