@@ -852,7 +852,10 @@ static int launch_trials(stmpm_handle* h, KArgs& a, cudaStream_t st) {
         return fail(STMPM_E_ARG, "catalog too large for shared-memory staging (" + std::to_string(smem_bytes) + " B)");
     if (a.n_bands > MAX_BANDS || a.lk_bands != LK_BANDS) return fail(STMPM_E_ARG, "sky grid has too many declination bands");
     auto kern = trials_kernel<MODE, PREC, INSTR>;
-    size_t& cached = h->smem_attr_set[MODE][PREC == 64 ? 0 : 1][INSTR];
+    // the attribute belongs to the FUNCTION (per device), not to a handle: keep a per-instantiation, per-device maximum so a
+    // second engine with a smaller catalog can never lower it under a live one
+    static size_t attr_set[64] = {};
+    size_t& cached = attr_set[h->device & 63];
     if (cached < smem_bytes) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         // leave the rest of the unified array to L1: register spills and the permuted input gathers live there

@@ -291,3 +291,17 @@ def test_garbage_inputs_do_not_hang_or_fault(engine):
             assert np.array_equal(e[keep], e_good[keep])
     st = engine.run_rng(make_dist(dict(BASIC_MEAN, FOCAL_LENGTH=np.nan), BASIC_SIGMA, 0.0), 2048, 1)   # NaN distribution
     assert st[0][0] + st[0][1] == 2048
+
+
+def test_two_engines_with_different_catalog_sizes_coexist(engine, catalog):
+    """Regression: the dynamic-shared-memory attribute is per kernel function, not per handle — a second engine with a
+    smaller catalog must not break launches of the first."""
+    from startrackermpm_b200.engine import TrialEngine
+    xyz, mag = catalog
+    cols = trial.sample_params(BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF, 3, 0, 600)
+    e0, d0 = engine.run_presampled(cols, 3, 0)
+    small = TrialEngine(0, catalog=(xyz[:3000], mag[:3000]), f_ideal=F)
+    small.run_presampled(cols, 3, 0)
+    e1, d1 = engine.run_presampled(cols, 3, 0)            # the big-catalog engine again
+    small.close()
+    assert np.array_equal(e0, e1) and np.array_equal(d0, d1)
