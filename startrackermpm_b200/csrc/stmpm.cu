@@ -543,7 +543,6 @@ struct stmpm_handle {
     uint16_t* lk_list = nullptr;
     int lk_bands = 0;
     float lk_cone = -1.0f;
-    long long lk_entries = 0;
     MathTables* tables = nullptr;
     uint8_t* lk_key = nullptr;    // work-key table [n_lk_cells][KEY_LEVELS]
     bool have_catalog = false, have_sensor = false;
@@ -563,7 +562,6 @@ struct stmpm_handle {
     double* stage_stats = nullptr;
     long long stage_stats_cap = 0;
     long long launches = 0;
-    size_t smem_attr_set[2][2][3] = {};
     unsigned long long* counters = nullptr;
 };
 
@@ -668,7 +666,6 @@ static int rebuild_lists(stmpm_handle* h) {
     CK(cudaMemcpy(h->lk_list, list.data(), sizeof(uint16_t) * list.size(), cudaMemcpyHostToDevice));
     h->lk_bands = nb;
     h->lk_cone = (float)cone;
-    h->lk_entries = (long long)list.size();
     cudaFree(h->lk_key); h->lk_key = nullptr;
     CK(cudaMalloc(&h->lk_key, key_tab.size()));
     CK(cudaMemcpy(h->lk_key, key_tab.data(), key_tab.size(), cudaMemcpyHostToDevice));

@@ -129,27 +129,11 @@ STMPM_HD unsigned long long double_to_bits(double d) {
     return b;
 #endif
 }
-STMPM_HD int clz64(unsigned long long v) {
-#if defined(__CUDA_ARCH__)
-    return __clzll((long long)v);
-#else
-    return __builtin_clzll(v);
-#endif
-}
-// 1/sqrt(x) and a/b for normal, finite operands (every use below: no zero / inf / denormal / NaN handling needed, which
+// a/b (and, in seed_rsqrt-based code below, 1/sqrt(x)) for normal, finite operands (every use below: no zero / inf / denormal / NaN handling needed, which
 // is what libm's expansions spend their branches on): MUFU seed (rel. error ~2^-22) + ONE Newton step -> ~2^-44 = 6e-14.
 // That is 5 orders of magnitude inside the parity bar for each use: the noise radius R (|dz| < 4e-13), the projection
 // scale n.p0 / n.r (centroid error < 1e-10 px) and the back-projection norm (a common scale of b, i.e. a 6e-14 relative
 // change of one star's Wahba weight).  The star loop is a single dependent chain, so every step removed is latency saved.
-STMPM_HD double fast_rsqrt(double x) {
-#if defined(__CUDA_ARCH__)
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    return y * fma(-0.5 * x * y, y, 1.5);
-#else
-    return 1.0 / sqrt(x);
-#endif
-}
 STMPM_HD double fast_div(double a, double b) {
 #if defined(__CUDA_ARCH__)
     double r;

@@ -78,7 +78,6 @@ class TrialEngine:
         _abi.check(self._lib.stmpm_set_sensor(self._h, C.byref(cfg)))
         self.f_ideal = float(f_ideal)
         self.hist_log2_sub = int(hist_log2_sub)
-        n = C.c_int64()
         self.stats_len = stats_len(hist_log2_sub)
 
     def close(self) -> None:
