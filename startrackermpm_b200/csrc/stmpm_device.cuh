@@ -431,10 +431,11 @@ template <class Tab>
 __device__ __forceinline__ bool star_f32(const Ctx64& c, const Ctx32& cf, const Tab T,
                                          const StarRec& s, uint32_t x0, uint32_t x1, double f_ideal, double half_u,
                                          double half_v, double* __restrict__ B) {
-    const float sx = (float)s.x, sy = (float)s.y, sz = (float)s.z;
-    const float dn = cf.NI[0] * sx + cf.NI[1] * sy + cf.NI[2] * sz;
-    const float du = cf.EU[0] * sx + cf.EU[1] * sy + cf.EU[2] * sz;
-    const float dv = cf.EV[0] * sx + cf.EV[1] * sy + cf.EV[2] * sz;
+    // the three plane-triad dot products in fp64: an fp32 dot product of O(1) terms carries ~6e-8 absolute error, which the
+    // projection scale (n.p0 / n.r ~ f) turns into ~2e-4 px — enough to break the 1e-6 rad bar for weak star geometries
+    const float dn = (float)(c.NI[0] * s.x + c.NI[1] * s.y + c.NI[2] * s.z);
+    const float du = (float)(c.EU[0] * s.x + c.EU[1] * s.y + c.EU[2] * s.z);
+    const float dv = (float)(c.EV[0] * s.x + c.EV[1] * s.y + c.EV[2] * s.z);
     const float lam = cf.np0 / dn;
     float z1, z2;
     box_muller_f(x0, x1, z1, z2);
