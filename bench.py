@@ -163,7 +163,9 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from startrackermpm_b200 import build, sharding
+    import ctypes
+
+    from startrackermpm_b200 import _abi, build, sharding
     from startrackermpm_b200.engine import TrialEngine, make_dist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -251,6 +253,20 @@ def run_ours(args):
                "trials_per_gpu_per_step": n_e2e, "steps": e2e_steps,
                "api": "stmpm_run_presampled_host (pinned host columns in, host records out, chunked H2D/kernel/D2H pipeline)",
                "records_match_device_run": bool(np.array_equal(he, err[:n_e2e].cpu().numpy()))}
+        # the same workload through the native-RNG host entry (MonteCarlo.create_data + run_sim fused on the device):
+        # nothing but the distribution goes up, the per-trial records come down
+        eng.run_rng(d, n_e2e, SEED, trial0, 64, out_err=he, out_ndet=hn)
+        barrier()
+        tw = time.perf_counter()
+        for _ in range(e2e_steps):
+            eng.run_rng(d, n_e2e, SEED, trial0, 64, out_err=he, out_ndet=hn)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - tw], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e["native_rng"] = {"value": world * n_e2e * e2e_steps / float(dt.item()), "unit": UNIT,
+                             "h2d_bytes_per_step": ctypes.sizeof(_abi.Dist), "d2h_bytes_per_step": BYTES_OUT_PER_TRIAL * n_e2e,
+                             "api": "stmpm_run_rng_host (parameters sampled on the device, host records + statistics out)"}
     except RuntimeError as ex:                                                   # pinned allocation refused
         e2e = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
 

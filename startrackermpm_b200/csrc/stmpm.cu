@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -72,23 +73,40 @@ static size_t smem_total(int n_stars) { return OFF_CAT + (size_t)(n_stars + 1) *
 // magnitude test alone terminates the walk: no per-entry sentinel or bounds check, and the next pack can always be
 // prefetched (the list array is padded by one pack).
 template <int INSTR>
-__device__ __forceinline__ bool scan_list(const Ctx32& c, uint32_t sb_cat, const uint16_t* __restrict__& lp, uint32_t sb_row,
-                                          int& cnt, unsigned long long* ins) {
-    uint4 pk_next = __ldg(reinterpret_cast<const uint4*>(lp));
+__device__ __forceinline__ bool scan_list(const Ctx32& c, uint32_t sb_cat, const uint16_t* __restrict__& lp, uint4 pk_next,
+                                          uint32_t sb_row, int& cnt, unsigned long long* ins) {
+    // pk_next = the pack at lp, loaded by the caller (the first one of a trial long before the scan starts)
     while (cnt <= LIST_CAP - 8) {
         const uint4 pk = pk_next;
         lp += 8;
-        pk_next = __ldg(reinterpret_cast<const uint4*>(lp));                          // prefetch the next 8 candidates
+        pk_next = __ldg(reinterpret_cast<const uint4*>(lp));                          // the next 8 candidates
         const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
-#pragma unroll
+        // The eight candidates of a pack are evaluated without an exit between them: one basic block, so ptxas can issue
+        // the eight catalog reads and the next pack's load ahead of the arithmetic (with an exit after every candidate it
+        // sinks that load below the exits, to just before its first use, where nothing hides its latency).  The list is
+        // magnitude-sorted, so once a star fails the magnitude test every later one fails it too: "the last one passed"
+        // is the continue condition, and the stars after the first failure cost a few predicated-off instructions.
+        bool m = true;
+        uint32_t pass = 0;                       // bit e: candidate e survives (pushes deferred: an intervening st.shared
+#pragma unroll                                   // would pin every later catalog read behind it — ptxas must assume aliasing)
         for (int e = 0; e < 8; ++e) {
             const uint32_t idx = (w4[e >> 1] >> (16 * (e & 1))) & 0xffffu;
             const float4 sc = lds_f4(sb_cat + idx * 16u);
-            if (INSTR == 1) ++ins[0];
-            if (!(sc.w <= c.magf)) return true;          // sorted by magnitude: every later star is fainter still
-            if (INSTR == 1) ++ins[1];
-            if (prefilter_geom(c, sc)) { sts_u16(sb_row + (uint32_t)cnt * (TPB * 2u), idx); ++cnt; if (INSTR == 1) ++ins[2]; }
+            if (INSTR == 1) ins[0] += m ? 1 : 0;
+            m = sc.w <= c.magf;
+            if (INSTR == 1) ins[1] += m ? 1 : 0;
+            const bool g = prefilter_geom(c, sc);        // evaluated regardless of m: no branch
+            pass |= (m & g) ? (1u << e) : 0u;
         }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            if (pass & (1u << e)) {
+                sts_u16(sb_row + (uint32_t)cnt * (TPB * 2u), (w4[e >> 1] >> (16 * (e & 1))) & 0xffffu);
+                ++cnt;
+                if (INSTR == 1) ++ins[2];
+            }
+        }
+        if (!m) return true;
     }
     return false;
 }
@@ -120,6 +138,81 @@ __device__ __forceinline__ int lookup_cell(const int2* __restrict__ s_lkband, in
     return bt.x + min(bt.y - 1, max(0, (int)floorf(ra0 * 0.159154943f * (float)bt.y)));
 }
 
+// ------------------------------------------------------------------------------------------------ fallback trial
+// A trial whose scan cone is wider than the candidate lists were built for (huge translations, tilts or centroid noise, tiny
+// focal lengths) is evaluated here in full: conservative fp32 walk over the sky-grid bands that overlap the cone, survivors
+// through the same exact per-star evaluation.  Never taken with the reference's configurations; out of line so that its
+// state (seven walk registers) stays out of the hot path's register budget.
+template <int PREC, int INSTR>
+__device__ __noinline__ void band_walk_trial(const Ctx64* cp, const Ctx32* cfp, const StarRec* __restrict__ cat64,
+                                             const uint16_t* __restrict__ g_cell, int n_bands, float inv_band_h, double f_ideal,
+                                             double half_u, double half_v, uint32_t sb, uint32_t ka, uint32_t kb, double* B_out,
+                                             int* n_det_out, float* mag_out, unsigned long long* ins) {
+    const Ctx64 c = *cp;
+    const Ctx32 cf = *cfp;
+    unsigned char* smem = reinterpret_cast<unsigned char*>(__cvta_shared_to_generic((size_t)sb));
+    const float4* s_cat = reinterpret_cast<const float4*>(smem + OFF_CAT);
+    const int2* s_band = reinterpret_cast<const int2*>(smem + OFF_BAND);
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(smem + OFF_LIST) + threadIdx.x;   // entry j at s_list[j * TPB]
+    const TabSmem tabs{sb + (uint32_t)OFF_TAB};
+    double B[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int n_det = 0;
+    float mag_faintest = -INFINITY;
+
+    int b = max(0, (int)floorf((cf.dec0 - cf.cone + 1.57079633f) * inv_band_h));
+    const int b_hi = min(n_bands - 1, (int)floorf((cf.dec0 + cf.cone + 1.57079633f) * inv_band_h));
+    float dalpha = -1.0f;                           // < 0: the cone touches a pole, take whole bands
+    if (fabsf(cf.dec0) + cf.cone < 1.5607963f) dalpha = asinf(fminf(sinf(cf.cone) / cosf(cf.dec0), 1.0f)) + 0.002f;
+    int i = 0, i_end = 0, pi = 0, p_end = 0;
+    bool scanning = true;
+    while (scanning) {
+        int cnt = 0;
+        while (cnt < LIST_CAP) {
+            if (i >= i_end) {
+                if (pi < p_end) { i = pi; i_end = p_end; pi = p_end = 0; continue; }
+                if (b > b_hi) { scanning = false; break; }
+                const int2 bt = s_band[b];
+                ++b;
+                const int base = bt.x, n = bt.y;
+                if (dalpha < 0.0f) { i = g_cell[base]; i_end = g_cell[base + n]; continue; }
+                const float inv_w = (float)n * 0.159154943f;
+                const int c_lo = (int)floorf((cf.ra0 - dalpha) * inv_w);
+                const int c_hi = (int)floorf((cf.ra0 + dalpha) * inv_w);
+                const int count = c_hi - c_lo + 1;
+                if (count >= n) { i = g_cell[base]; i_end = g_cell[base + n]; continue; }
+                int lo = c_lo % n;
+                if (lo < 0) lo += n;
+                if (lo + count <= n) { i = g_cell[base + lo]; i_end = g_cell[base + lo + count]; }
+                else {
+                    i = g_cell[base + lo]; i_end = g_cell[base + n];
+                    pi = g_cell[base]; p_end = g_cell[base + lo + count - n];
+                }
+                continue;
+            }
+            const float4 sc = s_cat[i];
+            if (INSTR == 1) { ++ins[0]; if (sc.w <= cf.magf) ++ins[1]; }
+            if (sc.w <= cf.magf && prefilter_geom(cf, sc)) {
+                s_list[cnt * TPB] = (uint16_t)i; ++cnt; if (INSTR == 1) ++ins[2];
+            }
+            ++i;
+        }
+        for (int j = 0; j < cnt; ++j) {
+            const StarRec s = cat64[s_list[j * TPB]];
+            uint32_t x0, x1;
+            philox2x32_10(s.star_id, kb, ka, x0, x1);
+            bool det;
+            if (PREC == 64) det = star_exact(c, tabs, s, x0, x1, f_ideal, half_u, half_v, B);
+            else det = star_f32(c, cf, tabs, s, x0, x1, f_ideal, half_u, half_v, B);
+            n_det += det ? 1 : 0;
+            if (INSTR == 2 && det) mag_faintest = fmaxf(mag_faintest, s.mag);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) B_out[k] = B[k];
+    *n_det_out = n_det;
+    *mag_out = mag_faintest;
+}
+
 // ------------------------------------------------------------------------------------------------ the trial kernel
 // MODE 0: pre-sampled columns.  MODE 1: native RNG.  PREC 64 / 32: per-star arithmetic.
 // INSTR 1: also count candidate visits / magnitude passes / pre-filter survivors (work-model calibration, not timed).
@@ -131,8 +224,6 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
     int2* s_band = reinterpret_cast<int2*>(smem + OFF_BAND);
     int2* s_lkband = reinterpret_cast<int2*>(smem + OFF_LKBAND);
     const MathTables* s_tab = reinterpret_cast<const MathTables*>(smem + OFF_TAB);
-    uint16_t* s_list = reinterpret_cast<uint16_t*>(smem + OFF_LIST) + threadIdx.x;   // entry j at s_list[j * TPB]
-    double* s_red = reinterpret_cast<double*>(smem + OFF_RED);
     // 32-bit shared-memory addresses of the hot regions, kept in registers (see lds_f4 / TabSmem)
     const uint32_t sb = smem_u32(smem);
     const uint32_t sb_cat = sb + (uint32_t)OFF_CAT;
@@ -168,7 +259,6 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
     while (!mbar_try_wait(s_bar, 0)) {}
     __syncthreads();
 
-    const uint16_t* __restrict__ g_cell = a.cell_start;   // sky-grid cell index (fallback scan only): read through L1/L2
     const float hu32 = (float)a.half_u, hv32 = (float)a.half_v;
     const int win = a.win;                                 // trials per window, multiple of 32, <= WIN_MAX
 
@@ -195,26 +285,56 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
             // ================= key pass: work key per trial, warp-local counting sort
             w_hist[lane] = 0u; w_hist[lane + 32] = 0u;
             __syncwarp();
-            for (int r = lane; r < win; r += 32) {
-                int key = KEY_BINS - 1;                               // padding slots sort last
-                if (r < nw) {
-                    double ra, dec, mm;
-                    if (MODE == 0) {
-                        ra = __ldg(a.cols[0] + rec0 + r); dec = __ldg(a.cols[1] + rec0 + r); mm = __ldg(a.cols[12] + rec0 + r);
-                    } else {
-                        const unsigned long long gi = (unsigned long long)(a.trial0 + rec0 + r);
-                        sample_key_params(*dist, s_tab, (uint32_t)gi, (uint32_t)(gi >> 32), a.k0, a.k1, ra, dec, mm);
+            if (MODE == 0) {
+                // all four slots' column loads are issued before the first use, then the four key-table loads: two exposed
+                // memory latencies per window instead of eight
+                static_assert(WIN_MAX == 128, "the batched key pass covers 4 slots per lane");
+                double kra[4], kdec[4], kmm[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int r = lane + 32 * q;
+                    kra[q] = kdec[q] = 0.0; kmm[q] = -100.0;
+                    if (r < nw) {
+                        kra[q] = __ldg(a.cols[0] + rec0 + r); kdec[q] = __ldg(a.cols[1] + rec0 + r); kmm[q] = __ldg(a.cols[12] + rec0 + r);
                     }
-                    // boresight (ra, dec) -> lookup cell (any finite input gives a valid cell; the key is only a hint)
-                    float raf = (float)ra, decf = (float)dec;
+                }
+                int kkey[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float raf = (float)kra[q], decf = (float)kdec[q];
                     raf -= 6.28318531f * floorf(raf * 0.159154943f);
                     decf = fminf(fmaxf(decf, -1.57079633f), 1.57079633f);
                     const int cell = lookup_cell(s_lkband, a.lk_bands, a.lk_inv_band_h, raf, decf);
-                    const int lev = min(KEY_LEVELS - 1, (int)floorf(((float)mm - KEY_M0) * 16.0f));
-                    key = lev < 0 ? 0 : (int)__ldg(a.lk_key + (size_t)cell * KEY_LEVELS + lev);
+                    const int lev = min(KEY_LEVELS - 1, (int)floorf(((float)kmm[q] - KEY_M0) * 16.0f));
+                    kkey[q] = lev < 0 ? 0 : (int)__ldg(a.lk_key + (size_t)cell * KEY_LEVELS + lev);
                 }
-                w_key[r] = (uint8_t)key;
-                atomicAdd(w_hist + (key >> 2), 1u << (8 * (key & 3)));
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int r = lane + 32 * q;
+                    if (r < win) {
+                        const int key = r < nw ? kkey[q] : KEY_BINS - 1;   // padding slots sort last
+                        w_key[r] = (uint8_t)key;
+                        atomicAdd(w_hist + (key >> 2), 1u << (8 * (key & 3)));
+                    }
+                }
+            } else {
+                for (int r = lane; r < win; r += 32) {
+                    int key = KEY_BINS - 1;                               // padding slots sort last
+                    if (r < nw) {
+                        double ra, dec, mm;
+                        const unsigned long long gi = (unsigned long long)(a.trial0 + rec0 + r);
+                        sample_key_params(*dist, s_tab, (uint32_t)gi, (uint32_t)(gi >> 32), a.k0, a.k1, ra, dec, mm);
+                        // boresight (ra, dec) -> lookup cell (any finite input gives a valid cell; the key is only a hint)
+                        float raf = (float)ra, decf = (float)dec;
+                        raf -= 6.28318531f * floorf(raf * 0.159154943f);
+                        decf = fminf(fmaxf(decf, -1.57079633f), 1.57079633f);
+                        const int cell = lookup_cell(s_lkband, a.lk_bands, a.lk_inv_band_h, raf, decf);
+                        const int lev = min(KEY_LEVELS - 1, (int)floorf(((float)mm - KEY_M0) * 16.0f));
+                        key = lev < 0 ? 0 : (int)__ldg(a.lk_key + (size_t)cell * KEY_LEVELS + lev);
+                    }
+                    w_key[r] = (uint8_t)key;
+                    atomicAdd(w_hist + (key >> 2), 1u << (8 * (key & 3)));
+                }
             }
             __syncwarp();
             {   // exclusive scan of the 256 byte counters: lane owns bins 8 lane .. 8 lane + 7 (two words)
@@ -272,70 +392,40 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                 } else {
                     sample_params(*dist, s_tab, t_lo, t_hi, a.k0, a.k1, p);
                 }
+                // ---- phase-A set-up, ordered so that the two dependent memory latencies in front of the candidate scan
+                // (list offset of the lookup cell, first pack of the list) are spent under the fp64 set-up instead of at the
+                // scan's first use.  For (ra, dec) in their principal ranges the boresight IS (ra, dec), so the cell comes
+                // from the raw angles (fp32 rounding moves it by < 4e-5 rad; the lists carry a > 3e-3 rad margin).
+                Ctx32 cf;
+                window_and_cone(p, hu32, hv32, cf);
+                const bool use_list = cf.cone <= a.lk_cone;
+                const float ra_f = (float)p.ra, dec_f = (float)p.dec;
+                const bool early = use_list && fabsf(dec_f) <= 1.57079633f && fabsf(ra_f) <= 256.0f;
+                uint32_t l_off = 0;
+                if (early) {
+                    const float ra_w = ra_f - 6.28318531f * floorf(ra_f * 0.159154943f);
+                    l_off = __ldg(a.lk_off + lookup_cell(s_lkband, a.lk_bands, a.lk_inv_band_h, ra_w, dec_f));
+                }
                 Ctx64 c;
                 setup64(p, c);
-                Ctx32 cf;
-                derive32(p, c, hu32, hv32, cf);
+                const uint16_t* __restrict__ lp = a.lk_list + l_off;
+                uint4 pk0 = __ldg(reinterpret_cast<const uint4*>(lp));
+                geom32(c, cf);
                 uint32_t ka, kb;
                 star_key(t_lo, t_hi, a.k0, a.k1, ka, kb);
-
-                // ---- phase-A state.  Fast path: the magnitude-sorted candidate list of the boresight's lookup cell.
-                // Fallback (scan cone wider than the lists were built for): walk the sky-grid bands.
-                const bool use_list = cf.cone <= a.lk_cone;
-                const uint16_t* __restrict__ lp = a.lk_list;
-                int b = 0, b_hi = -1, i = 0, i_end = 0, pi = 0, p_end = 0;
-                float dalpha = -1.0f;
-                if (use_list) {
-                    const int cell = lookup_cell(s_lkband, a.lk_bands, a.lk_inv_band_h, cf.ra0, cf.dec0);
-                    lp += __ldg(a.lk_off + cell);
-                } else {
-                    b = max(0, (int)floorf((cf.dec0 - cf.cone + 1.57079633f) * a.inv_band_h));
-                    b_hi = min(a.n_bands - 1, (int)floorf((cf.dec0 + cf.cone + 1.57079633f) * a.inv_band_h));
-                    if (fabsf(cf.dec0) + cf.cone < 1.5607963f)
-                        dalpha = asinf(fminf(sinf(cf.cone) / cosf(cf.dec0), 1.0f)) + 0.002f;
+                if (use_list && !early) {                       // folded / far-out angles: cell from the rotated boresight
+                    boresight32(c, cf);
+                    lp = a.lk_list + __ldg(a.lk_off + lookup_cell(s_lkband, a.lk_bands, a.lk_inv_band_h, cf.ra0, cf.dec0));
+                    pk0 = __ldg(reinterpret_cast<const uint4*>(lp));
                 }
-                bool scanning = valid;
+
+                bool scanning = valid && use_list;
                 int cnt = 0, n_det = 0;
                 float mag_faintest = -INFINITY;
                 double B[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                if (scanning && scan_list<INSTR>(cf, sb_cat, lp, pk0, sb_row, cnt, ins)) scanning = false;
 
-                do {
-                    if (scanning) {
-                        if (use_list) {
-                            if (scan_list<INSTR>(cf, sb_cat, lp, sb_row, cnt, ins)) scanning = false;
-                        } else {
-                            // sky-grid band walk (fp32, conservative): cells overlapping the scan cone
-                            while (scanning && cnt < LIST_CAP) {
-                                if (i >= i_end) {
-                                    if (pi < p_end) { i = pi; i_end = p_end; pi = p_end = 0; continue; }
-                                    if (b > b_hi) { scanning = false; break; }
-                                    const int2 bt = s_band[b];
-                                    ++b;
-                                    const int base = bt.x, n = bt.y;
-                                    if (dalpha < 0.0f) { i = g_cell[base]; i_end = g_cell[base + n]; continue; }
-                                    const float inv_w = (float)n * 0.159154943f;
-                                    const int c_lo = (int)floorf((cf.ra0 - dalpha) * inv_w);
-                                    const int c_hi = (int)floorf((cf.ra0 + dalpha) * inv_w);
-                                    const int count = c_hi - c_lo + 1;
-                                    if (count >= n) { i = g_cell[base]; i_end = g_cell[base + n]; continue; }
-                                    int lo = c_lo % n;
-                                    if (lo < 0) lo += n;
-                                    if (lo + count <= n) { i = g_cell[base + lo]; i_end = g_cell[base + lo + count]; }
-                                    else {
-                                        i = g_cell[base + lo]; i_end = g_cell[base + n];
-                                        pi = g_cell[base]; p_end = g_cell[base + lo + count - n];
-                                    }
-                                    continue;
-                                }
-                                const float4 sc = s_cat[i];
-                                if (INSTR == 1) { ++ins[0]; if (sc.w <= cf.magf) ++ins[1]; }
-                                if (sc.w <= cf.magf && prefilter_geom(cf, sc)) {
-                                    s_list[cnt * TPB] = (uint16_t)i; ++cnt; if (INSTR == 1) ++ins[2];
-                                }
-                                ++i;
-                            }
-                        }
-                    }
+                for (;;) {
                     __syncwarp();
                     // ---- phase B: exact evaluation of the listed stars (lanes in lock-step).
                     // Software-pipelined: the 32-byte record of star j+1 is in flight while star j is evaluated.
@@ -364,7 +454,29 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                         if (INSTR == 2 && det) mag_faintest = fmaxf(mag_faintest, s.mag);
                     }
                     cnt = 0;
-                } while (__any_sync(0xffffffffu, scanning));
+                    if (!__any_sync(0xffffffffu, scanning)) break;
+                    if (scanning) {                             // survivor row was full: re-derive the fp32 geometry, go on
+                        geom32(c, cf);
+                        if (scan_list<INSTR>(cf, sb_cat, lp, __ldg(reinterpret_cast<const uint4*>(lp)), sb_row, cnt, ins))
+                            scanning = false;
+                    }
+                }
+                // ---- fallback: scan cone wider than the lists were built for -> whole trial on the sky-grid band walk
+                if (valid && !use_list) {
+                    Ctx64 c2 = c;
+                    Ctx32 cf2 = cf;
+                    geom32(c, cf2);
+                    boresight32(c, cf2);
+                    double B2[9];
+                    int nd2 = 0;
+                    float mf2 = -INFINITY;
+                    band_walk_trial<PREC, INSTR>(&c2, &cf2, a.cat64, a.cell_start, a.n_bands, a.inv_band_h, a.f_ideal, a.half_u,
+                                                 a.half_v, sb, ka, kb, B2, &nd2, &mf2, INSTR == 1 ? ins : nullptr);
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) B[k] = B2[k];
+                    n_det = nd2;
+                    mag_faintest = mf2;
+                }
 
                 // ---- solve + record
                 double err = -1.0;
@@ -401,7 +513,8 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) atomicAdd(a.counters + k, ins[k]);
         }
-        // ---- unit epilogue: block reduction of the moments, one atomic per CTA per quantity
+        // ---- unit epilogue: warp reduction of the moments, six atomics per warp per unit.  No CTA barrier anywhere in the
+        // trial loop: a warp that finishes its windows early moves on to the next unit instead of waiting for the slowest.
         if (want_stats) {
             double v[5] = {(double)acc_ok, (double)acc_fail, acc_x, acc_xx, (double)acc_ndet};
 #pragma unroll
@@ -410,21 +523,14 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                 for (int k = 0; k < 5; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
                 acc_max = fmax(acc_max, __shfl_xor_sync(0xffffffffu, acc_max, off));
             }
-            __syncthreads();
-            if (lane == 0) {
-#pragma unroll
-                for (int k = 0; k < 5; ++k) s_red[warp * 8 + k] = v[k];
-                s_red[warp * 8 + 5] = acc_max;
-            }
-            __syncthreads();
             double* st = a.stats + seg * a.stats_len;
-            if (threadIdx.x < 6) {
-                double r = 0.0;
-                for (int w = 0; w < TPB / 32; ++w)
-                    r = (threadIdx.x == 5) ? fmax(r, s_red[w * 8 + 5]) : r + s_red[w * 8 + threadIdx.x];
-                if (threadIdx.x == 5)
-                    atomicMax(reinterpret_cast<unsigned long long*>(st + 5), (unsigned long long)__double_as_longlong(r));
-                else if (r != 0.0) atomicAdd(st + threadIdx.x, r);
+            if (lane < 5) {
+                double r = v[0];
+#pragma unroll
+                for (int k = 1; k < 5; ++k) r = (lane == k) ? v[k] : r;
+                if (r != 0.0) atomicAdd(st + lane, r);
+            } else if (lane == 5) {
+                atomicMax(reinterpret_cast<unsigned long long*>(st + 5), (unsigned long long)__double_as_longlong(acc_max));
             }
         }
     }
@@ -589,6 +695,10 @@ static int rebuild_lists(stmpm_handle* h) {
     const double pad = cfg.scan_pad_px > 0 ? cfg.scan_pad_px : 32.0;
     const double cone = std::atan(std::sqrt(2.0) * (std::max(cfg.half_u, cfg.half_v) + pad) / cfg.f_ideal) + 0.002;
     const int S = h->n_stars;
+    // radius of the work-key disc: 1.07 x the disc of the array's area (measured optimum, flat within +-10 %:
+    // scripts/sweep_keyradius.sh); STMPM_KEY_RADIUS_DEG overrides it for that sweep (0 = count the whole candidate list)
+    double key_radius = std::atan(1.07 * std::sqrt(4.0 * cfg.half_u * cfg.half_v / M_PI) / cfg.f_ideal);
+    if (const char* e = std::getenv("STMPM_KEY_RADIUS_DEG")) key_radius = std::atof(e) * M_PI / 180.0;
     // stars in magnitude order, SoA floats
     std::vector<int> order(S);
     for (int i = 0; i < S; ++i) order[i] = i;
@@ -631,6 +741,9 @@ static int rebuild_lists(stmpm_handle* h) {
         }
         const double reach = std::min(M_PI, cone + 1.1 * rho + 0.002);
         const float thresh = (float)std::cos(reach) - 4e-6f;
+        // work key: stars inside a disc of the field of view's area around the cell centre, i.e. the expected number of
+        // pre-filter SURVIVORS (a star evaluation costs ~6 candidate visits, so the sort equalises those)
+        const float key_thresh = key_radius > 0 ? (float)std::cos(std::min(reach, key_radius)) : thresh;
         for (int rc = 0; rc < n_ra; ++rc) {
             const double ra = (rc + 0.5) * w;
             const float cx = (float)(std::cos(dm) * std::cos(ra)), cy = (float)(std::cos(dm) * std::sin(ra)),
@@ -645,7 +758,7 @@ static int rebuild_lists(stmpm_handle* h) {
                     // stars come in magnitude order: close every level this star is fainter than
                     while (lev < KEY_LEVELS && smag[i] > KEY_M0 + (lev + 1) / 16.0f) kt[lev++] = (uint8_t)std::min(n_in, 255);
                     list.push_back((uint16_t)order[i]);
-                    ++n_in;
+                    if (dots[i] >= key_thresh) ++n_in;
                 }
                 while (lev < KEY_LEVELS) kt[lev++] = (uint8_t)std::min(n_in, 255);
             }
@@ -655,7 +768,7 @@ static int rebuild_lists(stmpm_handle* h) {
             off[bt[b].x + rc + 1] = (uint32_t)list.size();
         }
     }
-    for (int k = 0; k < 8; ++k) list.push_back((uint16_t)S);              // one pack of slack for the unconditional prefetch
+    for (int k = 0; k < 24; ++k) list.push_back((uint16_t)S);             // slack for the unconditional load / prefetch ahead
     cudaFree(h->lk_band_tab); cudaFree(h->lk_off); cudaFree(h->lk_list);
     h->lk_band_tab = nullptr; h->lk_off = nullptr; h->lk_list = nullptr;
     CK(cudaMalloc(&h->lk_band_tab, sizeof(int2) * nb));

@@ -313,8 +313,9 @@ __device__ __forceinline__ void window_and_cone(const TrialParams& p, float half
     c.cone = (depth > 1.0f) ? atanf(reach / depth) + 0.002f : 3.2f;
 }
 
-// fp32 context derived from the fp64 one (pass 2: overflow / wide-cone trials, and the fp32 precision mode)
-__device__ __forceinline__ void derive32(const TrialParams& p, const Ctx64& d, float half_u, float half_v, Ctx32& c) {
+// fp32 copies of the plane geometry (what prefilter_geom reads).  Cheap enough to redo for the rare re-scan, so the twelve
+// floats need not stay live across the fp64 star loop.
+__device__ __forceinline__ void geom32(const Ctx64& d, Ctx32& c) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         c.NI[i] = opaque((float)d.NI[i]);
@@ -324,10 +325,18 @@ __device__ __forceinline__ void derive32(const TrialParams& p, const Ctx64& d, f
     c.np0 = opaque((float)d.np0);
     c.cu = opaque((float)d.cu);
     c.cv = opaque((float)d.cv);
-    window_and_cone(p, half_u, half_v, c);
+}
+// boresight = third column of C; its (ra, dec) key the lookup grid
+__device__ __forceinline__ void boresight32(const Ctx64& d, Ctx32& c) {
     c.dec0 = asinf(fminf(fmaxf((float)d.C[8], -1.0f), 1.0f));
     const float a0 = atan2f((float)d.C[5], (float)d.C[2]);
     c.ra0 = a0 < 0.0f ? a0 + 6.28318531f : a0;
+}
+// fp32 context derived from the fp64 one
+__device__ __forceinline__ void derive32(const TrialParams& p, const Ctx64& d, float half_u, float half_v, Ctx32& c) {
+    geom32(d, c);
+    window_and_cone(p, half_u, half_v, c);
+    boresight32(d, c);
 }
 
 // fp32 context straight from the parameters (pass 1): fp32 sincosf of the fp32-rounded angles.  Angle errors ~|x| 6e-8

@@ -176,12 +176,20 @@ class TrialEngine:
         return arr, len(dists)
 
     def run_rng(self, dists, trials_per_segment: int, seed: int, trial0: int = 0, precision: int = 64,
-                records: bool = False):
-        """HOST results.  Returns stats [n_segments, stats_len] (and err, n_det [n_segments*trials_per_segment] if records)."""
+                records: bool = False, out_err=None, out_ndet=None):
+        """HOST results.  Returns stats [n_segments, stats_len] (and err, n_det [n_segments*trials_per_segment] if records).
+        out_err / out_ndet: caller-owned (e.g. pinned) record buffers; giving them implies records."""
         arr, ns = self._dist_array(dists)
         n = ns * int(trials_per_segment)
-        err = np.empty(n, dtype=np.float64) if records else None
-        ndet = np.empty(n, dtype=np.int32) if records else None
+        if (out_err is None) != (out_ndet is None):
+            raise ValueError("out_err and out_ndet go together")
+        if out_err is not None:
+            if out_err.dtype != np.float64 or out_ndet.dtype != np.int32 or out_err.size != n or out_ndet.size != n \
+                    or not out_err.flags.c_contiguous or not out_ndet.flags.c_contiguous:
+                raise ValueError(f"out_err must be contiguous float64[{n}], out_ndet contiguous int32[{n}]")
+            records = True
+        err = out_err if out_err is not None else (np.empty(n, dtype=np.float64) if records else None)
+        ndet = out_ndet if out_ndet is not None else (np.empty(n, dtype=np.int32) if records else None)
         stats = np.zeros((ns, self.stats_len), dtype=np.float64)
         _abi.check(self._lib.stmpm_run_rng_host(self._h, int(precision), ns, int(trials_per_segment),
                                                 int(seed) & (2**64 - 1), int(trial0), arr, _ptr(err), _ptr(ndet),
