@@ -17,6 +17,7 @@
 
 using namespace stmpm;
 
+
 // ------------------------------------------------------------------------------------------------ kernel arguments
 struct KArgs {
     const float4* cat32;
@@ -33,7 +34,8 @@ struct KArgs {
     float lk_inv_band_h, lk_cone; // a trial whose scan cone exceeds lk_cone takes the sky-grid scan instead
     const MathTables* tables;
     const uint8_t* lk_key;        // [n_lk_cells][KEY_LEVELS]: candidates with mag <= KEY_M0 + (k+1)/16, saturated at 255
-    int win;                      // trials per warp-local sort window (multiple of 32, <= WIN_MAX)
+    int win;                      // trials per CTA sort window (multiple of 32, <= WIN_MAX)
+    int windows_per_unit;         // ceil(part_len / win)
     double f_ideal, half_u, half_v;
     int n_min, hist_shift, n_bins;   // hist_shift = 52 - log2(sub-bins per octave)
     long long n_segments, trials_per_segment, trial0, part_len;
@@ -52,61 +54,85 @@ struct KArgs {
 
 // Shared-memory layout: every region at a COMPILE-TIME offset (fixed-size regions first, the variable-size catalog
 // last), so ptxas addresses them as [reg + immediate] instead of re-deriving bases from kernel parameters per access.
-constexpr size_t WIN_BYTES = WIN_MAX /*keys u8*/ + 2 * WIN_MAX /*perm u16*/ + KEY_BINS /*bin counters u8*/;
-static_assert(WIN_MAX <= 128 && KEY_BINS == 256, "byte-wide bin counters: counts and offsets must stay below 256");
+// CTA-wide sort window: two permutation buffers (window w uses buffer w & 1: w + 1 is built while w is consumed), the keys
+// and the 256 bin counters (16 bit, two per atomic word) of the window being built, and the scheduler words.
+constexpr size_t WIN_BYTES = 2 * 2 * (size_t)WIN_MAX /*perm u16 x2*/ + WIN_MAX /*keys u8*/ + 2 * KEY_BINS /*counters u16*/ + 32 /*sched*/;
+static_assert(WIN_MAX <= 4096 && WIN_MAX % 128 == 0 && KEY_BINS == 256, "16-bit bin counters; the key pass runs 128 trials per round");
 constexpr int LK_BANDS = 180;          // 1-degree lookup grid
 constexpr int MAX_BANDS = 256;         // sky-grid declination bands (fallback scan)
 constexpr size_t OFF_LIST = 0;
 constexpr size_t OFF_WIN = OFF_LIST + (size_t)LIST_CAP * TPB * 2;
-constexpr size_t OFF_TAB = OFF_WIN + (size_t)(TPB / 32) * WIN_BYTES;
-constexpr size_t OFF_RED = OFF_TAB + (sizeof(MathTables) + 15) / 16 * 16;
-constexpr size_t OFF_MBAR = OFF_RED + (size_t)(TPB / 32) * 8 * 8;
+constexpr size_t OFF_TAB = OFF_WIN + (WIN_BYTES + 15) / 16 * 16;
+constexpr size_t OFF_MBAR = OFF_TAB + (sizeof(MathTables) + 15) / 16 * 16;
 constexpr size_t OFF_LKBAND = OFF_MBAR + 16;
 constexpr size_t OFF_BAND = OFF_LKBAND + (size_t)LK_BANDS * 8;
 constexpr size_t OFF_CAT = (OFF_BAND + (size_t)MAX_BANDS * 8 + 127) / 128 * 128;
 static size_t smem_total(int n_stars) { return OFF_CAT + (size_t)(n_stars + 1) * 16; }   // + the +inf terminator star
 
-// Walks the magnitude-sorted candidate list of the boresight's lookup cell from position lk on, pushing pre-filter
-// survivors to row[cnt * TPB]; the first star fainter than MAX_MAGNITUDE ends the scan (returns true).  Returns false
-// while candidates remain and fewer than 8 row slots are free: the caller drains the row and calls again.
-// Every list ends with at least one entry that points at a dummy catalog star of magnitude +inf (index n_stars), so the
-// magnitude test alone terminates the walk: no per-entry sentinel or bounds check, and the next pack can always be
-// prefetched (the list array is padded by one pack).
+// One star record = one 32-byte sector = ONE load: sm_100's 256-bit LDG.  The lanes of a warp gather 32 different records,
+// and the LSU works such an instruction off one tag look-up per distinct line — two 128-bit loads per record would keep
+// it busy twice as long, and shared-memory loads queue behind it in the same pipe.
+__device__ __forceinline__ double4 ld_rec(const StarRec* p) {
+    double4 v;
+    asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    return v;
+}
+// fire-and-forget fp64 add (RED, no response): atomicAdd with an unused result compiles to ATOMG ... RZ here
+__device__ __forceinline__ void red_add_f64(double* p, double v) {
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Evaluates the eight candidates of one pack WITHOUT an exit between them: one basic block, so ptxas can issue the eight
+// catalog reads (and the caller's next-pack load) ahead of the arithmetic — with an exit after every candidate it sinks
+// that load below the exits, to just before its first use, where nothing hides its latency.  The list is magnitude-
+// sorted, so once a star fails the magnitude test every later one fails it too: "the last one passed" (the return value)
+// is the continue condition, and the stars after the first failure cost a few predicated-off instructions.
 template <int INSTR>
-__device__ __forceinline__ bool scan_list(const Ctx32& c, uint32_t sb_cat, const uint16_t* __restrict__& lp, uint4 pk_next,
-                                          uint32_t sb_row, int& cnt, unsigned long long* ins) {
-    // pk_next = the pack at lp, loaded by the caller (the first one of a trial long before the scan starts)
-    while (cnt <= LIST_CAP - 8) {
-        const uint4 pk = pk_next;
-        lp += 8;
-        pk_next = __ldg(reinterpret_cast<const uint4*>(lp));                          // the next 8 candidates
-        const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
-        // The eight candidates of a pack are evaluated without an exit between them: one basic block, so ptxas can issue
-        // the eight catalog reads and the next pack's load ahead of the arithmetic (with an exit after every candidate it
-        // sinks that load below the exits, to just before its first use, where nothing hides its latency).  The list is
-        // magnitude-sorted, so once a star fails the magnitude test every later one fails it too: "the last one passed"
-        // is the continue condition, and the stars after the first failure cost a few predicated-off instructions.
-        bool m = true;
-        uint32_t pass = 0;                       // bit e: candidate e survives (pushes deferred: an intervening st.shared
-#pragma unroll                                   // would pin every later catalog read behind it — ptxas must assume aliasing)
-        for (int e = 0; e < 8; ++e) {
-            const uint32_t idx = (w4[e >> 1] >> (16 * (e & 1))) & 0xffffu;
-            const float4 sc = lds_f4(sb_cat + idx * 16u);
-            if (INSTR == 1) ins[0] += m ? 1 : 0;
-            m = sc.w <= c.magf;
-            if (INSTR == 1) ins[1] += m ? 1 : 0;
-            const bool g = prefilter_geom(c, sc);        // evaluated regardless of m: no branch
-            pass |= (m & g) ? (1u << e) : 0u;
-        }
+__device__ __forceinline__ bool eval_pack(const Ctx32& c, uint32_t sb_cat, const uint4 pk, uint32_t sb_row, int& cnt,
+                                          unsigned long long* ins) {
+    const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
+    bool m = true;
+    uint32_t pass = 0;                       // bit e: candidate e survives (pushes deferred: an intervening st.shared
+#pragma unroll                               // would pin every later catalog read behind it — ptxas must assume aliasing)
+    for (int e = 0; e < 8; ++e) {
+        const uint32_t idx = (w4[e >> 1] >> (16 * (e & 1))) & 0xffffu;
+        const float4 sc = lds_f4(sb_cat + idx * 16u);
+        if (INSTR == 1) ins[0] += m ? 1 : 0;
+        m = sc.w <= c.magf;
+        if (INSTR == 1) ins[1] += m ? 1 : 0;
+        const bool g = prefilter_geom(c, sc);        // evaluated regardless of m: no branch
+        pass |= (m & g) ? (1u << e) : 0u;
+    }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            if (pass & (1u << e)) {
-                sts_u16(sb_row + (uint32_t)cnt * (TPB * 2u), (w4[e >> 1] >> (16 * (e & 1))) & 0xffffu);
-                ++cnt;
-                if (INSTR == 1) ++ins[2];
-            }
+    for (int e = 0; e < 8; ++e) {
+        if (pass & (1u << e)) {
+            sts_u16(sb_row + (uint32_t)cnt * (TPB * 2u), (w4[e >> 1] >> (16 * (e & 1))) & 0xffffu);
+            ++cnt;
+            if (INSTR == 1) ++ins[2];
         }
-        if (!m) return true;
+    }
+    return m;
+}
+
+struct Pack { uint4 a; };
+constexpr int PACK_N = 8;
+__device__ __forceinline__ Pack ld_pack(const uint16_t* p) { Pack v; v.a = __ldg(reinterpret_cast<const uint4*>(p)); return v; }
+
+// Walks the magnitude-sorted candidate list of the boresight's lookup cell from lp on, pushing pre-filter survivors to
+// row[cnt * TPB]; the first star fainter than MAX_MAGNITUDE ends the scan (returns true).  Returns false while candidates
+// remain and fewer than PACK_N row slots are free: the caller drains the row and calls again.  Every list ends with a
+// pack of entries that point at a dummy catalog star of magnitude +inf (index n_stars), so the magnitude test alone
+// terminates the walk: no per-entry sentinel or bounds check, and the next pack can always be loaded (slack at the end).
+// pk_next = the pack at lp, loaded by the caller (the first one of a trial long before the scan starts).
+template <int INSTR>
+__device__ __forceinline__ bool scan_list(const Ctx32& c, uint32_t sb_cat, const uint16_t* __restrict__& lp, Pack pk_next,
+                                          uint32_t sb_row, int& cnt, unsigned long long* ins) {
+    while (cnt <= LIST_CAP - PACK_N) {
+        const Pack pk = pk_next;
+        lp += PACK_N;
+        pk_next = ld_pack(lp);
+        if (!eval_pack<INSTR>(c, sb_cat, pk.a, sb_row, cnt, ins)) return true;
     }
     return false;
 }
@@ -213,6 +239,27 @@ __device__ __noinline__ void band_walk_trial(const Ctx64* cp, const Ctx32* cfp, 
     *mag_out = mag_faintest;
 }
 
+// Warp reduction of the per-thread moments into one segment's packed statistics (six atomics per warp), then reset.
+__device__ __forceinline__ void flush_moments(double* st, int lane, unsigned int& acc_ok, unsigned int& acc_fail,
+                                              unsigned long long& acc_ndet, double& acc_x, double& acc_xx, double& acc_max) {
+    double v[5] = {(double)acc_ok, (double)acc_fail, acc_x, acc_xx, (double)acc_ndet};
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+        acc_max = fmax(acc_max, __shfl_xor_sync(0xffffffffu, acc_max, off));
+    }
+    if (lane < 5) {
+        double r = v[0];
+#pragma unroll
+        for (int k = 1; k < 5; ++k) r = (lane == k) ? v[k] : r;
+        if (r != 0.0) atomicAdd(st + lane, r);
+    } else if (lane == 5) {
+        atomicMax(reinterpret_cast<unsigned long long*>(st + 5), (unsigned long long)__double_as_longlong(acc_max));
+    }
+    acc_ok = acc_fail = 0; acc_ndet = 0; acc_x = acc_xx = acc_max = 0.0;
+}
+
 // ------------------------------------------------------------------------------------------------ the trial kernel
 // MODE 0: pre-sampled columns.  MODE 1: native RNG.  PREC 64 / 32: per-star arithmetic.
 // INSTR 1: also count candidate visits / magnitude passes / pre-filter survivors (work-model calibration, not timed).
@@ -231,16 +278,19 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
     asm volatile("" : "+r"(sb_row));   // keep it: ptxas otherwise re-reads %tid.x and re-adds at every list push
     const TabSmem tabs{sb + (uint32_t)OFF_TAB};
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // this warp's sort window: keys, permutation, bin counters
-    uint8_t* w_key = smem + OFF_WIN + (size_t)warp * WIN_BYTES;
-    uint16_t* w_perm = reinterpret_cast<uint16_t*>(w_key + WIN_MAX);
-    unsigned int* w_hist = reinterpret_cast<unsigned int*>(w_perm + WIN_MAX);   // 256 byte-wide counters, 4 per word
+    // the CTA's sort window: two permutation buffers, keys + bin counters of the window being built, scheduler words
+    uint16_t* s_perm = reinterpret_cast<uint16_t*>(smem + OFF_WIN);                       // [2][WIN_MAX]
+    uint8_t* w_key = smem + OFF_WIN + 4 * (size_t)WIN_MAX;                                // [WIN_MAX]
+    unsigned int* w_hist = reinterpret_cast<unsigned int*>(w_key + WIN_MAX);              // 256 16-bit counters, 2 per word
+    int* s_sched = reinterpret_cast<int*>(w_hist + KEY_BINS / 2);                         // claim, built, reads[2]
+    volatile int* v_sched = s_sched;
 
     // ---- stage the catalog + tables into shared memory (once per CTA; the CTA is persistent).  The 146 KB fp32 catalog
     // goes through the TMA unit: one elected thread issues cp.async.bulk chunks that complete on an mbarrier while the
     // other threads load the small tables; nobody touches s_cat before the barrier phase flips.
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + OFF_MBAR);
     if (threadIdx.x == 0) mbar_init(s_bar, 1);
+    if (threadIdx.x < 8) s_sched[threadIdx.x] = 0;
     __syncthreads();
     if (threadIdx.x == 0) {
         const uint32_t total = (uint32_t)(a.n_stars + 1) * 16u;
@@ -260,61 +310,95 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
     __syncthreads();
 
     const float hu32 = (float)a.half_u, hv32 = (float)a.half_v;
+    const bool want_stats = a.stats != nullptr;
+
+    // ---- work distribution.  The CTA owns units blockIdx.x, blockIdx.x + gridDim.x, ... (unit = a contiguous range of
+    // one segment's trials); a unit is cut into windows of `win` trials.  Each window is ordered by work key ONCE for the
+    // whole CTA (counting sort by one warp, into the permutation buffer the previous-but-one window has vacated), and the
+    // 16 warps then claim its groups of 32 consecutive sorted trials from a shared counter.  The wider the window, the
+    // more alike the 32 trials a warp runs in lock-step: 2 048 instead of 128 per-warp trials is worth ~8 % of the issue
+    // slots (lanes idle in the star loop), and the permuted gathers still span only win x 104 B per SM of L2.
+    // No CTA barrier: window w + 1 is built by the warp that claims the first group of window w, while the others consume w.
     const int win = a.win;                                 // trials per window, multiple of 32, <= WIN_MAX
-
+    const int gpw = win >> 5;                              // groups per window
     const long long n_units = a.n_segments * (long long)a.parts_per_segment;
-    for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-        const long long seg = unit / a.parts_per_segment;
-        const long long part = unit - seg * a.parts_per_segment;
-        const long long t_begin = part * a.part_len;
-        const long long t_end = min(t_begin + a.part_len, a.trials_per_segment);
-        const bool want_stats = a.stats != nullptr;
-        const DistDev* dist = (MODE == 1) ? ((a.n_segments == 1) ? &a.dist0 : a.dists + seg) : nullptr;
+    const long long my_units = (n_units - (long long)blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const int n_windows = (int)(my_units * a.windows_per_unit);
+    const int n_groups = n_windows * gpw;                  // launch_trials keeps this below 2^31
 
-        // per-thread streaming accumulators (MODEL.md §9)
-        unsigned int acc_ok = 0, acc_fail = 0;
-        unsigned long long acc_ndet = 0;
-        double acc_x = 0.0, acc_xx = 0.0, acc_max = 0.0;
-        unsigned long long ins[4] = {0, 0, 0, 0};
+    // per-thread streaming accumulators (MODEL.md §9), flushed whenever the warp moves on to another segment
+    unsigned int acc_ok = 0, acc_fail = 0;
+    unsigned long long acc_ndet = 0;
+    double acc_x = 0.0, acc_xx = 0.0, acc_max = 0.0;
+    unsigned long long ins[4] = {0, 0, 0, 0};
+    long long cur_seg = -1;
 
-        // warps work independently: warp w takes windows w, w + 16, ... of this unit — no CTA barrier inside the unit
-        for (long long wb = t_begin + (long long)warp * win; wb < t_end; wb += (long long)(TPB / 32) * win) {
-            const int nw = (int)min((long long)win, t_end - wb);     // valid trials in this window
+    int build_w = (warp == 0 && n_windows > 0) ? 0 : -1;   // pending window to build (warp 0 builds the first one)
+    bool have_group = false;
+    int grp_w = 0, grp_r = 0;
+    for (;;) {
+        if (build_w >= 0) {
+            // ================= key pass + counting sort of window build_w into permutation buffer build_w & 1
+            const int bw = build_w;
+            build_w = -1;
+            uint16_t* w_perm = s_perm + (bw & 1) * WIN_MAX;
+            {   // the buffer is free once every group of window bw - 2 has copied its permutation entries out
+                const int need = gpw * (bw >> 1);
+                unsigned int spins = 0;
+                while (v_sched[2 + (bw & 1)] < need) { __nanosleep(32); if (++spins > (1u << 26)) __trap(); }
+                __threadfence_block();
+            }
+            const long long ku = bw / a.windows_per_unit;
+            const long long unit = (long long)blockIdx.x + ku * gridDim.x;
+            const long long seg = unit / a.parts_per_segment;
+            const long long part = unit - seg * a.parts_per_segment;
+            const long long t_begin = part * a.part_len;
+            const long long t_end = min(t_begin + a.part_len, a.trials_per_segment);
+            const long long wb = t_begin + (long long)(bw - ku * a.windows_per_unit) * win;
+            const int nw = (int)max(0LL, min((long long)win, t_end - wb));     // valid trials in this window
             const long long rec0 = seg * a.trials_per_segment + wb;
-
-            // ================= key pass: work key per trial, warp-local counting sort
-            w_hist[lane] = 0u; w_hist[lane + 32] = 0u;
+            const DistDev* dist = (MODE == 1) ? ((a.n_segments == 1) ? &a.dist0 : a.dists + seg) : nullptr;
+#pragma unroll
+            for (int q = 0; q < KEY_BINS / 2 / 32; ++q) w_hist[lane + 32 * q] = 0u;
             __syncwarp();
             if (MODE == 0) {
-                // all four slots' column loads are issued before the first use, then the four key-table loads: two exposed
-                // memory latencies per window instead of eight
-                static_assert(WIN_MAX == 128, "the batched key pass covers 4 slots per lane");
-                double kra[4], kdec[4], kmm[4];
+                // 128 trials per round: the four slots' column loads are issued before the first use, then the four
+                // key-table loads — two exposed memory latencies per round
+                for (int r0 = 0; r0 < win; r0 += 128) {
+                    double kra[4], kdec[4], kmm[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int r = lane + 32 * q;
-                    kra[q] = kdec[q] = 0.0; kmm[q] = -100.0;
-                    if (r < nw) {
-                        kra[q] = __ldg(a.cols[0] + rec0 + r); kdec[q] = __ldg(a.cols[1] + rec0 + r); kmm[q] = __ldg(a.cols[12] + rec0 + r);
+                    for (int q = 0; q < 4; ++q) {
+                        const int r = r0 + lane + 32 * q;
+                        kra[q] = kdec[q] = 0.0; kmm[q] = -100.0;
+                        if (r < nw) {
+                            kra[q] = __ldg(a.cols[0] + rec0 + r); kdec[q] = __ldg(a.cols[1] + rec0 + r); kmm[q] = __ldg(a.cols[12] + rec0 + r);
+                        }
                     }
-                }
-                int kkey[4];
+                    // pull the round's other ten columns into L2 (one 32-byte sector = 4 trials per lane): the groups gather
+                    // them in key order, 32 scattered sectors per load — as L2 hits those gathers hold their L1 miss slots
+                    // a quarter as long as DRAM misses do, and the LSU pipe they share with shared memory stays fluid
+                    if (r0 + 4 * lane < nw) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float raf = (float)kra[q], decf = (float)kdec[q];
-                    raf -= 6.28318531f * floorf(raf * 0.159154943f);
-                    decf = fminf(fmaxf(decf, -1.57079633f), 1.57079633f);
-                    const int cell = lookup_cell(s_lkband, a.lk_bands, a.lk_inv_band_h, raf, decf);
-                    const int lev = min(KEY_LEVELS - 1, (int)floorf(((float)kmm[q] - KEY_M0) * 16.0f));
-                    kkey[q] = lev < 0 ? 0 : (int)__ldg(a.lk_key + (size_t)cell * KEY_LEVELS + lev);
-                }
+                        for (int cI = 2; cI < 12; ++cI) prefetch_l2(a.cols[cI] + rec0 + r0 + 4 * lane);
+                    }
+                    int kkey[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int r = lane + 32 * q;
-                    if (r < win) {
-                        const int key = r < nw ? kkey[q] : KEY_BINS - 1;   // padding slots sort last
-                        w_key[r] = (uint8_t)key;
-                        atomicAdd(w_hist + (key >> 2), 1u << (8 * (key & 3)));
+                    for (int q = 0; q < 4; ++q) {
+                        float raf = (float)kra[q], decf = (float)kdec[q];
+                        raf -= 6.28318531f * floorf(raf * 0.159154943f);
+                        decf = fminf(fmaxf(decf, -1.57079633f), 1.57079633f);
+                        const int cell = lookup_cell(s_lkband, a.lk_bands, a.lk_inv_band_h, raf, decf);
+                        const int lev = min(KEY_LEVELS - 1, (int)floorf(((float)kmm[q] - KEY_M0) * 16.0f));
+                        kkey[q] = lev < 0 ? 0 : (int)__ldg(a.lk_key + (size_t)cell * KEY_LEVELS + lev);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int r = r0 + lane + 32 * q;
+                        if (r < win) {
+                            const int key = r < nw ? kkey[q] : KEY_BINS - 1;   // padding slots sort last
+                            w_key[r] = (uint8_t)key;
+                            atomicAdd(w_hist + (key >> 1), 1u << (16 * (key & 1)));
+                        }
                     }
                 }
             } else {
@@ -333,15 +417,14 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                         key = lev < 0 ? 0 : (int)__ldg(a.lk_key + (size_t)cell * KEY_LEVELS + lev);
                     }
                     w_key[r] = (uint8_t)key;
-                    atomicAdd(w_hist + (key >> 2), 1u << (8 * (key & 3)));
+                    atomicAdd(w_hist + (key >> 1), 1u << (16 * (key & 1)));
                 }
             }
             __syncwarp();
-            {   // exclusive scan of the 256 byte counters: lane owns bins 8 lane .. 8 lane + 7 (two words)
-                const uint32_t w0 = w_hist[2 * lane], w1 = w_hist[2 * lane + 1];
-                uint32_t hv[8], tot = 0;
+            {   // exclusive scan of the 256 16-bit counters: lane owns bins 8 lane .. 8 lane + 7 (four words)
+                uint32_t wv[4], hv[8], tot = 0;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { hv[q] = (w0 >> (8 * q)) & 0xffu; hv[4 + q] = (w1 >> (8 * q)) & 0xffu; }
+                for (int q = 0; q < 4; ++q) { wv[q] = w_hist[4 * lane + q]; hv[2 * q] = wv[q] & 0xffffu; hv[2 * q + 1] = wv[q] >> 16; }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) tot += hv[q];
                 uint32_t incl = tot;
@@ -350,25 +433,66 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                     const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
                     if (lane >= off) incl += o;
                 }
-                uint32_t run = incl - tot, o0 = 0, o1 = 0;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) { o0 |= (run & 0xffu) << (8 * q); run += hv[q]; }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) { o1 |= (run & 0xffu) << (8 * q); run += hv[4 + q]; }
+                uint32_t run = incl - tot;
                 __syncwarp();
-                w_hist[2 * lane] = o0; w_hist[2 * lane + 1] = o1;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t lo = run; run += hv[2 * q];
+                    const uint32_t hi = run; run += hv[2 * q + 1];
+                    w_hist[4 * lane + q] = lo | (hi << 16);
+                }
             }
             __syncwarp();
             for (int r = lane; r < win; r += 32) {
                 const int key = w_key[r];
-                const unsigned int old = atomicAdd(w_hist + (key >> 2), 1u << (8 * (key & 3)));
-                w_perm[(old >> (8 * (key & 3))) & 0xffu] = (uint16_t)r;
+                const unsigned int old = atomicAdd(w_hist + (key >> 1), 1u << (16 * (key & 1)));
+                w_perm[(old >> (16 * (key & 1))) & 0xffffu] = (uint16_t)r;
             }
+            __threadfence_block();
             __syncwarp();
+            if (lane == 0) v_sched[1] = bw + 1;            // publish: windows 0 .. bw are built
+        }
 
-            // ================= the trials of this window, 32 at a time in key order
-            for (int g0 = 0; g0 < win; g0 += 32) {
-                const int r = w_perm[g0 + lane];
+        if (!have_group) {
+            int g = 0;
+            if (lane == 0) g = atomicAdd(s_sched, 1);
+            g = __shfl_sync(0xffffffffu, g, 0);
+            if (g >= n_groups) break;
+            grp_w = g / gpw;
+            const int gi = g - grp_w * gpw;
+            {
+                unsigned int spins = 0;
+                while (v_sched[1] <= grp_w) { __nanosleep(64); if (++spins > (1u << 26)) __trap(); }
+            }
+            __threadfence_block();
+            grp_r = s_perm[(grp_w & 1) * WIN_MAX + gi * 32 + lane];
+            __threadfence_block();                        // the entry is in a register before the slot is reported free
+            __syncwarp();
+            if (lane == 0) atomicAdd(s_sched + 2 + (grp_w & 1), 1);
+            have_group = true;
+            if (gi == 0 && grp_w + 1 < n_windows) { build_w = grp_w + 1; continue; }   // build the next window first
+        }
+        have_group = false;
+
+        // ================= one group: 32 trials of window grp_w, consecutive in key order
+        {
+            const long long ku = grp_w / a.windows_per_unit;
+            const long long unit = (long long)blockIdx.x + ku * gridDim.x;
+            const long long seg = unit / a.parts_per_segment;
+            const long long part = unit - seg * a.parts_per_segment;
+            const long long t_begin = part * a.part_len;
+            const long long t_end = min(t_begin + a.part_len, a.trials_per_segment);
+            const long long wb = t_begin + (long long)(grp_w - ku * a.windows_per_unit) * win;
+            const int nw = (int)max(0LL, min((long long)win, t_end - wb));
+            const long long rec0 = seg * a.trials_per_segment + wb;
+            const DistDev* dist = (MODE == 1) ? ((a.n_segments == 1) ? &a.dist0 : a.dists + seg) : nullptr;
+            if (seg != cur_seg) {
+                if (want_stats && cur_seg >= 0)
+                    flush_moments(a.stats + cur_seg * a.stats_len, lane, acc_ok, acc_fail, acc_ndet, acc_x, acc_xx, acc_max);
+                cur_seg = seg;
+            }
+            {
+                const int r = grp_r;
                 const bool valid = r < nw;
                 if (!__any_sync(0xffffffffu, valid)) continue;
                 const long long rec = rec0 + r;
@@ -378,13 +502,16 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                 TrialParams p;
                 if (MODE == 0) {
                     if (valid) {
-                        p.ra = __ldg(a.cols[0] + rec);     p.dec = __ldg(a.cols[1] + rec);
-                        p.roll = __ldg(a.cols[2] + rec);   p.f = __ldg(a.cols[3] + rec);
-                        p.ex = __ldg(a.cols[4] + rec);     p.ey = __ldg(a.cols[5] + rec);
-                        p.ez = __ldg(a.cols[6] + rec);     p.phi = __ldg(a.cols[7] + rec);
-                        p.theta = __ldg(a.cols[8] + rec);  p.psi = __ldg(a.cols[9] + rec);
-                        p.devx = __ldg(a.cols[10] + rec);  p.devy = __ldg(a.cols[11] + rec);
-                        p.maxmag = __ldg(a.cols[12] + rec);
+                        // ld.global.cg: the 32 lanes gather from 32 different lines of the window; cached in L1 each of the 13
+                        // loads would claim 32 of its ~220 lines at once and stall the LSU pipe (shared-memory loads queue
+                        // behind it) on line allocation.  L2 holds the window (prefetched by the key pass).
+                        p.ra = __ldcg(a.cols[0] + rec);     p.dec = __ldcg(a.cols[1] + rec);
+                        p.roll = __ldcg(a.cols[2] + rec);   p.f = __ldcg(a.cols[3] + rec);
+                        p.ex = __ldcg(a.cols[4] + rec);     p.ey = __ldcg(a.cols[5] + rec);
+                        p.ez = __ldcg(a.cols[6] + rec);     p.phi = __ldcg(a.cols[7] + rec);
+                        p.theta = __ldcg(a.cols[8] + rec);  p.psi = __ldcg(a.cols[9] + rec);
+                        p.devx = __ldcg(a.cols[10] + rec);  p.devy = __ldcg(a.cols[11] + rec);
+                        p.maxmag = __ldcg(a.cols[12] + rec);
                     } else {
                         p.ra = p.dec = p.roll = 0.0; p.f = 1000.0; p.ex = p.ey = p.ez = p.phi = p.theta = p.psi = 0.0;
                         p.devx = p.devy = 0.0; p.maxmag = -100.0;
@@ -409,14 +536,14 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                 Ctx64 c;
                 setup64(p, c);
                 const uint16_t* __restrict__ lp = a.lk_list + l_off;
-                uint4 pk0 = __ldg(reinterpret_cast<const uint4*>(lp));
+                Pack pk0 = ld_pack(lp);
                 geom32(c, cf);
                 uint32_t ka, kb;
                 star_key(t_lo, t_hi, a.k0, a.k1, ka, kb);
                 if (use_list && !early) {                       // folded / far-out angles: cell from the rotated boresight
                     boresight32(c, cf);
                     lp = a.lk_list + __ldg(a.lk_off + lookup_cell(s_lkband, a.lk_bands, a.lk_inv_band_h, cf.ra0, cf.dec0));
-                    pk0 = __ldg(reinterpret_cast<const uint4*>(lp));
+                    pk0 = ld_pack(lp);
                 }
 
                 bool scanning = valid && use_list;
@@ -429,20 +556,14 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                     __syncwarp();
                     // ---- phase B: exact evaluation of the listed stars (lanes in lock-step).
                     // Software-pipelined: the 32-byte record of star j+1 is in flight while star j is evaluated.
-                    double2 r_lo = make_double2(0.0, 0.0), r_hi = make_double2(0.0, 0.0);
-                    if (cnt > 0) {
-                        const double2* g = reinterpret_cast<const double2*>(a.cat64 + lds_u16(sb_row));
-                        r_lo = __ldg(g); r_hi = __ldg(g + 1);
-                    }
+                    double4 rr = make_double4(0.0, 0.0, 0.0, 0.0);
+                    if (cnt > 0) rr = ld_rec(a.cat64 + lds_u16(sb_row));
                     for (int j = 0; j < cnt; ++j) {
                         StarRec s;
-                        s.x = r_lo.x; s.y = r_lo.y; s.z = r_hi.x;
-                        s.star_id = (uint32_t)(__double_as_longlong(r_hi.y) & 0xffffffffll);
-                        if (INSTR == 2) s.mag = __int_as_float((int)(__double_as_longlong(r_hi.y) >> 32));
-                        if (j + 1 < cnt) {
-                            const double2* g = reinterpret_cast<const double2*>(a.cat64 + lds_u16(sb_row + (uint32_t)(j + 1) * (TPB * 2u)));
-                            r_lo = __ldg(g); r_hi = __ldg(g + 1);
-                        }
+                        s.x = rr.x; s.y = rr.y; s.z = rr.z;
+                        s.star_id = (uint32_t)(__double_as_longlong(rr.w) & 0xffffffffll);
+                        if (INSTR == 2) s.mag = __int_as_float((int)(__double_as_longlong(rr.w) >> 32));
+                        if (j + 1 < cnt) rr = ld_rec(a.cat64 + lds_u16(sb_row + (uint32_t)(j + 1) * (TPB * 2u)));
                         // (hand-pipelining Philox one star ahead, or two stars per iteration, both measured slower:
                         // ptxas already overlaps the integer chain with the fp64 one, and extra live state spills)
                         uint32_t x0, x1;
@@ -457,7 +578,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                     if (!__any_sync(0xffffffffu, scanning)) break;
                     if (scanning) {                             // survivor row was full: re-derive the fp32 geometry, go on
                         geom32(c, cf);
-                        if (scan_list<INSTR>(cf, sb_cat, lp, __ldg(reinterpret_cast<const uint4*>(lp)), sb_row, cnt, ins))
+                        if (scan_list<INSTR>(cf, sb_cat, lp, ld_pack(lp), sb_row, cnt, ins))
                             scanning = false;
                     }
                 }
@@ -499,41 +620,22 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                             // the packed statistics in L2 (bins are spread over ~10^3 addresses: no hot spot)
                             double* st = a.stats + seg * a.stats_len;
                             const int slot = e < 0 ? 6 : (e >= a.n_bins ? 7 : STMPM_STATS_HEAD + (int)e);
-                            atomicAdd(st + slot, 1.0);
+                            red_add_f64(st + slot, 1.0);
                         } else {
                             ++acc_fail;
                         }
                     }
                 }
             }
-            __syncwarp();   // the window buffers are reused by this warp's next window
-        }
-
-        if (INSTR == 1) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) atomicAdd(a.counters + k, ins[k]);
-        }
-        // ---- unit epilogue: warp reduction of the moments, six atomics per warp per unit.  No CTA barrier anywhere in the
-        // trial loop: a warp that finishes its windows early moves on to the next unit instead of waiting for the slowest.
-        if (want_stats) {
-            double v[5] = {(double)acc_ok, (double)acc_fail, acc_x, acc_xx, (double)acc_ndet};
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-#pragma unroll
-                for (int k = 0; k < 5; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
-                acc_max = fmax(acc_max, __shfl_xor_sync(0xffffffffu, acc_max, off));
-            }
-            double* st = a.stats + seg * a.stats_len;
-            if (lane < 5) {
-                double r = v[0];
-#pragma unroll
-                for (int k = 1; k < 5; ++k) r = (lane == k) ? v[k] : r;
-                if (r != 0.0) atomicAdd(st + lane, r);
-            } else if (lane == 5) {
-                atomicMax(reinterpret_cast<unsigned long long*>(st + 5), (unsigned long long)__double_as_longlong(acc_max));
-            }
         }
     }
+
+    if (INSTR == 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) atomicAdd(a.counters + k, ins[k]);
+    }
+    if (want_stats && cur_seg >= 0)
+        flush_moments(a.stats + cur_seg * a.stats_len, lane, acc_ok, acc_fail, acc_ndet, acc_x, acc_xx, acc_max);
 }
 
 // ------------------------------------------------------------------------------------------------ generator kernel
@@ -763,12 +865,12 @@ static int rebuild_lists(stmpm_handle* h) {
                 while (lev < KEY_LEVELS) kt[lev++] = (uint8_t)std::min(n_in, 255);
             }
             list.push_back((uint16_t)S);                                    // terminator: the +inf dummy star
-            while ((list.size() - start) % 8) list.push_back((uint16_t)S);
+            while ((list.size() - start) % PACK_N) list.push_back((uint16_t)S);
             if (list.size() > 0xfffffff0ull) return fail(STMPM_E_ARG, "candidate lists exceed 2^32 entries: field of view too wide");
             off[bt[b].x + rc + 1] = (uint32_t)list.size();
         }
     }
-    for (int k = 0; k < 24; ++k) list.push_back((uint16_t)S);             // slack for the unconditional load / prefetch ahead
+    for (int k = 0; k < 2 * PACK_N; ++k) list.push_back((uint16_t)S);             // slack for the unconditional load / prefetch ahead
     cudaFree(h->lk_band_tab); cudaFree(h->lk_off); cudaFree(h->lk_list);
     h->lk_band_tab = nullptr; h->lk_off = nullptr; h->lk_list = nullptr;
     CK(cudaMalloc(&h->lk_band_tab, sizeof(int2) * nb));
@@ -974,26 +1076,28 @@ static int launch_trials(stmpm_handle* h, KArgs& a, cudaStream_t st) {
         cached = smem_bytes;
     }
     const int n_sm = h->prop.multiProcessorCount;
-    // work units: (segment, part).  Inside a unit each warp sorts + runs windows of `win` trials; small launches shrink
-    // the window so that all 16 warps of the CTAs in use have work.
+    // work units: (segment, part).  A unit is consumed in CTA-wide sort windows of `win` trials; small launches shrink
+    // the window so that more CTAs have work.
     const long long tps = a.trials_per_segment;
     const long long total = tps * a.n_segments;
-    long long win = WIN_DEFAULT;
+    long long win = MODE == 0 ? WIN_PRESAMPLED : WIN_RNG;
     if (const char* e = getenv("STMPM_WIN")) win = std::max(32, std::min(WIN_MAX, atoi(e) / 32 * 32));   // tuning knob
-    const long long per_warp = (total + (long long)n_sm * (TPB / 32) - 1) / ((long long)n_sm * (TPB / 32));
-    if (per_warp < win) win = std::max(32LL, (per_warp + 31) / 32 * 32);
+    const long long per_cta = (total + n_sm - 1) / n_sm;
+    if (per_cta < win) win = std::max(32LL, (per_cta + 31) / 32 * 32);
     a.win = (int)win;
-    const long long cta_round = win * (TPB / 32);                    // trials one CTA covers per sweep of its warps
-    const long long rounds_per_seg = (tps + cta_round - 1) / cta_round;
+    const long long rounds_per_seg = (tps + win - 1) / win;          // windows per segment
     long long parts = 1;
     if (a.n_segments < 8LL * n_sm) parts = std::max(1LL, std::min(rounds_per_seg, (8LL * n_sm + a.n_segments - 1) / a.n_segments));   // 8 units per CTA, strided: inputs with a trend still balance
     const long long rounds_per_part = (rounds_per_seg + parts - 1) / parts;
     parts = (rounds_per_seg + rounds_per_part - 1) / rounds_per_part;
     a.parts_per_segment = (int)parts;
-    a.part_len = rounds_per_part * cta_round;
+    a.part_len = rounds_per_part * win;
+    a.windows_per_unit = (int)rounds_per_part;
     const long long n_units = a.n_segments * parts;
     const int grid = (int)std::min<long long>(n_units, n_sm);
     if (grid <= 0) return 0;
+    if (rounds_per_part > 0x7fffffffLL || ((n_units + grid - 1) / grid) * rounds_per_part * (win / 32) > 0x7fffffffLL)
+        return fail(STMPM_E_ARG, "launch too large: more than 2^31 trial groups per CTA (split the call)");
     kern<<<grid, TPB, smem_bytes, st>>>(a);
     CK(cudaGetLastError());
     ++h->launches;

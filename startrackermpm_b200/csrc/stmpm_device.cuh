@@ -2,9 +2,10 @@
 //
 // Replaces the per-row body of Simulation.run_sim + quest_objective (called at /root/reference/monte_carlo.py:52 and
 // sensitivity.py:77; bodies absent from the mount).  One trial per thread:
-//   key pass : per warp, a window of up to 512 trials is ordered by its work key (the number of catalog candidates the
-//              trial will visit: a table look-up from boresight cell and MAX_MAGNITUDE) — warp-local counting sort,
-//              so the 32 trials a warp runs together do the same amount of work; keys never affect results
+//   key pass : per CTA, a window of up to 2048 trials is ordered by its work key (the number of stars the trial is
+//              expected to evaluate: a table look-up from boresight cell and MAX_MAGNITUDE) — counting sort by one warp
+//              while the others consume the previous window — so the 32 trials a warp runs together do the same
+//              amount of work; keys never affect results
 //   set-up (fp64) -> phase A: candidate scan with a conservative fp32 pre-filter out of shared memory
 //                 -> phase B: exact per-star projection + Philox centroid noise + detection + B accumulation
 //                 -> QUEST Newton solve in the body frame + error angle.
@@ -22,8 +23,10 @@ namespace stmpm {
 
 constexpr int TPB = 512;          // threads per CTA (1 CTA / SM: the fp32 catalog lives in shared memory)
 constexpr int LIST_CAP = 48;      // per-thread survivor list in shared memory (phase A -> phase B hand-off), drained in rounds
-constexpr int WIN_MAX = 128;      // largest warp-local sort window (trials)
-constexpr int WIN_DEFAULT = 128;  // default: 128 x 16 warps x 148 SMs x 104 B of permuted inputs stays L2-resident
+constexpr int WIN_MAX = 2048;     // largest CTA sort window (trials)
+constexpr int WIN_PRESAMPLED = 256;   // default window, pre-sampled columns: wider windows sort better but every column gather then
+                                      // touches 32 different lines, and the LSU pipe (shared with shared memory) saturates
+constexpr int WIN_RNG = 2048;         // default window, native RNG: no gathers, so the widest sort wins
 constexpr int KEY_LEVELS = 128;   // work-key table: candidate visits per lookup cell at magnitude levels KEY_M0 + (k+1)/16
 constexpr float KEY_M0 = 1.0f;
 constexpr int KEY_BINS = 256;     // sort bins (= candidate visits, saturated)
