@@ -558,9 +558,6 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                     // Software-pipelined: the 32-byte record of star j+1 is in flight while star j is evaluated.
                     double4 rr = make_double4(0.0, 0.0, 0.0, 0.0);
                     if (cnt > 0) rr = ld_rec(a.cat64 + lds_u16(sb_row));
-#ifdef STMPM_UNROLL2
-#pragma unroll 2
-#endif
                     for (int j = 0; j < cnt; ++j) {
                         StarRec s;
                         s.x = rr.x; s.y = rr.y; s.z = rr.z;
