@@ -2,8 +2,9 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC  (see build.py)
 //
 // Kernel design: persistent CTAs, one per SM, 512 threads, one trial per thread.  The fp32 copy of the
-// sky-grid-sorted catalog (16 B/star), the cell index and a log-linear error histogram live in shared memory; the
-// exact fp64 star records (one 32 B sector each) are gathered from L1/L2 only for pre-filter survivors.
+// sky-grid-sorted catalog (16 B/star), the Box-Muller tables, the per-thread survivor lists and the CTA's sort window +
+// group scheduler live in shared memory; the exact fp64 star records (one 32 B sector each) are gathered from L2 only for
+// pre-filter survivors; the error histogram is accumulated with fire-and-forget REDs in L2.
 #include "../../include/stmpm.h"
 #include "stmpm_device.cuh"
 
@@ -29,7 +30,7 @@ struct KArgs {
     // per-boresight-cell candidate lists (magnitude-sorted star indices), the fast phase-A path
     const int2* lk_band_tab;      // lookup grid: (cell_base, n_ra) per band
     const uint32_t* lk_off;       // n_lk_cells + 1 offsets into lk_list (multiples of 8 entries)
-    const uint16_t* lk_list;      // star indices into the sorted catalog, 0xFFFF padded
+    const uint16_t* lk_list;      // star indices into the sorted catalog; each list ends with index n_stars (the +inf dummy)
     int lk_bands;
     float lk_inv_band_h, lk_cone; // a trial whose scan cone exceeds lk_cone takes the sky-grid scan instead
     const MathTables* tables;
@@ -316,8 +317,8 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
     // one segment's trials); a unit is cut into windows of `win` trials.  Each window is ordered by work key ONCE for the
     // whole CTA (counting sort by one warp, into the permutation buffer the previous-but-one window has vacated), and the
     // 16 warps then claim its groups of 32 consecutive sorted trials from a shared counter.  The wider the window, the
-    // more alike the 32 trials a warp runs in lock-step: 2 048 instead of 128 per-warp trials is worth ~8 % of the issue
-    // slots (lanes idle in the star loop), and the permuted gathers still span only win x 104 B per SM of L2.
+    // more alike the 32 trials a warp runs in lock-step (2 048 instead of 128 trials: ~8 % of the issue slots, lanes idle in
+    // the star loop) — but the wider the 32 lanes' column gathers scatter (launch_trials picks the window per mode).
     // No CTA barrier: window w + 1 is built by the warp that claims the first group of window w, while the others consume w.
     const int win = a.win;                                 // trials per window, multiple of 32, <= WIN_MAX
     const int gpw = win >> 5;                              // groups per window
