@@ -7,6 +7,10 @@
 * `leo_lifetime`           — BASELINE config 4: one segment per orbit step with thermal / radiation parameter overrides
   (thermal focal update sensitivity.py:115-118; radiation -> image noise -> detection threshold README.md:12).
 
+* `result_frame` / `write_result_pickle` — the result files of driver.py:337-339 (`data/<name>.pkl`: a DataFrame of the
+  sampled parameter columns + the objective column) from a bulk GPU run, so `toolplot.py -s m/s/c` reads GPU output
+  unchanged.
+
 Nothing numerical about the trial happens here: these build `stmpm_dist` arrays and call `TrialEngine.run_rng*`.
 """
 from __future__ import annotations
@@ -194,9 +198,56 @@ def study_matrix(engine: TrialEngine, means: Mapping[str, float], sigmas: Mappin
     return out
 
 
+QUEST_OUTPUT = "QUATERNION_ERROR_[arcsec]"      # toolplot.py:71
+N_DET_OUTPUT = "N_STARS_DETECTED"
+MAG_OUTPUT = "MAXIMUM MAGNITUDE VISIBLE"            # toolplot.py:241
+
+
+def result_frame(engine, means: Mapping[str, float] | None = None, sigmas: Mapping[str, float] | None = None,
+                 thermal_coef: float = 0.0, n: int = 0, seed: int = 0, *, trial0: int = 0, precision: int = 64,
+                 keep_failed: bool = False, star_mag: bool = False, cols: np.ndarray | None = None):
+    """The DataFrame driver.py accumulates and pickles (driver.py:286-339), from one bulk run.
+
+    Columns: the 13 parameter columns under the reference's names, `QUATERNION_ERROR_[arcsec]` (toolplot.py:71),
+    `N_STARS_DETECTED`, and with star_mag=True `MAXIMUM MAGNITUDE VISIBLE` (toolplot.py:241, objective `-func M`).
+    Parameters are drawn on the device by the seeded generator (`fill_presampled_device`: exactly native-RNG mode's
+    draws) unless pre-sampled `cols` [13, n] are given.  Failed trials (fewer than n_min detections) are dropped, as
+    Simulation.run_sim drops them (the driver's row shortfall is its failure count, driver.py:321); keep_failed=True keeps
+    them with the -1 sentinel, which is what `toolplot.py -s s` turns into its star-count failure rate (toolplot.py:168-180)."""
+    import pandas as pd
+    if cols is None:
+        import torch
+        dist = make_dist(means, sigmas, thermal_coef)
+        dev = torch.empty((len(_abi.COLUMNS), int(n)), dtype=torch.float64, device=f"cuda:{engine.device}")
+        engine.fill_presampled_device(dev, dist, seed=seed, trial0=trial0)
+        torch.cuda.synchronize()
+        cols = dev.cpu().numpy()
+    cols = np.ascontiguousarray(cols, dtype=np.float64)
+    out = engine.run_presampled(cols, seed, trial0, precision, want_maxmag=star_mag)
+    err, ndet = out[0], out[1]
+    df = pd.DataFrame({name: cols[i] for i, name in enumerate(_abi.COLUMNS)})
+    df[QUEST_OUTPUT] = err
+    df[N_DET_OUTPUT] = ndet
+    if star_mag:
+        df[MAG_OUTPUT] = out[2]
+    return df if keep_failed else df[err >= 0].reset_index(drop=True)
+
+
+def write_result_pickle(df, name: str, data_dir: str = "data") -> str:
+    """driver.py:337-339: `pd.to_pickle(fin_df, <repo>/data/<name>.pkl)` — the file `toolplot.py -f data/<name>.pkl` reads."""
+    import os
+
+    import pandas as pd
+    os.makedirs(data_dir, exist_ok=True)
+    path = os.path.join(data_dir, name + ".pkl")
+    pd.to_pickle(df, path)
+    return path
+
+
 def summaries(stats: np.ndarray, hist_log2_sub: int = 8) -> list[dict]:
     return [summarize(s, hist_log2_sub) for s in np.atleast_2d(stats)]
 
 
 __all__ = ["monte_carlo_converged", "grid_axes", "sensitivity_grid_dists", "sensitivity_grid", "leo_lifetime_dists",
-           "run_segments", "summaries", "study_matrix", "STUDY_TAGS", "NORMAL_PARAMS"]
+           "run_segments", "summaries", "study_matrix", "STUDY_TAGS", "NORMAL_PARAMS", "result_frame",
+           "write_result_pickle", "QUEST_OUTPUT", "N_DET_OUTPUT", "MAG_OUTPUT"]

@@ -94,3 +94,63 @@ def test_run_sh_study_matrix_on_gpu(engine):
     assert stars["fail_rate"][0] > 0.9 and stars["fail_rate"][-1] == 0.0                        # mag 3 -> 9
     assert res["EPS_LONG"]["mc"]["mean"] < res["EPS_LAT"]["mc"]["mean"]                         # vertical shift hurts less
     assert res["PHI"]["mc"]["sigma_halfnormal"] > res["CENTROID"]["mc"]["sigma_halfnormal"]
+
+
+def test_result_frame_is_the_file_toolplot_reads(lib_built, tmp_path):
+    """the pickled frame has the reference's columns, drops failed rows like Simulation.run_sim (or
+    keeps them with the -1 sentinel for `toolplot.py -s s`), and toolplot.py:82-99 / 168-180 evaluated on the re-read
+    file reproduce the oracle's reductions.  Host logic only: oracle engine double, pre-sampled columns."""
+    from oracle import stats as ostats
+    from oracle import trial
+    from oracle_engine import OracleEngine
+    from startrackermpm_b200 import _abi, studies
+    mean = dict(BASIC_MEAN, MAX_MAGNITUDE=3.6)                             # bright limit: a visible share of trials fails
+    cols = trial.sample_params(mean, dict(BASIC_SIGMA, MAX_MAGNITUDE=0.0), THERMAL_COEF, 5, 0, 1500)
+    cols[12, 750:] = 4.0                                                    # two magnitude levels, as a STARS study has
+    eng = OracleEngine()
+    kept = studies.result_frame(eng, cols=cols, seed=5)
+    full = studies.result_frame(eng, cols=cols, seed=5, keep_failed=True, star_mag=True)
+    assert list(kept.columns) == list(_abi.COLUMNS) + [studies.QUEST_OUTPUT, studies.N_DET_OUTPUT]
+    assert studies.MAG_OUTPUT in full.columns and len(full) == 1500
+    failed = full[studies.QUEST_OUTPUT] < 0
+    assert 0 < failed.sum() < 1500 and (full.loc[failed, studies.QUEST_OUTPUT] == -1.0).all()
+    assert len(kept) == 1500 - failed.sum() and (kept[studies.QUEST_OUTPUT] >= 0).all()
+    path = studies.write_result_pickle(kept, "MC_TEST", str(tmp_path / "data"))
+    assert path.endswith("data/MC_TEST.pkl")                                # toolplot.py:72 wants exactly dir/name.pkl
+    df = pd.read_pickle(path)
+    col = studies.QUEST_OUTPUT
+    std = np.sqrt((df[col] ** 2).sum() / len(df.index))                     # toolplot.py:82-99, verbatim arithmetic
+    clip = df[df[col] <= 6 * std]
+    h = np.histogram(clip[col], bins=50, density=True)
+    newsig = np.sqrt(((clip[col] - h[1][np.argmax(h[0])]) ** 2).sum() / len(clip.index))
+    ref = ostats.toolplot_reductions(full[col].to_numpy())
+    assert std == pytest.approx(ref["rms"], rel=1e-12) and len(clip) == ref["n_kept"]
+    assert newsig == pytest.approx(ref["sigma_about_mode"], rel=1e-12)
+    data = full[["MAX_MAGNITUDE", col]].copy()                              # toolplot.py:168-180: star-count failure rate
+    data.loc[data[col] > 0, col] = 0
+    data[col] *= -1
+    rates = {m: data[data.MAX_MAGNITUDE == m][col].sum() / (data.MAX_MAGNITUDE == m).sum() for m in data.MAX_MAGNITUDE.unique()}
+    assert set(rates) == {3.6, 4.0} and rates[3.6] > rates[4.0] >= 0
+    assert rates[3.6] == pytest.approx(failed[:750].mean())
+
+
+@pytest.mark.gpu
+def test_result_frame_on_gpu(engine, tmp_path):
+    """The bulk GPU route to the same file: device-generated parameters, records through the C ABI, toolplot's reductions
+    from the frame equal the on-device ones."""
+    from startrackermpm_b200 import studies
+    from startrackermpm_b200.engine import make_dist
+    n = 200_000
+    df = studies.result_frame(engine, BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF, n, seed=9, keep_failed=True, star_mag=True)
+    _, e, d = engine.run_rng(make_dist(BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF), n, 9, 0, records=True)
+    assert np.array_equal(df[studies.QUEST_OUTPUT].to_numpy(), e) and np.array_equal(df[studies.N_DET_OUTPUT].to_numpy(), d)
+    ok = e >= 0
+    assert np.isfinite(df.loc[ok, studies.MAG_OUTPUT]).all() and (df.loc[ok, studies.MAG_OUTPUT] <= df.loc[ok, "MAX_MAGNITUDE"]).all()
+    import torch
+    tp = engine.toolplot_reduce(torch.from_numpy(e).cuda())
+    x = df.loc[ok, studies.QUEST_OUTPUT]
+    std = np.sqrt((x ** 2).sum() / len(x))
+    assert std == pytest.approx(tp["rms"], rel=1e-12) and int((x <= 6 * std).sum()) == tp["n_kept"]
+    kept = studies.result_frame(engine, BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF, n, seed=9)
+    assert len(kept) == int(ok.sum())
+    assert pd.read_pickle(studies.write_result_pickle(kept, "MC_GPU", str(tmp_path / "data"))).equals(kept)
