@@ -131,3 +131,29 @@ def test_unmodified_reference_sensitivity_sweep(dropin, monkeypatch):
     err = out["QUATERNION_ERROR_[arcsec]"].to_numpy()
     assert np.allclose(err, np.abs(psi) * 3600.0, atol=1e-6)          # pure psi -> error = |psi| exactly (MAX_MAGNITUDE = 20)
     assert (out["MAX_MAGNITUDE"] == 20).all() and "D_FOCAL_LENGTH" in out.columns      # sensitivity.py:112,118
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference checkout not present")
+def test_unmodified_toolplot_reads_the_bulk_result_file(monkeypatch, tmp_path, capsys):
+    """/root/reference/toolplot.py, unmodified, on the pickle `studies.write_result_pickle` writes.
+    It prints its statistics (toolplot.py:80-96) before it starts plotting, where the matplotlib stub stops it; the numbers
+    must be the oracle's toolplot reductions."""
+    from oracle import stats as ostats
+    from oracle import trial
+    from startrackermpm_b200 import studies
+    from conftest import BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF
+    monkeypatch.syspath_prepend(STUBS_DIR)
+    monkeypatch.syspath_prepend(REFERENCE_DIR)
+    cols = trial.sample_params(BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF, 12, 0, 3000)
+    df = studies.result_frame(OracleEngine(), cols=cols, seed=12)
+    path = studies.write_result_pickle(df, "FULL_TEST", str(tmp_path / "data"))
+    ref = ostats.toolplot_reductions(df[studies.QUEST_OUTPUT].to_numpy())
+    for mode in ("m", "s"):
+        monkeypatch.setattr(sys, "argv", ["toolplot.py", "-f", path, "-s", mode, "-p"])    # absolute -f wins os.path.join
+        with pytest.raises(RuntimeError, match="matplotlib stub"):
+            runpy.run_path(os.path.join(REFERENCE_DIR, "toolplot.py"), run_name="__main__")
+        out = capsys.readouterr().out.split()
+        assert out[:2] == ["bins:", "50"] and int(out[2]) == len(df) and int(out[3]) == ref["n_kept"]
+        if mode == "m":
+            assert out[4:7] == ["HMAX", "IDX:", str(ref["mode_bin"])]
+            assert float(out[7].split(":")[1]) == pytest.approx(ref["mode"], rel=1e-12)
