@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -1068,6 +1069,8 @@ static int launch_trials(stmpm_handle* h, KArgs& a, cudaStream_t st) {
     // the attribute belongs to the FUNCTION (per device), not to a handle: keep a per-instantiation, per-device maximum so a
     // second engine with a smaller catalog can never lower it under a live one
     static size_t attr_set[64] = {};
+    static std::mutex attr_mutex;                       // handles on different host threads may launch concurrently
+    std::lock_guard<std::mutex> attr_lock(attr_mutex);
     size_t& cached = attr_set[h->device & 63];
     if (cached < smem_bytes) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
