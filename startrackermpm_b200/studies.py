@@ -96,6 +96,32 @@ def sensitivity_grid(engine: TrialEngine, means, sigmas, thermal_coef, eps_axis,
     return run_segments(engine, dists, trials_per_point, seed, precision, segments)
 
 
+# /root/reference/constants.py:99-108 — the thermal-balance constants the reference carries (its balance code is absent)
+SOLARFLUX, EARTHFLUX, STEFBOLTZ, C1U, C3U, TEMP_GAMMA = 1367.0, 213.0, 5.670367e-8, 0.01, 0.03, 0.273
+
+
+def radiative_equilibrium(form_factor: str = "1U", sunlit: bool = True) -> float:
+    """[FREE, SURVEY.md §8f rank 4] Radiative-equilibrium temperature [K] of a CubeSat from the reference's constants:
+    absorbed = TEMP_GAMMA (= alpha / epsilon) x SOLARFLUX on one face (sunlit arcs only) + EARTHFLUX (Earth IR) on one face;
+    emitted = STEFBOLTZ T^4 over all faces.  Face areas C1U (10 cm x 10 cm) / C3U (10 cm x 30 cm)."""
+    if form_factor == "1U":
+        a_sun = a_earth = C1U
+        a_tot = 6.0 * C1U
+    elif form_factor == "3U":
+        a_sun = a_earth = C3U
+        a_tot = 2.0 * C1U + 4.0 * C3U
+    else:
+        raise ValueError("form_factor must be '1U' or '3U'")
+    q = (TEMP_GAMMA * SOLARFLUX * a_sun if sunlit else 0.0) + EARTHFLUX * a_earth
+    return float((q / (STEFBOLTZ * a_tot)) ** 0.25)
+
+
+def orbit_dtemp_amplitude(form_factor: str = "1U", damping: float = 0.65) -> float:
+    """Half the sunlit / eclipse equilibrium swing, damped by the structure's thermal inertia (fraction of the swing the
+    optics actually follow within one ~90 min orbit): the D_TEMP amplitude [K] `leo_lifetime_dists` defaults to (~15 K)."""
+    return 0.5 * damping * (radiative_equilibrium(form_factor, True) - radiative_equilibrium(form_factor, False))
+
+
 def leo_lifetime_dists(means: Mapping[str, float], sigmas: Mapping[str, float], thermal_coef: float, n_steps: int = 60,
                        years: float = 5.0, dtemp_amp: float = 15.0, dtemp_sigma: float = 5.0,
                        mag_loss_per_year: float = 0.12, dev_growth_per_year: float = 0.15):
@@ -250,4 +276,4 @@ def summaries(stats: np.ndarray, hist_log2_sub: int = 8) -> list[dict]:
 
 __all__ = ["monte_carlo_converged", "grid_axes", "sensitivity_grid_dists", "sensitivity_grid", "leo_lifetime_dists",
            "run_segments", "summaries", "study_matrix", "STUDY_TAGS", "NORMAL_PARAMS", "result_frame",
-           "write_result_pickle", "QUEST_OUTPUT", "N_DET_OUTPUT", "MAG_OUTPUT"]
+           "write_result_pickle", "QUEST_OUTPUT", "N_DET_OUTPUT", "MAG_OUTPUT", "radiative_equilibrium", "orbit_dtemp_amplitude"]

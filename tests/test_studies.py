@@ -154,3 +154,14 @@ def test_result_frame_on_gpu(engine, tmp_path):
     kept = studies.result_frame(engine, BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF, n, seed=9)
     assert len(kept) == int(ok.sum())
     assert pd.read_pickle(studies.write_result_pickle(kept, "MC_GPU", str(tmp_path / "data"))).equals(kept)
+
+
+def test_thermal_balance_from_the_reference_constants(lib_built):
+    """the schedule's D_TEMP amplitude comes from a radiative balance on constants.py:99-108."""
+    from startrackermpm_b200 import studies
+    t_sun, t_ecl = studies.radiative_equilibrium("1U", True), studies.radiative_equilibrium("1U", False)
+    assert t_sun == pytest.approx(((0.273 * 1367 + 213) * 0.01 / (5.670367e-8 * 0.06)) ** 0.25) and 150 < t_ecl < t_sun < 230
+    assert studies.radiative_equilibrium("3U", True) > t_sun                  # larger absorbing share of the total area
+    assert studies.orbit_dtemp_amplitude("1U") == pytest.approx(15.0, abs=1.0)  # the default amplitude of leo_lifetime_dists
+    with pytest.raises(ValueError):
+        studies.radiative_equilibrium("6U")
