@@ -105,3 +105,33 @@ if __name__ == "__main__":  # python -m startrackermpm_b200.catalog  -> (re)writ
     save_catalog()
     x, m = load_catalog()
     print("wrote", DEFAULT_CATALOG_PATH, x.shape, m.shape, "mag<=5.5:", int((m <= 5.5).sum()))
+
+
+def load_bsc5(path: str):
+    """Yale Bright Star Catalog, 5th ed., binary distribution (`BSC5`, /root/reference/constants.py:33 `BSC5BIN`; the file is
+    absent from the reference mount — SURVEY.md §8f rank 4: "real-catalog loader if a catalog file is ever supplied").
+
+    Format (28-byte header of seven int32: STAR0, STAR1, STARN, STNUM, MPROP, NMAG, NBENT; |STARN| entries of NBENT = 32
+    bytes: XNO f32, SRA0 f64 [rad], SDEC0 f64 [rad], IS 2 chars, MAG i16 [V x 100], XRPM f32, XDPM f32 [rad/yr]); STARN < 0
+    marks J2000 coordinates.  Either byte order is accepted.  Entries without a position (the catalog's 14 non-stellar
+    rows: RA = Dec = 0) are dropped.  Returns (xyz f64 [S, 3], mag f32 [S], hr_number i32 [S]) — pass (xyz, mag) to
+    `build_sky_grid` / `TrialEngine(catalog=...)`."""
+    raw = np.fromfile(path, dtype=np.uint8)
+    if raw.size < 28:
+        raise ValueError(f"{path}: too short for a BSC5 header")
+    for order in ("<", ">"):
+        hdr = raw[:28].view(np.dtype(order + "i4"))
+        if hdr[6] == 32 and 0 < abs(int(hdr[2])) <= (raw.size - 28) // 32:
+            break
+    else:
+        raise ValueError(f"{path}: not a BSC5 binary catalog (NBENT != 32 in either byte order)")
+    n = abs(int(hdr[2]))
+    rec = np.dtype([("xno", order + "f4"), ("ra", order + "f8"), ("dec", order + "f8"), ("sp", "S2"), ("mag", order + "i2"),
+                    ("pm_ra", order + "f4"), ("pm_dec", order + "f4")])
+    assert rec.itemsize == 32
+    ent = raw[28:28 + 32 * n].view(rec)
+    keep = ~((ent["ra"] == 0.0) & (ent["dec"] == 0.0))
+    ra, dec = ent["ra"][keep].astype(np.float64), ent["dec"][keep].astype(np.float64)
+    xyz = np.stack([np.cos(dec) * np.cos(ra), np.cos(dec) * np.sin(ra), np.sin(dec)], axis=1)
+    return (np.ascontiguousarray(xyz), (ent["mag"][keep].astype(np.float32) / np.float32(100.0)),
+            ent["xno"][keep].astype(np.int32))

@@ -165,3 +165,36 @@ def test_thermal_balance_from_the_reference_constants(lib_built):
     assert studies.orbit_dtemp_amplitude("1U") == pytest.approx(15.0, abs=1.0)  # the default amplitude of leo_lifetime_dists
     with pytest.raises(ValueError):
         studies.radiative_equilibrium("6U")
+
+
+@pytest.mark.parametrize("order", ["<", ">"])
+def test_bsc5_binary_loader_round_trip(tmp_path, order):
+    """A BSC5-format file written by the test (the real file is absent from the reference mount) is read back in either byte
+    order: unit vectors, magnitudes / 100, HR numbers; position-less entries dropped."""
+    from startrackermpm_b200 import catalog
+    rng = np.random.default_rng(4)
+    n = 50
+    rec = np.dtype([("xno", order + "f4"), ("ra", order + "f8"), ("dec", order + "f8"), ("sp", "S2"), ("mag", order + "i2"),
+                    ("pm_ra", order + "f4"), ("pm_dec", order + "f4")])
+    ent = np.zeros(n, dtype=rec)
+    ent["xno"] = np.arange(1, n + 1)
+    ent["ra"] = rng.uniform(0.01, 2 * np.pi, n)
+    ent["dec"] = rng.uniform(-1.5, 1.5, n)
+    ent["mag"] = rng.integers(-146, 796, n)
+    ent["sp"] = b"G2"
+    ent["ra"][[7, 31]] = 0.0                                                # two non-stellar rows without a position
+    ent["dec"][[7, 31]] = 0.0
+    hdr = np.array([0, 1, -n, 1, 1, 1, 32], dtype=order + "i4")
+    path = tmp_path / "BSC5"
+    path.write_bytes(hdr.tobytes() + ent.tobytes())
+    xyz, mag, hr = catalog.load_bsc5(str(path))
+    keep = np.setdiff1d(np.arange(n), [7, 31])
+    assert xyz.shape == (n - 2, 3) and np.allclose(np.linalg.norm(xyz, axis=1), 1.0, atol=1e-15)
+    assert np.array_equal(hr, keep + 1) and np.array_equal(mag, (ent["mag"][keep] / 100.0).astype(np.float32))
+    assert np.allclose(np.arctan2(xyz[:, 1], xyz[:, 0]) % (2 * np.pi), ent["ra"][keep]) and np.allclose(np.arcsin(xyz[:, 2]), ent["dec"][keep])
+    g = catalog.build_sky_grid(xyz, mag)                                    # feeds the same grid builder as the synthetic catalog
+    assert g.n_stars == n - 2 and sorted(g.star_id.tolist()) == list(range(n - 2))
+    with pytest.raises(ValueError):
+        bad = tmp_path / "bad"
+        bad.write_bytes(b"\0" * 64)
+        catalog.load_bsc5(str(bad))
