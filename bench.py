@@ -188,6 +188,8 @@ def run_ours(args):
 
     n = int(args.trials)
     eng = TrialEngine(local, f_ideal=F_IDEAL)
+    if args.window or args.key_radius_deg >= 0:
+        eng.set_tuning(args.window, args.key_radius_deg)
     d = make_dist(BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF)
     trial0 = rank * n                                      # weak scaling: every rank its own global trial-index range
     cols = torch.empty((13, n), dtype=torch.float64, device="cuda")
@@ -339,6 +341,8 @@ def main():
                     help="oracle-port trials per host process: default 131072 for the cpu_baseline leg (~13 s), 32768 per step "
                          "for --impl reference (~3 s per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--window", type=int, default=0, help="tuning sweep: CTA sort window in trials (0 = default)")
+    ap.add_argument("--key-radius-deg", type=float, default=-1.0, help="tuning sweep: work-key disc radius (<0 = default)")
     args = ap.parse_args()
     if args.cpu_trials_per_core is None:
         args.cpu_trials_per_core = 32768 if args.impl == "reference" else 131072

@@ -83,13 +83,20 @@ int stmpm_destroy(stmpm_t* h);
 /* sm_count, max dynamic shared memory per block, SM clock kHz, memory clock kHz */
 int stmpm_device_info(stmpm_t* h, int32_t* sm_count, int64_t* smem_per_block, int32_t* sm_khz, int32_t* mem_khz);
 
-/* Catalog sorted by sky-grid cell (host pointers; uploaded once).  xyz is S x 3 row-major float64 unit vectors,
+/* Catalog sorted by sky-grid cell (host pointers; uploaded once).  n_stars is bounded by the shared-memory staging of the
+ * fp32 catalog: (227 KB - fixed regions) / 16 B = about 9 250 stars on B200 (checked here, with the exact limit in the
+ * error message); n_bands <= 256.  xyz is S x 3 row-major float64 unit vectors,
  * star_id the Philox key of each row (MODEL.md §5).  Band b (n_bands equal declination bands from -pi/2) has n_ra[b]
  * equal RA cells; cell_start has sum(n_ra)+1 entries.  Replaces the BSC5 catalog the reference loads from
  * utils/BSC5PKL.pkl (constants.py:32-33). */
 int stmpm_set_catalog(stmpm_t* h, const double* xyz_host, const float* mag_host, const int32_t* star_id_host,
                       int32_t n_stars, int32_t n_bands, const int32_t* n_ra_host, const int32_t* cell_start_host);
 int stmpm_set_sensor(stmpm_t* h, const stmpm_sensor_cfg* cfg);
+/* Performance knobs of the trial kernel; results never depend on them (tests/test_gpu_parity.py checks bit-identity).
+ * window: trials per CTA sort window (multiple of 32, <= 2048; 0 = the measured default per mode).  key_radius_deg: radius
+ * of the work-key disc (< 0 = default, 0 = whole candidate list); changing it synchronises the device and rebuilds the
+ * key table.  Not to be called while launches on this handle are in flight. */
+int stmpm_set_tuning(stmpm_t* h, int32_t window, double key_radius_deg);
 
 /* Packed statistics buffer (MODEL.md §9): STMPM_STATS_HEAD doubles then 34 * 2^hist_log2_sub histogram bins; every entry
  * but x_max is a sum, so ranks merge with one allreduce(sum).  Host-only helpers (no GPU needed). */
@@ -114,7 +121,9 @@ int stmpm_trials_presampled_ex(stmpm_t* h, int precision, int64_t n, uint64_t se
  * on the device from Philox streams keyed by (seed, global trial index).  n_segments independent parameter sets (a
  * sensitivity grid point / an orbit step: sensitivity.py:39-55) of trials_per_segment trials each; segment s uses
  * dists_host[s], global trial indices trial0 + s*trials_per_segment + i, and accumulates into
- * stats_dev[s*stats_len ...].  Records (optional, may be NULL) are n_segments*trials_per_segment long. */
+ * stats_dev[s*stats_len ...].  Records (optional, may be NULL) are n_segments*trials_per_segment long.
+ * dists_host is consumed before the call returns; the device copy is allocated and freed in stream order per call
+ * (cudaMallocAsync), so calls on different streams of one handle may overlap. */
 int stmpm_trials_rng(stmpm_t* h, int precision, int64_t n_segments, int64_t trials_per_segment, uint64_t seed,
                      int64_t trial0, const stmpm_dist* dists_host, double* err_arcsec_dev, int32_t* n_det_dev,
                      double* stats_dev, void* stream);

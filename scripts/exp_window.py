@@ -23,7 +23,7 @@ def timeit(fn):
     e1.record(); torch.cuda.synchronize()
     return 3 * N / (e0.elapsed_time(e1) * 1e-3)
 for w in [int(x) for x in sys.argv[1:]] or [128, 512, 2048]:
-    os.environ["STMPM_WIN"] = str(w)
+    eng.set_tuning(window=w)
     a = timeit(lambda: eng.run_presampled_device(cols, err, nd, stats, seed=SEED, stream=s))
     b = timeit(lambda: eng.run_presampled_device(cols, None, None, stats, seed=SEED, stream=s))
     c = timeit(lambda: eng.run_rng_device(d, N, stats, err, nd, seed=SEED, stream=s))

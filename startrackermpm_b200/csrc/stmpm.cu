@@ -69,7 +69,10 @@ constexpr size_t OFF_MBAR = OFF_TAB + (sizeof(MathTables) + 15) / 16 * 16;
 constexpr size_t OFF_LKBAND = OFF_MBAR + 16;
 constexpr size_t OFF_BAND = OFF_LKBAND + (size_t)LK_BANDS * 8;
 constexpr size_t OFF_CAT = (OFF_BAND + (size_t)MAX_BANDS * 8 + 127) / 128 * 128;
-static size_t smem_total(int n_stars) { return OFF_CAT + (size_t)(n_stars + 1) * 16; }   // + the +inf terminator star
+constexpr size_t CAT_ENTRY_BYTES = 16;
+static size_t smem_total(int n_stars) { return OFF_CAT + (size_t)(n_stars + 1) * CAT_ENTRY_BYTES; }   // + the +inf terminator star
+// the real catalog (BSC5: 9 110 stars, 9 096 after load_bsc5 drops the non-stellar entries) must fit the 227 KB a CTA can opt in to
+static_assert(OFF_CAT + (9110 + 1) * CAT_ENTRY_BYTES <= 227 * 1024, "a 9110-star catalog no longer fits in shared memory");
 
 // One star record = one 32-byte sector = ONE load: sm_100's 256-bit LDG.  The lanes of a warp gather 32 different records,
 // and the LSU works such an instruction off one tag look-up per distinct line — two 128-bit loads per record would keep
@@ -737,6 +740,19 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
             return fail((int)e_, std::string(#call) + ": " + cudaGetErrorString(e_));                  \
     } while (0)
 
+// Every entry point runs on the handle's device and puts the caller's current device back on the way out (the library
+// shares the CUDA runtime with torch: silently changing the current device would redirect the caller's next allocation).
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) cudaSetDevice(device); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 struct stmpm_handle {
     int device = 0;
     cudaDeviceProp prop{};
@@ -758,9 +774,6 @@ struct stmpm_handle {
     bool have_catalog = false, have_sensor = false;
     stmpm_sensor_cfg cfg{};
     int n_bins = 0;
-    // rng dists
-    DistDev* dists = nullptr;
-    long long dists_cap = 0;
     // host pipeline
     static constexpr int NBUF = 3;
     cudaStream_t streams[NBUF] = {nullptr, nullptr, nullptr};
@@ -773,6 +786,9 @@ struct stmpm_handle {
     long long stage_stats_cap = 0;
     long long launches = 0;
     unsigned long long* counters = nullptr;
+    // tuning (stmpm_set_tuning): 0 / negative = the measured defaults
+    int tune_window = 0;
+    double tune_key_radius_deg = -1.0;
 };
 
 // Tables of box_muller_tab (stmpm_device.cuh), computed with the host libm.
@@ -800,9 +816,9 @@ static int rebuild_lists(stmpm_handle* h) {
     const double cone = std::atan(std::sqrt(2.0) * (std::max(cfg.half_u, cfg.half_v) + pad) / cfg.f_ideal) + 0.002;
     const int S = h->n_stars;
     // radius of the work-key disc: 1.07 x the disc of the array's area (measured optimum, flat within +-10 %:
-    // scripts/sweep_keyradius.sh); STMPM_KEY_RADIUS_DEG overrides it for that sweep (0 = count the whole candidate list)
+    // scripts/sweep_keyradius.sh); stmpm_set_tuning overrides it for that sweep (0 = count the whole candidate list)
     double key_radius = std::atan(1.07 * std::sqrt(4.0 * cfg.half_u * cfg.half_v / M_PI) / cfg.f_ideal);
-    if (const char* e = std::getenv("STMPM_KEY_RADIUS_DEG")) key_radius = std::atof(e) * M_PI / 180.0;
+    if (h->tune_key_radius_deg >= 0.0) key_radius = h->tune_key_radius_deg * M_PI / 180.0;
     // stars in magnitude order, SoA floats
     std::vector<int> order(S);
     for (int i = 0; i < S; ++i) order[i] = i;
@@ -900,15 +916,19 @@ extern "C" int stmpm_create(stmpm_t** out, int device) {
         return fail(STMPM_E_NOGPU, std::string("stmpm_create: no CUDA device (") + cudaGetErrorString(e) +
                                        "); this library has no CPU fallback");
     if (device < 0 || device >= n) return fail(STMPM_E_ARG, "stmpm_create: bad device index");
-    CK(cudaSetDevice(device));
+    DeviceGuard guard(device);
     stmpm_handle* h = new stmpm_handle();
     h->device = device;
-    CK(cudaGetDeviceProperties(&h->prop, device));
-    for (int i = 0; i < stmpm_handle::NBUF; ++i) CK(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
-    MathTables mt;
-    stmpm_host_tables(&mt);
-    CK(cudaMalloc(&h->tables, sizeof(MathTables)));
-    CK(cudaMemcpy(h->tables, &mt, sizeof(MathTables), cudaMemcpyHostToDevice));
+    const int rc = [&]() -> int {
+        CK(cudaGetDeviceProperties(&h->prop, device));
+        for (int i = 0; i < stmpm_handle::NBUF; ++i) CK(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
+        MathTables mt;
+        stmpm_host_tables(&mt);
+        CK(cudaMalloc(&h->tables, sizeof(MathTables)));
+        CK(cudaMemcpy(h->tables, &mt, sizeof(MathTables), cudaMemcpyHostToDevice));
+        return 0;
+    }();
+    if (rc) { stmpm_destroy(h); return rc; }          // nothing leaks on a failed create
     *out = h;
     return 0;
 }
@@ -923,8 +943,8 @@ static void free_stage(stmpm_handle* h) {
 
 extern "C" int stmpm_destroy(stmpm_t* h) {
     if (!h) return 0;
-    cudaSetDevice(h->device);
-    cudaFree(h->cat32); cudaFree(h->cat64); cudaFree(h->cell_start); cudaFree(h->band_tab); cudaFree(h->dists);
+    DeviceGuard guard(h->device);
+    cudaFree(h->cat32); cudaFree(h->cat64); cudaFree(h->cell_start); cudaFree(h->band_tab);
     cudaFree(h->stage_stats); cudaFree(h->counters);
     cudaFree(h->lk_band_tab); cudaFree(h->lk_off); cudaFree(h->lk_list); cudaFree(h->tables);
     cudaFree(h->lk_key);
@@ -950,8 +970,14 @@ extern "C" int stmpm_set_catalog(stmpm_t* h, const double* xyz, const float* mag
     if (!h || !xyz || !mag || !star_id || !n_ra || !cell_start) return fail(STMPM_E_ARG, "stmpm_set_catalog: null");
     if (n_stars <= 0 || n_stars > 65534)
         return fail(STMPM_E_ARG, "stmpm_set_catalog: n_stars must be in [1, 65534] (16-bit candidate indices + one terminator)");
-    if (n_bands <= 0 || n_bands > 4096) return fail(STMPM_E_ARG, "stmpm_set_catalog: bad n_bands");
-    CK(cudaSetDevice(h->device));
+    if (n_bands <= 0 || n_bands > MAX_BANDS) return fail(STMPM_E_ARG, "stmpm_set_catalog: n_bands must be in [1, 256]");
+    // the whole fp32 catalog is staged into shared memory by every CTA: refuse here, with the true limit, not at the first launch
+    if (smem_total(n_stars) > (size_t)h->prop.sharedMemPerBlockOptin) {
+        const long long cap = ((long long)h->prop.sharedMemPerBlockOptin - (long long)OFF_CAT) / (long long)CAT_ENTRY_BYTES - 1;
+        return fail(STMPM_E_ARG, "stmpm_set_catalog: " + std::to_string(n_stars) + " stars do not fit the shared-memory catalog (limit " +
+                                     std::to_string(cap) + " stars on this device)");
+    }
+    DeviceGuard guard(h->device);
     long long n_cells = 0;
     std::vector<int2> bt(n_bands);
     for (int b = 0; b < n_bands; ++b) {
@@ -1004,6 +1030,18 @@ extern "C" int stmpm_set_sensor(stmpm_t* h, const stmpm_sensor_cfg* cfg) {
     h->cfg = *cfg;
     h->n_bins = STMPM_HIST_OCTAVES << cfg->hist_log2_sub;
     h->have_sensor = true;
+    return rebuild_lists(h);
+}
+
+extern "C" int stmpm_set_tuning(stmpm_t* h, int32_t window, double key_radius_deg) {
+    if (!h) return fail(STMPM_E_ARG, "stmpm_set_tuning: null handle");
+    if (window < 0 || window > WIN_MAX || window % 32) return fail(STMPM_E_ARG, "stmpm_set_tuning: window must be 0 (default) or a multiple of 32 up to 2048");
+    const bool rebuild = key_radius_deg != h->tune_key_radius_deg;
+    h->tune_window = window;
+    h->tune_key_radius_deg = key_radius_deg;
+    if (!rebuild) return 0;
+    DeviceGuard guard(h->device);
+    CK(cudaDeviceSynchronize());                       // the work-key table is about to be replaced
     return rebuild_lists(h);
 }
 
@@ -1085,7 +1123,7 @@ static int launch_trials(stmpm_handle* h, KArgs& a, cudaStream_t st) {
     const long long tps = a.trials_per_segment;
     const long long total = tps * a.n_segments;
     long long win = MODE == 0 ? WIN_PRESAMPLED : WIN_RNG;
-    if (const char* e = getenv("STMPM_WIN")) win = std::max(32, std::min(WIN_MAX, atoi(e) / 32 * 32));   // tuning knob
+    if (h->tune_window > 0) win = std::max(32, std::min(WIN_MAX, h->tune_window / 32 * 32));   // stmpm_set_tuning
     const long long per_cta = (total + n_sm - 1) / n_sm;
     if (per_cta < win) win = std::max(32LL, (per_cta + 31) / 32 * 32);
     a.win = (int)win;
@@ -1139,7 +1177,7 @@ extern "C" int stmpm_trials_presampled_ex(stmpm_t* h, int precision, int64_t n, 
     if (int rc = fill_common(h, a, precision)) return rc;
     if (n < 0 || !cols) return fail(STMPM_E_ARG, "stmpm_trials_presampled: bad n / cols");
     if (n == 0) return 0;
-    CK(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
     for (int i = 0; i < STMPM_NCOLS; ++i) {
         if (!cols[i]) return fail(STMPM_E_ARG, "stmpm_trials_presampled: null column pointer");
         a.cols[i] = cols[i];
@@ -1165,32 +1203,34 @@ extern "C" int stmpm_trials_rng(stmpm_t* h, int precision, int64_t n_segments, i
     if (int rc = fill_common(h, a, precision)) return rc;
     if (n_segments < 0 || tps < 0 || !dists) return fail(STMPM_E_ARG, "stmpm_trials_rng: bad arguments");
     if (n_segments == 0 || tps == 0) return 0;
-    CK(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
     static_assert(sizeof(DistDev) == sizeof(stmpm_dist), "dist layout");
+    DistDev* d_dists = nullptr;
     if (n_segments == 1) {
         to_dev_dist(dists[0], a.dist0);
-    } else {   // NOTE: multi-segment calls on one handle share this buffer: do not issue them concurrently
-        if (h->dists_cap < n_segments) {
-            CK(cudaStreamSynchronize((cudaStream_t)stream));
-            cudaFree(h->dists); h->dists = nullptr; h->dists_cap = 0;
-            CK(cudaMalloc(&h->dists, sizeof(DistDev) * n_segments));
-            h->dists_cap = n_segments;
-        }
-        CK(cudaMemcpyAsync(h->dists, dists, sizeof(DistDev) * n_segments, cudaMemcpyHostToDevice, (cudaStream_t)stream));
-        a.dists = h->dists;
+    } else {
+        // every call owns its distribution array: allocated, filled and freed in stream order on the caller's stream, so
+        // concurrent multi-segment calls on different streams never share storage (the host array is pageable memory:
+        // cudaMemcpyAsync has staged it before it returns, the caller may reuse it at once)
+        CK(cudaMallocAsync(&d_dists, sizeof(DistDev) * n_segments, (cudaStream_t)stream));
+        cudaError_t e = cudaMemcpyAsync(d_dists, dists, sizeof(DistDev) * n_segments, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+        if (e != cudaSuccess) { cudaFreeAsync(d_dists, (cudaStream_t)stream); return fail((int)e, std::string("dists upload: ") + cudaGetErrorString(e)); }
+        a.dists = d_dists;
     }
     a.n_segments = n_segments; a.trials_per_segment = tps; a.trial0 = trial0;
     a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
     a.err = err; a.ndet = ndet; a.stats = stats;
-    return precision == 64 ? launch_trials<1, 64>(h, a, (cudaStream_t)stream)
-                           : launch_trials<1, 32>(h, a, (cudaStream_t)stream);
+    const int rc = precision == 64 ? launch_trials<1, 64>(h, a, (cudaStream_t)stream)
+                                   : launch_trials<1, 32>(h, a, (cudaStream_t)stream);
+    if (d_dists) cudaFreeAsync(d_dists, (cudaStream_t)stream);
+    return rc;
 }
 
 extern "C" int stmpm_fill_presampled(stmpm_t* h, int64_t n, uint64_t seed, int64_t trial0, const stmpm_dist* dist,
                                      double* const* cols, void* stream) {
     if (!h || !dist || !cols || n < 0) return fail(STMPM_E_ARG, "stmpm_fill_presampled: bad arguments");
     if (n == 0) return 0;
-    CK(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
     for (int i = 0; i < STMPM_NCOLS; ++i) if (!cols[i]) return fail(STMPM_E_ARG, "stmpm_fill_presampled: null column");
     DistDev d;
     to_dev_dist(*dist, d);
@@ -1239,7 +1279,7 @@ extern "C" int stmpm_run_presampled_host_ex(stmpm_t* h, int precision, int64_t n
     if (n < 0 || !cols || !err || !ndet) return fail(STMPM_E_ARG, "stmpm_run_presampled_host: bad arguments");
     for (int i = 0; i < STMPM_NCOLS; ++i) if (!cols[i]) return fail(STMPM_E_ARG, "null column pointer");
     if (n == 0) return 0;
-    CK(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
     const long long chunk = std::min<long long>(HOST_CHUNK, n);
     if (int rc = ensure_stage(h, chunk, true)) return rc;
     const long long slen = probe.stats_len;
@@ -1285,7 +1325,7 @@ extern "C" int stmpm_run_rng_host(stmpm_t* h, int precision, int64_t n_segments,
     if (n_segments < 0 || tps < 0 || !dists) return fail(STMPM_E_ARG, "stmpm_run_rng_host: bad arguments");
     if ((err == nullptr) != (ndet == nullptr)) return fail(STMPM_E_ARG, "err and n_det must both be given or both NULL");
     if (n_segments == 0 || tps == 0) return 0;
-    CK(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
     const long long slen = probe.stats_len;
     cudaStream_t s0 = h->streams[0];
     if (stats) {
@@ -1322,26 +1362,32 @@ extern "C" int stmpm_run_rng_host(stmpm_t* h, int precision, int64_t n_segments,
 extern "C" int stmpm_fma_peak(stmpm_t* h, int precision, double* tflops) {
     if (!h || !tflops) return fail(STMPM_E_ARG, "stmpm_fma_peak: null");
     if (precision != 64 && precision != 32) return fail(STMPM_E_ARG, "precision must be 64 or 32");
-    CK(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
     void* out = nullptr;
-    CK(cudaMalloc(&out, 64));
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    const int grid = h->prop.multiProcessorCount * 8, iters = precision == 64 ? 1 << 15 : 1 << 16;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
     double best = 0.0;
-    for (int rep = 0; rep < 4; ++rep) {
-        CK(cudaEventRecord(e0, h->streams[0]));
-        if (precision == 64) fma_peak_kernel<double><<<grid, 256, 0, h->streams[0]>>>((double*)out, iters, 1.0000001, 1e-9);
-        else fma_peak_kernel<float><<<grid, 256, 0, h->streams[0]>>>((float*)out, iters, 1.0001f, 1e-6f);
-        CK(cudaEventRecord(e1, h->streams[0]));
-        CK(cudaEventSynchronize(e1));
-        ++h->launches;
-        float ms = 0;
-        CK(cudaEventElapsedTime(&ms, e0, e1));
-        const double flops = 2.0 * 8.0 * (double)iters * 256.0 * (double)grid;
-        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
-    }
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    const int rc = [&]() -> int {
+        CK(cudaMalloc(&out, 64));
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        const int grid = h->prop.multiProcessorCount * 8, iters = precision == 64 ? 1 << 15 : 1 << 16;
+        for (int rep = 0; rep < 4; ++rep) {
+            CK(cudaEventRecord(e0, h->streams[0]));
+            if (precision == 64) fma_peak_kernel<double><<<grid, 256, 0, h->streams[0]>>>((double*)out, iters, 1.0000001, 1e-9);
+            else fma_peak_kernel<float><<<grid, 256, 0, h->streams[0]>>>((float*)out, iters, 1.0001f, 1e-6f);
+            CK(cudaEventRecord(e1, h->streams[0]));
+            CK(cudaEventSynchronize(e1));
+            ++h->launches;
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            const double flops = 2.0 * 8.0 * (double)iters * 256.0 * (double)grid;
+            if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        }
+        return 0;
+    }();
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(out);
+    if (rc) return rc;
     *tflops = best;
     return 0;
 }
@@ -1351,7 +1397,7 @@ extern "C" int stmpm_work_counters(stmpm_t* h, int64_t n, uint64_t seed, int64_t
     KArgs a;
     if (int rc = fill_common(h, a, 64)) return rc;
     if (n <= 0 || !dist || !per_trial4) return fail(STMPM_E_ARG, "stmpm_work_counters: bad arguments");
-    CK(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
     if (!h->counters) CK(cudaMalloc(&h->counters, 4 * sizeof(unsigned long long)));
     CK(cudaMemsetAsync(h->counters, 0, 4 * sizeof(unsigned long long), h->streams[0]));
     to_dev_dist(*dist, a.dist0);
@@ -1378,10 +1424,11 @@ extern "C" int stmpm_toolplot_reduce(stmpm_t* h, const double* err_dev, int64_t 
                                      double* density_host, void* stream) {
     if (!h || !err_dev || !out || n <= 0 || bins < 1 || bins > 4096)
         return fail(STMPM_E_ARG, "stmpm_toolplot_reduce: bad arguments");
-    CK(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
-    double* acc = nullptr;
-    CK(cudaMalloc(&acc, sizeof(double) * 8 + sizeof(unsigned long long) * bins));
+    struct DevBuf { void* p = nullptr; ~DevBuf() { cudaFree(p); } } acc_buf;       // freed on every exit path
+    CK(cudaMalloc(&acc_buf.p, sizeof(double) * 8 + sizeof(unsigned long long) * bins));
+    double* acc = static_cast<double*>(acc_buf.p);
     unsigned long long* hist = reinterpret_cast<unsigned long long*>(acc + 8);
     CK(cudaMemsetAsync(acc, 0, sizeof(double) * 8 + sizeof(unsigned long long) * bins, st));
     const unsigned long long inf_bits = 0x7FF0000000000000ull;
@@ -1397,7 +1444,6 @@ extern "C" int stmpm_toolplot_reduce(stmpm_t* h, const double* err_dev, int64_t 
     CK(cudaMemcpyAsync(a.data(), acc, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(hh.data(), hist, sizeof(unsigned long long) * bins, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    cudaFree(acc);
     std::memset(out, 0, sizeof(*out));
     out->n = a[0];
     if (a[0] <= 0) return 0;

@@ -80,6 +80,11 @@ class TrialEngine:
         self.hist_log2_sub = int(hist_log2_sub)
         self.stats_len = stats_len(hist_log2_sub)
 
+    def set_tuning(self, window: int = 0, key_radius_deg: float = -1.0) -> None:
+        """Performance knobs (results never depend on them): CTA sort window in trials (0 = default) and work-key disc
+        radius in degrees (< 0 = default).  Replaces round 1's STMPM_WIN / STMPM_KEY_RADIUS_DEG environment variables."""
+        _abi.check(self._lib.stmpm_set_tuning(self._h, int(window), float(key_radius_deg)))
+
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:
             self._lib.stmpm_destroy(self._h)
@@ -114,6 +119,21 @@ class TrialEngine:
         _abi.check(self._lib.stmpm_work_counters(self._h, int(n), int(seed), int(trial0), C.byref(dist), out))
         return {"visits": out[0], "mag_pass": out[1], "survivors": out[2], "detected": out[3]}
 
+    def _check_dev(self, t, dtype, numel: int, name: str, optional: bool = False) -> None:
+        """A device buffer handed to the C ABI must be a contiguous CUDA tensor of the right dtype and size on THIS engine's
+        device: the library writes numel * itemsize bytes through the raw pointer."""
+        if t is None:
+            if optional:
+                return
+            raise ValueError(f"{name} is required")
+        if isinstance(t, np.ndarray) or not getattr(t, "is_cuda", False):
+            raise ValueError(f"{name} must be a CUDA tensor (host buffers go through run_presampled / run_rng)")
+        if t.device.index != self.device:
+            raise ValueError(f"{name} lives on cuda:{t.device.index}, the engine on cuda:{self.device}")
+        if t.dtype != dtype or t.numel() != int(numel) or not t.is_contiguous():
+            raise ValueError(f"{name} must be a contiguous {dtype} tensor of {int(numel)} elements "
+                             f"(got {t.dtype}, {t.numel()} elements, contiguous={t.is_contiguous()})")
+
     # ---------------------------------------------------------------- pre-sampled mode
     @staticmethod
     def _col_ptrs(cols, n_expected=None):
@@ -140,6 +160,8 @@ class TrialEngine:
         if isinstance(cols, np.ndarray):
             cols = np.ascontiguousarray(cols, dtype=np.float64)
         ptrs, n = self._col_ptrs(cols)
+        _check_host_out(out_err, np.float64, n, "out_err")
+        _check_host_out(out_ndet, np.int32, n, "out_ndet")
         err = out_err if out_err is not None else np.empty(n, dtype=np.float64)
         ndet = out_ndet if out_ndet is not None else np.empty(n, dtype=np.int32)
         stats = np.zeros(self.stats_len, dtype=np.float64) if want_stats else None
@@ -158,12 +180,19 @@ class TrialEngine:
                               stream: int = 0) -> None:
         """DEVICE buffers (torch CUDA tensors), stream-ordered, asynchronous."""
         ptrs, n = self._col_ptrs(cols)
+        for r in (cols[i] for i in range(_abi.NCOLS)):
+            self._check_dev(r, _torch_f64(), n, "cols")
+        self._check_dev(err, _torch_f64(), n, "err", optional=True)
+        self._check_dev(ndet, _torch_dtype("int32"), n, "ndet", optional=True)
+        self._check_dev(stats, _torch_f64(), self.stats_len, "stats", optional=True)
         _abi.check(self._lib.stmpm_trials_presampled(self._h, int(precision), n, int(seed) & (2**64 - 1), int(trial0),
                                                      ptrs, _ptr(err), _ptr(ndet), _ptr(stats), int(stream)))
 
     def fill_presampled_device(self, cols, dist: _abi.Dist, *, seed: int, trial0: int = 0, stream: int = 0) -> None:
         """The seeded generator kernel of config 2: fills 13 device columns with native-RNG mode's draws."""
         ptrs, n = self._col_ptrs(cols)
+        for r in (cols[i] for i in range(_abi.NCOLS)):
+            self._check_dev(r, _torch_f64(), n, "cols")
         _abi.check(self._lib.stmpm_fill_presampled(self._h, n, int(seed) & (2**64 - 1), int(trial0), C.byref(dist), ptrs,
                                                    int(stream)))
 
@@ -200,6 +229,10 @@ class TrialEngine:
                        precision: int = 64, stream: int = 0) -> None:
         """DEVICE buffers, stream-ordered, asynchronous. stats (+=) must be zeroed by the caller: [n_segments, stats_len]."""
         arr, ns = self._dist_array(dists)
+        n = ns * int(trials_per_segment)
+        self._check_dev(stats, _torch_f64(), ns * self.stats_len, "stats", optional=True)
+        self._check_dev(err, _torch_f64(), n, "err", optional=True)
+        self._check_dev(ndet, _torch_dtype("int32"), n, "ndet", optional=True)
         _abi.check(self._lib.stmpm_trials_rng(self._h, int(precision), ns, int(trials_per_segment),
                                               int(seed) & (2**64 - 1), int(trial0), arr, _ptr(err), _ptr(ndet),
                                               _ptr(stats), int(stream)))
@@ -243,6 +276,19 @@ def summarize(stats: np.ndarray, hist_log2_sub: int = 8) -> dict:
     s = _abi.Summary()
     _abi.check(_abi.load().stmpm_stats_finalize(int(hist_log2_sub), _ptr(stats), C.byref(s)))
     return {k: getattr(s, k) for k, _ in _abi.Summary._fields_}
+
+
+def _check_host_out(a, dtype, n: int, name: str) -> None:
+    if a is None:
+        return
+    if not isinstance(a, np.ndarray) or a.dtype != dtype or a.size != int(n) or not a.flags.c_contiguous \
+            or not a.flags.writeable:
+        raise ValueError(f"{name} must be a writeable C-contiguous numpy {np.dtype(dtype).name}[{int(n)}] array")
+
+
+def _torch_dtype(name: str):
+    import torch
+    return getattr(torch, name)
 
 
 def _torch_f64():

@@ -10,7 +10,13 @@ if ROOT not in sys.path:
 
 REFERENCE_DIR = "/root/reference"
 STUBS_DIR = os.path.join(ROOT, "tests", "stubs")
-GOLDEN = os.path.join(ROOT, "tests", "golden", "trial_golden_v1.npz")
+GOLDEN = os.path.join(ROOT, "tests", "golden", "trial_golden_v1.npz")      # regression pin (made by the oracle itself)
+GOLDEN_V2 = os.path.join(ROOT, "tests", "golden", "trial_golden_v2.npz")   # made by tests/golden/independent_trial.py
+# the reference's entry scripts: /root/reference here; on the GPU box the copy __graft_entry__.build() staged
+# (baseline/_ref is git-ignored but travels with the snapshot)
+STAGED_REFERENCE_DIR = os.path.join(ROOT, "baseline", "_ref")
+if not os.path.exists(os.path.join(REFERENCE_DIR, "driver.py")) and os.path.exists(os.path.join(STAGED_REFERENCE_DIR, "driver.py")):
+    REFERENCE_DIR = STAGED_REFERENCE_DIR
 
 BASIC_MEAN = dict(FOCAL_LENGTH=3500.0, F_ARR_EPS_X=0.0, F_ARR_EPS_Y=0.0, F_ARR_EPS_Z=0.0, F_ARR_PHI=0.0,
                   F_ARR_THETA=0.0, F_ARR_PSI=0.0, BASE_DEV_X=0.0, BASE_DEV_Y=0.0, MAX_MAGNITUDE=6.0, D_TEMP=0.0)
@@ -33,6 +39,13 @@ def catalog():
 @pytest.fixture(scope="session")
 def golden():
     with np.load(GOLDEN) as f:
+        return {k: f[k] for k in f.files}
+
+
+@pytest.fixture(scope="session")
+def golden_v2():
+    """Inputs and outputs of the independent scalar restatement (scipy align_vectors, libm, own Philox)."""
+    with np.load(GOLDEN_V2) as f:
         return {k: f[k] for k in f.files}
 
 

@@ -70,3 +70,20 @@ def test_table_box_muller_matches_libm(lib_built):
     z1, z2 = engine.debug_box_muller(wa, wb)
     r1, r2 = philox.box_muller(wa, wb)
     assert np.abs(z1 - r1).max() < 1e-12 and np.abs(z2 - r2).max() < 1e-12
+
+
+def test_engine_rejects_mis_sized_host_buffers(lib_built):
+    """caller-owned record buffers are written through raw pointers, so dtype / size / contiguity are
+    checked before the C ABI sees them.  (The check runs before any GPU work: testable without a device.)"""
+    import numpy as np
+    import pytest
+    from startrackermpm_b200 import engine as eng
+    for bad in (np.empty(9, np.float64), np.empty(10, np.float32), np.empty(20, np.float64)[::2], [0.0] * 10):
+        with pytest.raises(ValueError):
+            eng._check_host_out(bad, np.float64, 10, "out_err")
+    ro = np.empty(10, np.float64)
+    ro.flags.writeable = False
+    with pytest.raises(ValueError):
+        eng._check_host_out(ro, np.float64, 10, "out_err")
+    eng._check_host_out(np.empty(10, np.float64), np.float64, 10, "out_err")
+    eng._check_host_out(None, np.float64, 10, "out_err")

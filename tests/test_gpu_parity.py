@@ -49,6 +49,18 @@ def test_golden_fixture(engine, golden, prec):
 
 
 @pytest.mark.parametrize("prec", [64, 32])
+def test_independent_golden_v2(engine, golden_v2, prec):
+    """CUDA against the fixture of the independent scalar restatement (tests/golden/independent_trial.py: scipy
+    align_vectors, libm Box-Muller, own Philox — no code shared with oracle/ or csrc/), 64-bit seed, trial indices
+    across 2^32."""
+    g = golden_v2
+    e, d = engine.run_presampled(g["cols"], int(g["seed"]), int(g["trial0"]), precision=prec)
+    compare(e, d, g["err_arcsec"], g["n_det"], prec)
+    e2, d2, m2 = engine.run_presampled(g["cols"], int(g["seed"]), int(g["trial0"]), precision=prec, want_maxmag=True)
+    assert np.array_equal(d2, g["n_det"]) and np.array_equal(m2, g["faintest_mag"])     # star_mag objective, bit-exact
+
+
+@pytest.mark.parametrize("prec", [64, 32])
 def test_stress_configs(engine, catalog, prec):
     """Sweep-like extremes: 4x sigmas, wide FOV (f = 1000 px), everything visible (MAX_MAGNITUDE = 20, sensitivity.py:112),
     nothing visible, poles / RA wrap, negative BASE_DEV (sensitivity.py:46-47)."""
@@ -307,16 +319,16 @@ def test_two_engines_with_different_catalog_sizes_coexist(engine, catalog):
     assert np.array_equal(e0, e1) and np.array_equal(d0, d1)
 
 
-def test_records_do_not_depend_on_the_sort_window(engine, monkeypatch):
+def test_records_do_not_depend_on_the_sort_window(engine):
     """The work-key sort and the dynamic group scheduling only reorder WHICH lanes run a trial: per-trial records are
-    bit-identical for every window size (STMPM_WIN is the kernel's tuning knob), in both modes, and the streamed
+    bit-identical for every window size (stmpm_set_tuning's window is the kernel's tuning knob), in both modes, and the streamed
     moments / histogram account for every trial exactly once."""
     n = 300_001                                            # ragged: last window / group partially filled
     cols = trial.sample_params(BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF, 33, 7, n)
     dist = make_dist(BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF)
     ref = ref_rng = None
-    for win in ("32", "96", "256", "1024", "2048"):
-        monkeypatch.setenv("STMPM_WIN", win)
+    for win in (32, 96, 256, 1024, 2048):
+        engine.set_tuning(window=win)
         e, d, st = engine.run_presampled(cols, 33, 7, want_stats=True)
         if ref is None:
             ref = (e, d)
@@ -333,3 +345,4 @@ def test_records_do_not_depend_on_the_sort_window(engine, monkeypatch):
         for k in range(3):
             ek, dk = e3[k * 70_001:(k + 1) * 70_001], d3[k * 70_001:(k + 1) * 70_001]
             assert s3[k, 0] == (ek >= 0).sum() and s3[k, 1] == (ek < 0).sum() and s3[k, 4] == dk.sum()
+    engine.set_tuning(window=0)

@@ -163,3 +163,47 @@ def test_oracle_reproduces_golden_fixture(catalog, golden):
     assert np.array_equal(e < 0, golden["err_arcsec"] < 0)
     ok = e >= 0
     assert np.abs(e[ok] - golden["err_arcsec"][ok]).max() / ARCSEC < 1e-10
+
+
+def test_oracle_reproduces_the_independent_golden_v2(catalog, golden_v2):
+    """trial_golden_v2.npz comes from tests/golden/independent_trial.py — a scalar per-row restatement of MODEL.md that
+    shares no function with this oracle (own Philox, libm Box-Muller, scipy's SVD align_vectors).  Counts and failure
+    flags must be identical, errors within 1e-12 rad (two different Wahba solvers in float64)."""
+    xyz, mag = catalog
+    g = golden_v2
+    e, d = trial.run_trials(g["cols"], xyz, mag, float(g["f_ideal"]), int(g["seed"]), int(g["trial0"]), brute=True, chunk=16)
+    assert np.array_equal(d, g["n_det"])
+    assert np.array_equal(e < 0, g["err_arcsec"] < 0)
+    ok = e >= 0
+    assert np.abs(e[ok] - g["err_arcsec"][ok]).max() / trial.RAD2ARCSEC < 1e-12
+    assert set(np.unique(g["scenario"])) >= {"basic", "ideal", "all_visible", "few_stars", "sigma_x5", "poles_wrap"}
+    assert (g["err_arcsec"] < 0).sum() > 20 and g["n_det"].max() > 90          # failures and star-rich fields are in it
+
+
+def test_oracle_sampler_matches_the_independent_sampler():
+    """MODEL.md §6 restated twice: oracle.sample_params (vectorised numpy) vs independent_trial.draw_rows (Python ints)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import independent_trial as it
+    from conftest import BASIC_MEAN, BASIC_SIGMA
+    seed, t0, n = 0xABCDEF0123456789, (1 << 32) - 7, 40
+    a = trial.sample_params(BASIC_MEAN, BASIC_SIGMA, 2e-5, seed, t0, n)
+    b = it.draw_rows(BASIC_MEAN, BASIC_SIGMA, 2e-5, seed, t0, n)
+    assert np.abs(a - b).max() < 1e-11
+    assert np.array_equal(a[:3], b[:3])                                         # the uniform draws are exact
+
+
+def test_independent_restatement_known_answers(catalog):
+    """The second restatement is itself pinned: an ideal tracker has zero error, a pure psi tilt returns psi."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import independent_trial as it
+    xyz, mag = catalog
+    row = [1.0, 0.3, -2.0, 3500.0, 0, 0, 0, 0, 0, 0, 0, 0, 6.0]
+    e, n, _ = it.one_trial(row, xyz, mag, 3500.0, 1, 0)
+    assert n >= 3 and e / trial.RAD2ARCSEC < 1e-12
+    row[9] = 0.25                                                               # psi = 0.25 deg about the boresight
+    e, n, _ = it.one_trial(row, xyz, mag, 3500.0, 1, 0)
+    assert abs(e / trial.RAD2ARCSEC - np.deg2rad(0.25)) < 1e-12
