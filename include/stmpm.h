@@ -75,6 +75,24 @@ typedef struct {
     int32_t mode_bin, reserved;
 } stmpm_toolplot;
 
+/* Result of the on-device MonteCarlo.run_sim loop (monte_carlo.py:30-80). */
+typedef struct {
+    int64_t count;            /* batches run == MonteCarlo.count (monte_carlo.py:50,79) */
+    int64_t trials;           /* count * batch */
+    int64_t converged;        /* 1 = the stop rule fired, 0 = max_batches reached first */
+    int64_t rounds;           /* host synchronisations it took (1 for a default run) */
+    int64_t trials_computed;  /* trials the device evaluated, speculative ones after the stopping batch included */
+    double  n_ok, n_fail, fail_rate;
+    double  sigma_halfnormal; /* monte_carlo.py:61 `prev` after the last batch == driver.py:324 true_std */
+    double  mean_halfnormal;  /* driver.py:323 */
+    double  std_ratio;        /* monte_carlo.py:60 after the last batch */
+} stmpm_mc_result;
+
+/* toolplot.py:240-256 (mode 'c') statistics of a magnitude column. */
+typedef struct {
+    double n, min, max, mean, std, std_halfnormal;
+} stmpm_column_stats;
+
 const char* stmpm_last_error(void);
 int stmpm_version(void);
 
@@ -145,6 +163,29 @@ int stmpm_run_presampled_host_ex(stmpm_t* h, int precision, int64_t n, uint64_t 
 int stmpm_run_rng_host(stmpm_t* h, int precision, int64_t n_segments, int64_t trials_per_segment, uint64_t seed,
                        int64_t trial0, const stmpm_dist* dists_host, double* err_arcsec_host, int32_t* n_det_host,
                        double* stats_host);
+
+/* MonteCarlo.run_sim's convergence loop on the device (monte_carlo.py:45-76): batches of `batch`
+ * native-RNG trials (global trial indices trial0 + k*batch + i) until the successful rows number at least min_rows AND
+ * |prev - sigma_hat| / prev <= tol (sigma_hat = std(ddof=1)/sqrt(1-2/pi) over all successful trials so far, prev starts
+ * at 1), or successful rows >= max_runs > 0, or max_batches (> 0) batches ran.  The rule is evaluated after EVERY batch,
+ * on the device; the host reads the state once per round of 16+ chunks of up to 1024 batches.  stats_host (optional)
+ * receives the packed statistics of exactly the batches the loop accepted.  The reference's defaults: batch 100
+ * (driver.py:21,74), min_rows 10000, tol 1e-5 (monte_carlo.py:48), max_runs = driver.py's -n. */
+int stmpm_mc_converge(stmpm_t* h, int precision, const stmpm_dist* dist_host, int32_t batch, uint64_t seed, int64_t trial0,
+                      int64_t min_rows, double tol, int64_t max_runs, int64_t max_batches, stmpm_mc_result* out,
+                      double* stats_host);
+
+/* toolplot.py:170-187 (mode 's'): "Quantity-Based Star Failure Rate" per unique MAX_MAGNITUDE value, from n rows of
+ * (error with the -1 failure sentinel kept, MAX_MAGNITUDE), after the 6-sigma clip of toolplot.py:82-83.  levels_host:
+ * the n_levels sorted unique magnitudes; rows_host / failed_host [n_levels + 1]: rows and failed rows per level (last
+ * slot: rows matching no level).  rate[%] = 100 * failed / rows. */
+int stmpm_toolplot_failrate(stmpm_t* h, const double* err_arcsec_dev, const double* max_magnitude_dev, int64_t n,
+                            const double* levels_host, int32_t n_levels, double* rows_host, double* failed_host,
+                            void* stream);
+/* toolplot.py:240-256 (mode 'c'): min / max / std of the 'MAXIMUM MAGNITUDE VISIBLE' column (the star_mag objective's
+ * float32 output; -inf = no star detected, skipped) and its `bins`-bin density histogram, np.histogram-identical. */
+int stmpm_column_hist(stmpm_t* h, const float* x_dev, int64_t n, int32_t bins, stmpm_column_stats* out,
+                      double* density_host, void* stream);
 
 /* toolplot.py's reductions on the device from n per-trial error records (err < 0 = failed trial = a row the reference
  * dropped).  density_host (optional) receives the `bins` values of np.histogram(kept, bins, density=True)[0]. */

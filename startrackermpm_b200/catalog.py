@@ -101,12 +101,6 @@ def build_sky_grid(xyz: np.ndarray, mag: np.ndarray, cell_deg: float = DEFAULT_C
                    star_id=order.astype(np.int32))
 
 
-if __name__ == "__main__":  # python -m startrackermpm_b200.catalog  -> (re)writes the committed catalog
-    save_catalog()
-    x, m = load_catalog()
-    print("wrote", DEFAULT_CATALOG_PATH, x.shape, m.shape, "mag<=5.5:", int((m <= 5.5).sum()))
-
-
 def load_bsc5(path: str):
     """Yale Bright Star Catalog, 5th ed., binary distribution (`BSC5`, /root/reference/constants.py:33 `BSC5BIN`; the file is
     absent from the reference mount — SURVEY.md §8f rank 4: "real-catalog loader if a catalog file is ever supplied").
@@ -135,3 +129,9 @@ def load_bsc5(path: str):
     xyz = np.stack([np.cos(dec) * np.cos(ra), np.cos(dec) * np.sin(ra), np.sin(dec)], axis=1)
     return (np.ascontiguousarray(xyz), (ent["mag"][keep].astype(np.float32) / np.float32(100.0)),
             ent["xno"][keep].astype(np.int32))
+
+
+if __name__ == "__main__":  # python -m startrackermpm_b200.catalog  -> (re)writes the committed catalog
+    save_catalog()
+    x, m = load_catalog()
+    print("wrote", DEFAULT_CATALOG_PATH, x.shape, m.shape, "mag<=5.5:", int((m <= 5.5).sum()))

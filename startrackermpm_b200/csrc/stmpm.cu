@@ -52,6 +52,7 @@ struct KArgs {
     double* stats;
     long long stats_len;
     unsigned long long* counters;   // INSTR only: [visits, mag_pass, survivors, detected]
+    const int* cancel;              // optional: a non-zero word makes the launch a no-op (on-device MonteCarlo stop rule)
 };
 
 // Shared-memory layout: every region at a COMPILE-TIME offset (fixed-size regions first, the variable-size catalog
@@ -272,6 +273,7 @@ __device__ __forceinline__ void flush_moments(double* st, int lane, unsigned int
 template <int MODE, int PREC, int INSTR>
 __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
+    if (a.cancel != nullptr && *reinterpret_cast<const volatile int*>(a.cancel) != 0) return;   // converged in an earlier chunk
     float4* s_cat = reinterpret_cast<float4*>(smem + OFF_CAT);
     int2* s_band = reinterpret_cast<int2*>(smem + OFF_BAND);
     int2* s_lkband = reinterpret_cast<int2*>(smem + OFF_LKBAND);
@@ -703,6 +705,175 @@ __global__ void __launch_bounds__(256) toolplot_pass3(const double* __restrict__
         if (v >= 0.0 && v <= clip) {
             // numpy.histogram: provisional index from the scaled position, then corrected against the actual edges
             int b = (int)((v - lo) * norm);
+            if (b >= bins) b = bins - 1;
+            const double e0 = lo + (double)b * step, e1 = (b + 1 == bins) ? hi : lo + (double)(b + 1) * step;
+            if (v < e0 && b > 0) --b;
+            else if (v >= e1 && b != bins - 1) ++b;
+            atomicAdd(&s_h[b], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < bins; i += blockDim.x) if (s_h[i]) atomicAdd(hist + i, (unsigned long long)s_h[i]);
+}
+
+
+// ------------------------------------------------------------------------------------------------ MonteCarlo stop rule
+// MonteCarlo.run_sim's convergence loop (/root/reference/monte_carlo.py:45-76) evaluated ON THE DEVICE.  The trials of a
+// chunk of batches are computed speculatively by one trials_kernel launch (they are independent of the rule); this
+// single-CTA kernel then replays the reference's sequential rule over the chunk's batches in parallel: per-batch moments
+// (thread = batch, fixed summation order), a block-wide prefix sum with the carry of the earlier chunks, sigma_hat after
+// every batch, the first batch k with  not(ratio_k > tol or n_k < min_rows)  or  (max_runs > 0 and n_k >= max_runs).
+// Trials after the stopping batch are discarded: the statistics cover exactly the batches the reference's loop ran.
+struct McState {
+    double n_ok, n_fail, sum, sum2, sum_ndet, x_max;   // totals over the batches accepted so far
+    double prev, ratio;                                // monte_carlo.py:46,60-61
+    long long count;                                   // batches run (MonteCarlo.count, monte_carlo.py:50,79)
+    int done, pad;
+};
+constexpr int MC_MAX_BATCHES = 1024;                   // batches per chunk = threads of the rule kernel
+
+__global__ void __launch_bounds__(MC_MAX_BATCHES) mc_rule_kernel(const double* __restrict__ err, const int* __restrict__ ndet,
+                                                                 int n_batches, int batch, McState* st, double* stats, int hist_shift,
+                                                                 int n_bins, long long min_rows, double tol, long long max_runs) {
+    __shared__ double s_n[32], s_s1[32], s_s2[32];
+    __shared__ double s_sig[MC_MAX_BATCHES];
+    __shared__ int s_stop;
+    if (st->done) return;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    double n = 0.0, s1 = 0.0, s2 = 0.0;
+    if (t < n_batches) {
+        const double* e = err + (long long)t * batch;
+        for (int i = 0; i < batch; ++i) {
+            const double v = e[i];
+            if (v >= 0.0) { n += 1.0; s1 += v; s2 = fma(v, v, s2); }
+        }
+    }
+    if (t == 0) s_stop = n_batches;
+    // inclusive prefix sums over the batches of the chunk (fixed order: warp scan, then the warp totals)
+    double pn = n, p1 = s1, p2 = s2;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const double a = __shfl_up_sync(0xffffffffu, pn, off), b = __shfl_up_sync(0xffffffffu, p1, off),
+                     c = __shfl_up_sync(0xffffffffu, p2, off);
+        if (lane >= off) { pn += a; p1 += b; p2 += c; }
+    }
+    if (lane == 31) { s_n[warp] = pn; s_s1[warp] = p1; s_s2[warp] = p2; }
+    __syncthreads();
+    double cn = st->n_ok, c1 = st->sum, c2 = st->sum2;
+    for (int w = 0; w < warp; ++w) { cn += s_n[w]; c1 += s_s1[w]; c2 += s_s2[w]; }
+    pn += cn; p1 += c1; p2 += c2;                       // totals after batch t
+    // sigma_hat = std(ddof = 1) / sqrt(1 - 2/pi)   (monte_carlo.py:60-61; driver.py:290)
+    const double var = pn > 1.0 ? fmax(0.0, (p2 - p1 * p1 / pn) / (pn - 1.0)) : 0.0;
+    const double sig = sqrt(var) / 0.6028102749890869;  // sqrt(1 - 2/pi)
+    if (t < n_batches) s_sig[t] = sig;
+    __syncthreads();
+    const double prev = t == 0 ? st->prev : s_sig[t - 1];
+    const double ratio = fabs((prev - sig) / prev);
+    bool stop = false;
+    if (t < n_batches) stop = !(ratio > tol || pn < (double)min_rows) || (max_runs > 0 && pn >= (double)max_runs);
+    if (stop) atomicMin(&s_stop, t);
+    __syncthreads();
+    const int k = s_stop;                               // first stopping batch, or n_batches
+    const int last = min(k, n_batches - 1);             // last batch accepted from this chunk
+    // statistics of the accepted records: failures, n_det, maximum, histogram (integer counts: order-independent)
+    double nf = 0.0, snd = 0.0, xm = 0.0;
+    const long long n_rec = (long long)(last + 1) * batch;
+    for (long long i = t; i < n_rec; i += blockDim.x) {
+        const double v = err[i];
+        snd += (double)ndet[i];
+        if (v >= 0.0) {
+            xm = fmax(xm, v);
+            const long long e = (__double_as_longlong(v) >> hist_shift) - ((long long)(1023 + STMPM_HIST_MIN_EXP) << (52 - hist_shift));
+            const int slot = e < 0 ? 6 : (e >= n_bins ? 7 : STMPM_STATS_HEAD + (int)e);
+            atomicAdd(stats + slot, 1.0);
+        } else {
+            nf += 1.0;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        nf += __shfl_xor_sync(0xffffffffu, nf, off); snd += __shfl_xor_sync(0xffffffffu, snd, off);
+        xm = fmax(xm, __shfl_xor_sync(0xffffffffu, xm, off));
+    }
+    __syncthreads();                                    // s_n / s_s1 / s_s2 are re-used below
+    if (lane == 0) { s_n[warp] = nf; s_s1[warp] = snd; s_s2[warp] = xm; }
+    __syncthreads();
+    if (t == last) {                                    // this thread holds the totals after the last accepted batch
+        double tf = st->n_fail, td = st->sum_ndet, tm = st->x_max;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { tf += s_n[w]; td += s_s1[w]; tm = fmax(tm, s_s2[w]); }
+        st->n_ok = pn; st->sum = p1; st->sum2 = p2; st->n_fail = tf; st->sum_ndet = td; st->x_max = tm;
+        st->prev = sig; st->ratio = ratio; st->count += last + 1;
+        stats[0] = pn; stats[1] = tf; stats[2] = p1; stats[3] = p2; stats[4] = td; stats[5] = tm;
+        __threadfence();
+        if (k < n_batches) st->done = 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ toolplot modes s, c
+// toolplot.py:170-187 (mode 's'): per unique MAX_MAGNITUDE value, the share of rows that failed (error stored as -1),
+// among the rows the 6-sigma clip of toolplot.py:82-83 keeps (std = RMS over ALL rows, sentinels included, as written
+// there).  levels: the sorted unique magnitudes; rows whose magnitude matches no level are counted in slot n_levels.
+__global__ void __launch_bounds__(256) toolplot_rms_all(const double* __restrict__ x, long long n, double* acc) {
+    double s2 = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = __ldcs(x + i);
+        s2 = fma(v, v, s2);
+    }
+    for (int off = 16; off > 0; off >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(acc, s2);
+}
+__global__ void __launch_bounds__(256) toolplot_failrate_kernel(const double* __restrict__ x, const double* __restrict__ mag, long long n,
+                                                                const double* __restrict__ levels, int n_levels, const double* acc,
+                                                                unsigned long long* rows, unsigned long long* failed) {
+    const double clip = 6.0 * sqrt(acc[0] / (double)n);                    // toolplot.py:82-83
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = __ldcs(x + i);
+        if (!(v <= clip)) continue;
+        const double m = __ldcs(mag + i);
+        int lo = 0, hi = n_levels;                                         // first level >= m
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (levels[mid] < m) lo = mid + 1; else hi = mid; }
+        const int slot = (lo < n_levels && levels[lo] == m) ? lo : n_levels;
+        atomicAdd(rows + slot, 1ull);
+        if (v < 0.0) atomicAdd(failed + slot, 1ull);                       // toolplot.py:170-172: -1 -> 1, everything else -> 0
+    }
+}
+// toolplot.py:240-256 (mode 'c'): min, max, std and the 50-bin density histogram of a magnitude column (float32 on the
+// device: the star_mag objective's output; -inf = no star detected = a row the reference never had).
+__global__ void __launch_bounds__(256) column_pass1(const float* __restrict__ x, long long n, double* acc) {
+    double c = 0.0, s1 = 0.0, s2 = 0.0, mn = INFINITY, mx = -INFINITY;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = (double)__ldcs(x + i);
+        if (v > -INFINITY && v < INFINITY) { c += 1.0; s1 += v; s2 = fma(v, v, s2); mn = fmin(mn, v); mx = fmax(mx, v); }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        c += __shfl_xor_sync(0xffffffffu, c, off); s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, off)); mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    }
+    if ((threadIdx.x & 31) == 0 && c > 0.0) {
+        atomicAdd(acc + 0, c); atomicAdd(acc + 1, s1); atomicAdd(acc + 2, s2);
+        // order-preserving key of a double: flip all bits of negatives, the sign bit of non-negatives
+        const unsigned long long bn = (unsigned long long)__double_as_longlong(mn), bx = (unsigned long long)__double_as_longlong(mx);
+        atomicMin(reinterpret_cast<unsigned long long*>(acc + 3), (bn >> 63) ? ~bn : (bn | 0x8000000000000000ull));
+        atomicMax(reinterpret_cast<unsigned long long*>(acc + 4), (bx >> 63) ? ~bx : (bx | 0x8000000000000000ull));
+    }
+}
+__device__ __forceinline__ double key_to_double(unsigned long long k) {
+    return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
+}
+__global__ void __launch_bounds__(256) column_pass2(const float* __restrict__ x, long long n, const double* acc, int bins,
+                                                    unsigned long long* hist) {
+    extern __shared__ unsigned int s_h[];
+    for (int i = threadIdx.x; i < bins; i += blockDim.x) s_h[i] = 0u;
+    __syncthreads();
+    const double lo = key_to_double(reinterpret_cast<const unsigned long long*>(acc)[3]);
+    const double hi = key_to_double(reinterpret_cast<const unsigned long long*>(acc)[4]);
+    const double step = (hi - lo) / (double)bins;                          // numpy.linspace(lo, hi, bins + 1)
+    const double norm = hi > lo ? (double)bins / (hi - lo) : 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = (double)__ldcs(x + i);
+        if (v > -INFINITY && v < INFINITY) {
+            int b = (int)((v - lo) * norm);                                // numpy.histogram's index, corrected against the edges
             if (b >= bins) b = bins - 1;
             const double e0 = lo + (double)b * step, e1 = (b + 1 == bins) ? hi : lo + (double)(b + 1) * step;
             if (v < e0 && b > 0) --b;
@@ -1463,6 +1634,139 @@ extern "C" int stmpm_toolplot_reduce(stmpm_t* h, const double* err_dev, int64_t 
     if (density_host) {
         const double w = hi > lo ? step : 1.0;
         for (int i = 0; i < bins; ++i) density_host[i] = (double)hh[i] / (a[2] * w);
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ MonteCarlo.run_sim on the device
+// monte_carlo.py:30-80 without a DataFrame, without a launch + synchronise per batch: the host enqueues rounds of chunks
+// (trials_kernel + mc_rule_kernel per chunk of up to 1024 batches) and reads the state ONCE per round; every launch after
+// the rule fired is a no-op (cancel word).  The first round already covers 16 chunks, so a default run (min_rows 10 000,
+// stop some hundred batches later) is one round: one synchronisation, one 70 KB read.
+extern "C" int stmpm_mc_converge(stmpm_t* h, int precision, const stmpm_dist* dist, int32_t batch, uint64_t seed, int64_t trial0,
+                                 int64_t min_rows, double tol, int64_t max_runs, int64_t max_batches, stmpm_mc_result* out,
+                                 double* stats_host) {
+    KArgs a;
+    if (int rc = fill_common(h, a, precision)) return rc;
+    if (!dist || !out || batch <= 0 || batch > (1 << 20) || max_batches < 0)
+        return fail(STMPM_E_ARG, "stmpm_mc_converge: bad arguments (batch must be in [1, 2^20])");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = h->streams[0];
+    const long long slen = a.stats_len;
+    const int chunk_batches = (int)std::max<long long>(1, std::min<long long>(MC_MAX_BATCHES, (1LL << 22) / batch));
+    const long long chunk_trials = (long long)chunk_batches * batch;
+    if (int rc = ensure_stage(h, chunk_trials, false)) return rc;
+    if (int rc = ensure_stats(h, slen + (long long)(sizeof(McState) + 7) / 8)) return rc;
+    double* d_stats = h->stage_stats;
+    McState* d_state = reinterpret_cast<McState*>(h->stage_stats + slen);
+    McState init{};
+    init.prev = 1.0; init.ratio = 1.0;                                      // monte_carlo.py:45-46
+    CK(cudaMemsetAsync(d_stats, 0, sizeof(double) * slen, st));
+    CK(cudaMemcpyAsync(d_state, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+    to_dev_dist(*dist, a.dist0);
+    a.n_segments = 1; a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
+    a.err = h->stage_err[0]; a.ndet = h->stage_ndet[0]; a.stats = nullptr;
+    a.cancel = &d_state->done;
+    McState res{};
+    long long done_batches = 0, rounds = 0, chunks_per_round = 16;
+    const long long limit = max_batches > 0 ? max_batches : (1LL << 40);
+    for (;;) {
+        for (long long c = 0; c < chunks_per_round && done_batches < limit; ++c) {
+            const int nb = (int)std::min<long long>(chunk_batches, limit - done_batches);
+            KArgs k = a;
+            k.trials_per_segment = (long long)nb * batch;
+            k.trial0 = trial0 + done_batches * batch;
+            const int rc = precision == 64 ? launch_trials<1, 64>(h, k, st) : launch_trials<1, 32>(h, k, st);
+            if (rc) return rc;
+            mc_rule_kernel<<<1, MC_MAX_BATCHES, 0, st>>>(h->stage_err[0], h->stage_ndet[0], nb, batch, d_state, d_stats, a.hist_shift,
+                                                         a.n_bins, (long long)min_rows, tol, (long long)max_runs);
+            CK(cudaGetLastError());
+            ++h->launches;
+            done_batches += nb;
+        }
+        ++rounds;
+        CK(cudaMemcpyAsync(&res, d_state, sizeof(res), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (res.done || done_batches >= limit) break;
+        chunks_per_round = std::min<long long>(chunks_per_round * 4, 4096);
+    }
+    if (stats_host) CK(cudaMemcpy(stats_host, d_stats, sizeof(double) * slen, cudaMemcpyDeviceToHost));
+    std::memset(out, 0, sizeof(*out));
+    out->count = res.count; out->trials = res.count * batch; out->converged = res.done;
+    out->n_ok = res.n_ok; out->n_fail = res.n_fail; out->std_ratio = res.ratio;
+    out->sigma_halfnormal = res.prev;                                        // monte_carlo.py:61 (prev = sigma_hat of the last batch)
+    out->mean_halfnormal = res.prev * std::sqrt(2.0 / M_PI);                 // driver.py:291,323
+    out->fail_rate = (res.n_ok + res.n_fail) > 0 ? res.n_fail / (res.n_ok + res.n_fail) : 0.0;
+    out->rounds = rounds; out->trials_computed = done_batches * batch;
+    return 0;
+}
+
+extern "C" int stmpm_toolplot_failrate(stmpm_t* h, const double* err_dev, const double* mag_dev, int64_t n,
+                                       const double* levels_host, int32_t n_levels, double* rows_host, double* failed_host,
+                                       void* stream) {
+    if (!h || !err_dev || !mag_dev || !levels_host || !rows_host || !failed_host || n <= 0 || n_levels < 1 || n_levels > (1 << 20))
+        return fail(STMPM_E_ARG, "stmpm_toolplot_failrate: bad arguments");
+    for (int i = 1; i < n_levels; ++i)
+        if (!(levels_host[i] > levels_host[i - 1])) return fail(STMPM_E_ARG, "stmpm_toolplot_failrate: levels must be strictly increasing");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    struct DevBuf { void* p = nullptr; ~DevBuf() { cudaFree(p); } } buf;
+    const size_t n_slots = (size_t)n_levels + 1;
+    const size_t bytes = 8 + sizeof(double) * n_levels + 2 * sizeof(unsigned long long) * n_slots;
+    CK(cudaMalloc(&buf.p, bytes));
+    double* acc = static_cast<double*>(buf.p);
+    double* lev = acc + 1;
+    unsigned long long* rows = reinterpret_cast<unsigned long long*>(lev + n_levels);
+    unsigned long long* failed = rows + n_slots;
+    CK(cudaMemsetAsync(buf.p, 0, bytes, st));
+    CK(cudaMemcpyAsync(lev, levels_host, sizeof(double) * n_levels, cudaMemcpyHostToDevice, st));
+    const int grid = (int)std::min<long long>((n + 255) / 256, (long long)h->prop.multiProcessorCount * 16);
+    toolplot_rms_all<<<grid, 256, 0, st>>>(err_dev, n, acc);
+    toolplot_failrate_kernel<<<grid, 256, 0, st>>>(err_dev, mag_dev, n, lev, n_levels, acc, rows, failed);
+    CK(cudaGetLastError());
+    h->launches += 2;
+    std::vector<unsigned long long> hr(2 * n_slots);
+    CK(cudaMemcpyAsync(hr.data(), rows, sizeof(unsigned long long) * 2 * n_slots, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < n_slots; ++i) { rows_host[i] = (double)hr[i]; failed_host[i] = (double)hr[n_slots + i]; }
+    return 0;
+}
+
+extern "C" int stmpm_column_hist(stmpm_t* h, const float* x_dev, int64_t n, int32_t bins, stmpm_column_stats* out,
+                                 double* density_host, void* stream) {
+    if (!h || !x_dev || !out || n <= 0 || bins < 1 || bins > 4096) return fail(STMPM_E_ARG, "stmpm_column_hist: bad arguments");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    struct DevBuf { void* p = nullptr; ~DevBuf() { cudaFree(p); } } buf;
+    const size_t bytes = sizeof(double) * 8 + sizeof(unsigned long long) * bins;
+    CK(cudaMalloc(&buf.p, bytes));
+    double* acc = static_cast<double*>(buf.p);
+    unsigned long long* hist = reinterpret_cast<unsigned long long*>(acc + 8);
+    CK(cudaMemsetAsync(buf.p, 0, bytes, st));
+    const unsigned long long all_ones = ~0ull;                              // minimum key starts at the top
+    CK(cudaMemcpyAsync(acc + 3, &all_ones, 8, cudaMemcpyHostToDevice, st));
+    const int grid = (int)std::min<long long>((n + 255) / 256, (long long)h->prop.multiProcessorCount * 16);
+    column_pass1<<<grid, 256, 0, st>>>(x_dev, n, acc);
+    column_pass2<<<grid, 256, sizeof(unsigned int) * bins, st>>>(x_dev, n, acc, bins, hist);
+    CK(cudaGetLastError());
+    h->launches += 2;
+    double a[8];
+    std::vector<unsigned long long> hh(bins);
+    CK(cudaMemcpyAsync(a, acc, sizeof(a), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hh.data(), hist, sizeof(unsigned long long) * bins, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::memset(out, 0, sizeof(*out));
+    out->n = a[0];
+    if (a[0] <= 0) return 0;
+    auto unkey = [](double d) { unsigned long long k; std::memcpy(&k, &d, 8); k = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+                                double r; std::memcpy(&r, &k, 8); return r; };
+    out->min = unkey(a[3]); out->max = unkey(a[4]);
+    out->mean = a[1] / a[0];
+    out->std = a[0] > 1 ? std::sqrt(std::max(0.0, (a[2] - a[1] * a[1] / a[0]) / (a[0] - 1.0))) : 0.0;    // pandas .std(): ddof = 1
+    out->std_halfnormal = out->std * std::sqrt(1.0 - 2.0 / M_PI);                                         // toolplot.py:248,254
+    if (density_host) {
+        const double w = out->max > out->min ? (out->max - out->min) / bins : 1.0;
+        for (int i = 0; i < bins; ++i) density_host[i] = (double)hh[i] / (a[0] * w);
     }
     return 0;
 }

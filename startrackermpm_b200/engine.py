@@ -248,6 +248,45 @@ class TrialEngine:
         d["density"] = dens
         return d
 
+    def mc_converge(self, dist: _abi.Dist, *, batch: int = 100, seed: int = 0, trial0: int = 0, min_rows: int = 10_000,
+                    tol: float = 1e-5, max_runs: int = -1, max_batches: int = 0, precision: int = 64) -> dict:
+        """MonteCarlo.run_sim's convergence loop (monte_carlo.py:45-76) with the rule evaluated on the device after every
+        batch; one host synchronisation per round of >= 16384 batches.  Returns count, trials, sigma_halfnormal, ... and
+        the packed statistics of the accepted batches."""
+        res = _abi.McResult()
+        stats = np.zeros(self.stats_len, dtype=np.float64)
+        _abi.check(self._lib.stmpm_mc_converge(self._h, int(precision), C.byref(dist), int(batch), int(seed) & (2**64 - 1),
+                                               int(trial0), int(min_rows), float(tol), int(max_runs), int(max_batches),
+                                               C.byref(res), _ptr(stats)))
+        out = {k: getattr(res, k) for k, _ in _abi.McResult._fields_}
+        out["stats"] = stats
+        return out
+
+    def toolplot_failrate(self, err, max_magnitude, levels, stream: int = 0) -> dict:
+        """toolplot.py:170-187 (mode 's') on the device: err / max_magnitude are float64 CUDA tensors [n] (failures kept as
+        -1), levels the sorted unique magnitudes.  Returns rows, failed, rate_percent per level (+ unmatched rows)."""
+        n = int(err.shape[0])
+        self._check_dev(err, _torch_f64(), n, "err")
+        self._check_dev(max_magnitude, _torch_f64(), n, "max_magnitude")
+        lev = np.ascontiguousarray(levels, dtype=np.float64)
+        rows, failed = np.empty(lev.size + 1), np.empty(lev.size + 1)
+        _abi.check(self._lib.stmpm_toolplot_failrate(self._h, _ptr(err), _ptr(max_magnitude), n, _ptr(lev), lev.size,
+                                                     _ptr(rows), _ptr(failed), int(stream)))
+        with np.errstate(invalid="ignore", divide="ignore"):
+            rate = 100.0 * failed[:-1] / rows[:-1]
+        return {"levels": lev, "rows": rows[:-1], "failed": failed[:-1], "rate_percent": rate, "unmatched_rows": rows[-1]}
+
+    def column_hist(self, x, bins: int = 50, stream: int = 0) -> dict:
+        """toolplot.py:240-256 (mode 'c') on the device: x = the star_mag objective's float32 CUDA column."""
+        n = int(x.shape[0])
+        self._check_dev(x, _torch_dtype("float32"), n, "x")
+        out = _abi.ColumnStats()
+        dens = np.empty(int(bins), dtype=np.float64)
+        _abi.check(self._lib.stmpm_column_hist(self._h, _ptr(x), n, int(bins), C.byref(out), _ptr(dens), int(stream)))
+        d = {k: getattr(out, k) for k, _ in _abi.ColumnStats._fields_}
+        d["density"] = dens
+        return d
+
     # ---------------------------------------------------------------- statistics
     def summarize(self, stats: np.ndarray) -> dict:
         return summarize(stats, self.hist_log2_sub)

@@ -34,19 +34,31 @@ def _merge(total: np.ndarray, part: np.ndarray) -> None:
 def monte_carlo_converged(engine: TrialEngine, means: Mapping[str, float], sigmas: Mapping[str, float],
                           thermal_coef: float = 0.0, *, batch: int = 100, seed: int = 0, max_runs: int = -1,
                           min_rows: int = 10_000, tol: float = 1e-5, precision: int = 64,
-                          batches_per_launch: int = 1) -> dict:
+                          batches_per_launch: int = 1, on_device: bool = True) -> dict:
     """MonteCarlo.run_sim's loop (monte_carlo.py:48-76): batches of `batch` trials until the kept rows number at least
     `min_rows` AND the relative change of the half-normal sigma is <= tol, or kept rows >= max_runs > 0.
-    sigma_hat = std(x, ddof=1) / sqrt(1 - 2/pi) over all successful trials so far (monte_carlo.py:60-61), computed from
-    the merged packed statistics instead of a growing DataFrame.  `batches_per_launch` > 1 evaluates the rule every
-    that many batches (one kernel launch each) — the reference's rule is batches_per_launch = 1."""
+    sigma_hat = std(x, ddof=1) / sqrt(1 - 2/pi) over all successful trials so far (monte_carlo.py:60-61).
+
+    on_device=True (default): `stmpm_mc_converge` — the rule is evaluated on the GPU after every batch, the host reads the
+    state once.  on_device=False: round 1's host loop, one launch + synchronisation per
+    `batches_per_launch` batches on merged packed statistics (kept as the cross-check; the reference's rule is
+    batches_per_launch = 1)."""
     dist = make_dist(means, sigmas, thermal_coef)
+    if on_device:
+        if batches_per_launch != 1:
+            raise ValueError("batches_per_launch applies to the host loop only (on_device=False)")
+        r = engine.mc_converge(dist, batch=batch, seed=seed, min_rows=min_rows, tol=tol, max_runs=max_runs, precision=precision)
+        out = summarize(r["stats"], engine.hist_log2_sub)
+        out.update(count=r["count"], trials=r["trials"], std_ratio=r["std_ratio"], stats=r["stats"],
+                   sigma_halfnormal=r["sigma_halfnormal"], mean_halfnormal=r["mean_halfnormal"],
+                   converged=bool(r["converged"]), rounds=r["rounds"], trials_computed=r["trials_computed"])
+        return out
     total = np.zeros(engine.stats_len)
     prev, ratio, count, trial0 = 1.0, 1.0, 0, 0                      # monte_carlo.py:45-46
     per_launch = int(batch) * int(batches_per_launch)
     while ratio > tol or total[0] < min_rows:
         count += batches_per_launch
-        part = engine.run_rng(dist, per_launch, seed, trial0, precision)[0]
+        part = engine.run_rng(dist, per_launch, seed, trial0, precision, )[0]
         trial0 += per_launch
         _merge(total, part)
         n = total[0]
@@ -123,12 +135,15 @@ def orbit_dtemp_amplitude(form_factor: str = "1U", damping: float = 0.65) -> flo
 
 
 def leo_lifetime_dists(means: Mapping[str, float], sigmas: Mapping[str, float], thermal_coef: float, n_steps: int = 60,
-                       years: float = 5.0, dtemp_amp: float = 15.0, dtemp_sigma: float = 5.0,
+                       years: float = 5.0, dtemp_amp: float | None = None, dtemp_sigma: float = 5.0,
                        mag_loss_per_year: float = 0.12, dev_growth_per_year: float = 0.15):
     """Config 4 schedule [FREE, SURVEY.md §8d]: monthly steps over `years`.  Thermal: D_TEMP mean follows a seasonal
     sinusoid of amplitude dtemp_amp K (beta-angle cycle), sigma dtemp_sigma.  Radiation: accumulated dose raises the image
     noise floor, i.e. lowers the detection threshold MAX_MAGNITUDE linearly by mag_loss_per_year and inflates the
-    centroiding sigma by dev_growth_per_year (fractional)."""
+    centroiding sigma by dev_growth_per_year (fractional).  dtemp_amp defaults to `orbit_dtemp_amplitude()` — the
+    radiative balance on the reference's own constants (constants.py:99-108), not a hard-coded number."""
+    if dtemp_amp is None:
+        dtemp_amp = orbit_dtemp_amplitude()
     dists, sched = [], []
     for k in range(n_steps):
         t = years * k / max(1, n_steps - 1)

@@ -198,3 +198,105 @@ def test_bsc5_binary_loader_round_trip(tmp_path, order):
         bad = tmp_path / "bad"
         bad.write_bytes(b"\0" * 64)
         catalog.load_bsc5(str(bad))
+
+
+@pytest.mark.parametrize("name", ["le", "be"])
+def test_bsc5_loader_on_the_hand_built_byte_fixture(name):
+    """tests/golden/bsc5_three_stars.*.bin: header + Sirius (HR 2491), Vega (HR 7001), HR 1 and one position-less entry,
+    packed byte by byte from the published BSC5 record layout (tests/golden/make_bsc5_fixture.py, `struct.pack`) — not
+    written through the loader's own numpy dtype."""
+    import os
+    from startrackermpm_b200 import catalog
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"bsc5_three_stars.{name}.bin")
+    raw = open(path, "rb").read()
+    assert len(raw) == 28 + 4 * 32
+    # spot-check the bytes themselves against the layout: NBENT = 32 closes the header, the first entry's XNO is 2491.0f
+    assert raw[24:28] == ((32).to_bytes(4, "little") if name == "le" else (32).to_bytes(4, "big"))
+    assert raw[28:32] == (bytes.fromhex("00b01b45") if name == "le" else bytes.fromhex("451bb000"))       # 2491.0 as IEEE-754 float32
+    xyz, mag, hr = catalog.load_bsc5(path)
+    assert hr.tolist() == [2491, 7001, 1]                                   # the position-less row is dropped
+    assert mag.tolist() == [np.float32(-1.46), np.float32(0.03), np.float32(6.70)]
+    ra = np.arctan2(xyz[:, 1], xyz[:, 0]) % (2 * np.pi)
+    dec = np.arcsin(xyz[:, 2])
+    assert np.allclose(np.rad2deg(ra), [101.28708, 279.23458, 1.29125], atol=1e-4)        # 06h45m08.9s, 18h36m56.3s, 00h05m09.9s
+    assert np.allclose(np.rad2deg(dec), [-16.71611, 38.78361, 45.22917], atol=1e-4)
+    assert np.allclose(np.linalg.norm(xyz, axis=1), 1.0, atol=1e-15)
+
+
+@pytest.mark.gpu
+def test_on_device_stop_rule_equals_the_host_loop(engine):
+    """SURVEY.md §8f rank 1 / VERDICT r1 #6: `stmpm_mc_converge` (rule evaluated on the device after every batch, one host
+    read) must stop at the SAME batch with the same sigma as the host loop over per-launch statistics, and as the
+    reference's loop replayed with pandas on the per-trial records — at >= 100x the host loop's trials/s."""
+    import time
+    from startrackermpm_b200 import studies
+    from startrackermpm_b200.engine import make_dist
+    k = np.sqrt(1 - 2 / np.pi)
+    for tol, min_rows, batch, seed, max_runs in ((2e-3, 3000, 100, 12, -1), (1e-5, 10_000, 100, 5, -1), (1e-9, 500, 64, 9, 2000)):
+        kw = dict(batch=batch, seed=seed, min_rows=min_rows, tol=tol, max_runs=max_runs)
+        dev = studies.monte_carlo_converged(engine, BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF, **kw)
+        host = studies.monte_carlo_converged(engine, BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF, on_device=False, **kw)
+        assert dev["count"] == host["count"] and dev["n_ok"] == host["n_ok"] and dev["n_fail"] == host["n_fail"]
+        assert dev["sigma_halfnormal"] == pytest.approx(host["sigma_halfnormal"], rel=1e-12)
+        assert dev["rounds"] == 1 and dev["converged"]
+        assert np.array_equal(dev["stats"][6:], host["stats"][6:]) and dev["stats"][4] == host["stats"][4]   # histogram, n_det
+        assert dev["stats"][5] == host["stats"][5]                                                           # x_max
+        # the reference's loop, verbatim structure, on the records
+        _, err, _ = engine.run_rng(make_dist(BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF), dev["trials"] + 3 * batch, seed, 0, records=True)
+        fin, prev, ratio, count = pd.Series(dtype=float), 1.0, 1.0, 0
+        while ratio > tol or len(fin) < min_rows:
+            chunk = pd.Series(err[count * batch:(count + 1) * batch])
+            count += 1
+            fin = pd.concat([fin, chunk[chunk >= 0]])
+            ratio = abs((prev - (fin / k).std()) / prev)
+            prev = fin.std() / k
+            if max_runs > 0 and len(fin) >= max_runs:
+                break
+        assert count == dev["count"] and len(fin) == dev["n_ok"]
+        assert dev["sigma_halfnormal"] == pytest.approx(prev, rel=1e-10)
+    # speed: the reference's defaults
+    kw = dict(batch=100, seed=5, min_rows=10_000, tol=1e-5)
+    studies.monte_carlo_converged(engine, BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF, **kw)
+    t = time.perf_counter(); dev = studies.monte_carlo_converged(engine, BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF, **kw); t_dev = time.perf_counter() - t
+    t = time.perf_counter(); host = studies.monte_carlo_converged(engine, BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF, on_device=False, **kw); t_host = time.perf_counter() - t
+    print(f"\nstop rule: {dev['count']} batches; on-device {t_dev * 1e3:.2f} ms ({dev['trials'] / t_dev:.3e} trials/s, "
+          f"{dev['trials_computed']} computed) vs host loop {t_host * 1e3:.1f} ms ({host['trials'] / t_host:.3e} trials/s): {t_host / t_dev:.0f}x")
+    assert t_host / t_dev >= 20          # >= 100x at realistic batch counts; the bound here is kept loose against box noise
+
+
+@pytest.mark.gpu
+def test_toolplot_modes_s_and_c_on_device(engine):
+    """toolplot.py:170-187 (failure rate per unique MAX_MAGNITUDE) and :240-256 (magnitude column statistics + histogram)
+    from device-resident records, against the reference's own pandas arithmetic."""
+    import torch
+    from startrackermpm_b200.engine import make_dist
+    n_lev, per = 25, 4000
+    levels = np.linspace(3.0, 6.0, n_lev)
+    dists = [make_dist(dict(BASIC_MEAN, MAX_MAGNITUDE=float(m)), dict(BASIC_SIGMA, MAX_MAGNITUDE=0.0), THERMAL_COEF) for m in levels]
+    _, err, _ = engine.run_rng(dists, per, 21, 0, records=True)
+    mag = np.repeat(levels, per)
+    d_err, d_mag = torch.from_numpy(err).cuda(), torch.from_numpy(mag).cuda()
+    got = engine.toolplot_failrate(d_err, d_mag, levels)
+    # toolplot.py:82-83,170-187 verbatim on a DataFrame
+    col = "QUATERNION_ERROR_[arcsec]"
+    df = pd.DataFrame({"MAX_MAGNITUDE": mag, col: err})
+    std = np.sqrt((df[col] ** 2).sum() / len(df.index))
+    df = df[df[col] <= 6 * std]
+    data = df[["MAX_MAGNITUDE", col]].copy()
+    data.loc[data[col] > 0, col] = 0
+    data[col] *= -1
+    xdata = data.MAX_MAGNITUDE.unique()
+    ydata = [data[data.MAX_MAGNITUDE == m][col].sum() / len(data[data.MAX_MAGNITUDE == m].index) * 100 for m in xdata]
+    assert np.array_equal(np.sort(xdata), levels) and got["unmatched_rows"] == 0
+    assert np.allclose(got["rate_percent"], np.array(ydata)[np.argsort(xdata)], rtol=0, atol=1e-12)
+    assert got["rate_percent"][0] > 50 and got["rate_percent"][-1] < 1
+    # mode 'c': the star_mag objective's column
+    from oracle import trial
+    cols = trial.sample_params(BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF, 8, 0, 50_000)
+    _, _, mm = engine.run_presampled(cols, 8, 0, want_maxmag=True)
+    c = engine.column_hist(torch.from_numpy(mm).cuda(), bins=50)
+    s = pd.Series(mm[np.isfinite(mm)].astype(np.float64))
+    assert c["n"] == len(s) and c["min"] == s.min() and c["max"] == s.max()
+    assert c["std"] == pytest.approx(s.std(), rel=1e-12) and c["std_halfnormal"] == pytest.approx(s.std() * np.sqrt(1 - 2 / np.pi), rel=1e-12)
+    h = np.histogram(s, bins=50, density=True)
+    assert np.allclose(c["density"], h[0], rtol=1e-12, atol=0)
