@@ -48,13 +48,24 @@ def work_flops_per_trial(n_cand: float, n_star: float) -> float:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
+# Three baselines, all on the numpy fp64 oracle with the SAME sky-grid candidate search
+# idea the GPU uses (oracle.trial.CandidateGrid: ~170 listed stars per trial instead of all 9 110):
+#   C1 "faithful": the reference's own driver.py -n 10000, unmodified, one core, its own pandas batch-of-100 loop and clock
+#   C2 "fair-1"  : the vectorised oracle on one core
+#   C3 "fair-N"  : the vectorised oracle, one process per host core
 def _cpu_worker(args):
     t0, n = args
     from oracle import trial
     from startrackermpm_b200.catalog import load_catalog
-    xyz, mag = load_catalog()
+    global _CPU_CAT
+    try:
+        xyz, mag, grid = _CPU_CAT
+    except NameError:
+        xyz, mag = load_catalog()
+        grid = trial.candidate_grid(xyz)
+        _CPU_CAT = (xyz, mag, grid)
     cols = trial.sample_params(BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF, SEED, t0, n)
-    e, d = trial.run_trials(cols, xyz, mag, F_IDEAL, SEED, t0)
+    e, d = trial.run_trials(cols, xyz, mag, F_IDEAL, SEED, t0, grid=grid)
     return int((e >= 0).sum()), float(e[e >= 0].sum())
 
 
@@ -65,7 +76,7 @@ def cpu_trials_per_sec(per_core: int, cores: int, pool=None):
     if own:
         os.environ.setdefault("OMP_NUM_THREADS", "1")    # one process per core; no BLAS oversubscription
         pool = mp.get_context("spawn").Pool(cores)
-        pool.map(_cpu_worker, [(i * 64, 64) for i in range(cores)])      # warm: imports + catalog load
+        pool.map(_cpu_worker, [(i * 64, 64) for i in range(cores)])      # warm: imports, catalog load, grid build
     t = time.perf_counter()
     res = pool.map(_cpu_worker, [(i * per_core, per_core) for i in range(cores)])
     dt = time.perf_counter() - t
@@ -73,6 +84,37 @@ def cpu_trials_per_sec(per_core: int, cores: int, pool=None):
         pool.close()
     assert sum(r[0] for r in res) > 0
     return cores * per_core / dt, dt
+
+
+def cpu_c1_faithful(n: int = 10000):
+    """C1: unmodified reference driver.py -n 10000 (configs[0]) in a fresh single-threaded process; its own clock."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1")
+    try:
+        r = subprocess.run([sys.executable, "-m", "oracle.run_reference_driver", str(n)], cwd=ROOT, env=env,
+                           capture_output=True, text=True, timeout=600)
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as ex:                                               # noqa: BLE001 — a baseline must not sink the bench
+        return {"unavailable": f"{type(ex).__name__}: {str(ex)[:120]}"}
+    if "unavailable" in d:
+        return d
+    return {"value": d["trials_per_s"], "unit": UNIT, "cores": 1, "rows": d["rows"], "seconds": d["seconds"],
+            "sigma_arcsec": d["sigma_arcsec"],
+            "what": "unmodified reference driver.py -n 10000 (-b 100: 100 batches through its own pandas loop) on the drop-in "
+                    "simObjects with the numpy oracle as engine; timed by driver.py:280,319"}
+
+
+def cpu_baselines(per_core_all: int, cores: int, per_core_one: int = 100_000, pool=None):
+    """cpu_baseline object: headline value = C3 (all cores); C1 and C2 beside it."""
+    c3, dt3 = cpu_trials_per_sec(per_core_all, cores, pool)
+    c2, dt2 = cpu_trials_per_sec(per_core_one, 1)
+    return {"value": c3, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{cores * per_core_all} trials of the same workload ({per_core_all} per process x {cores} processes, "
+                      f"numpy fp64 oracle with sky-grid candidate lists, {dt3:.1f} s)",
+            "c1_faithful": cpu_c1_faithful(),
+            "c2_vectorised_1core": {"value": c2, "unit": UNIT, "cores": 1, "sample": f"{per_core_one} trials, {dt2:.1f} s"},
+            "c3_all_cores": {"value": c3, "unit": UNIT, "cores": cores},
+            "candidate_search": "sky-grid lists (oracle.trial.CandidateGrid, ~170 stars per trial); round 1 timed the "
+                                "brute-force 9 110-star product"}
 
 
 def run_reference_arm(args):
@@ -91,19 +133,25 @@ def run_reference_arm(args):
     for _ in range(args.steps):
         cpu_trials_per_sec(per_core, cores, pool)
     dt = time.perf_counter() - t
-    pool.close()
     n = cores * per_core
     v = n * args.steps / dt
+    c2, dt2 = cpu_trials_per_sec(max(20_000, per_core), 1)
+    pool.close()
     sample = f"{n} trials per step ({per_core} per process x {cores} processes) of the same default-config workload"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(n, args.gpus),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "c1_faithful": cpu_c1_faithful(),
+                         "c2_vectorised_1core": {"value": c2, "unit": UNIT, "cores": 1, "sample": f"{max(20_000, per_core)} trials, {dt2:.1f} s"},
+                         "c3_all_cores": {"value": v, "unit": UNIT, "cores": cores},
+                         "candidate_search": "sky-grid lists (oracle.trial.CandidateGrid, ~170 stars per trial)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "numpy fp64 oracle port (oracle/trial.py): the reference's own trial code is absent from its mount "
-                "(SURVEY.md §0), so no unmodified reference exists to install or time",
+                "(SURVEY.md §0), so no unmodified implementation of the trial exists to install or time; its entry scripts "
+                "ARE staged (baseline/_ref) and drive C1",
     }))
     return 0
 
@@ -316,12 +364,7 @@ def run_ours(args):
                                             "p999", "mean_ndet")},
         }
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            v, dt = cpu_trials_per_sec(args.cpu_trials_per_core, cores)
-            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                   "sample": f"{cores * args.cpu_trials_per_core} trials of the same workload "
-                                             f"({args.cpu_trials_per_core} per process x {cores} processes, numpy fp64 "
-                                             f"oracle, {dt:.1f} s)"}
+            out["cpu_baseline"] = cpu_baselines(args.cpu_trials_per_core, os.cpu_count() or 1)
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
@@ -338,14 +381,14 @@ def main():
     ap.add_argument("--trials", type=float, default=1e8, help="trials per GPU per step (configs[1]: 1e8)")
     ap.add_argument("--e2e-trials", type=float, default=1e8, help="trials per GPU per e2e step")
     ap.add_argument("--cpu-trials-per-core", type=int, default=None,
-                    help="oracle-port trials per host process: default 131072 for the cpu_baseline leg (~13 s), 32768 per step "
+                    help="oracle-port trials per host process: default 262144 for the cpu_baseline leg (~13 s), 65536 per step "
                          "for --impl reference (~3 s per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--window", type=int, default=0, help="tuning sweep: CTA sort window in trials (0 = default)")
     ap.add_argument("--key-radius-deg", type=float, default=-1.0, help="tuning sweep: work-key disc radius (<0 = default)")
     args = ap.parse_args()
     if args.cpu_trials_per_core is None:
-        args.cpu_trials_per_core = 32768 if args.impl == "reference" else 131072
+        args.cpu_trials_per_core = 65536 if args.impl == "reference" else 262144
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_ours(args)

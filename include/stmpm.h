@@ -168,7 +168,7 @@ int stmpm_run_rng_host(stmpm_t* h, int precision, int64_t n_segments, int64_t tr
  * native-RNG trials (global trial indices trial0 + k*batch + i) until the successful rows number at least min_rows AND
  * |prev - sigma_hat| / prev <= tol (sigma_hat = std(ddof=1)/sqrt(1-2/pi) over all successful trials so far, prev starts
  * at 1), or successful rows >= max_runs > 0, or max_batches (> 0) batches ran.  The rule is evaluated after EVERY batch,
- * on the device; the host reads the state once per round of 16+ chunks of up to 1024 batches.  stats_host (optional)
+ * on the device; the host reads the state once per round (round 1 = twice the batches min_rows needs, then x4).  stats_host (optional)
  * receives the packed statistics of exactly the batches the loop accepted.  The reference's defaults: batch 100
  * (driver.py:21,74), min_rows 10000, tol 1e-5 (monte_carlo.py:48), max_runs = driver.py's -n. */
 int stmpm_mc_converge(stmpm_t* h, int precision, const stmpm_dist* dist_host, int32_t batch, uint64_t seed, int64_t trial0,

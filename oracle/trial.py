@@ -146,14 +146,69 @@ def candidate_cos_limit(cols):
     return np.cos(np.minimum(ang, np.pi))
 
 
+class CandidateGrid:
+    """Sky-grid candidate search for the CPU arm (VERDICT r1 "weak" #6: the brute-force `bore @ cat_xyz.T` visits all
+    9 110 stars per trial, the GPU ~42 — a handicapped baseline).  For every cell of a `cell_deg` lookup grid: the indices
+    of all stars within `cone_rad` + the cell's radius of the cell centre, as one padded int32 table.  A trial whose own
+    candidate cone (candidate_cos_limit) fits inside `cone_rad` reads its boresight cell's list; any other trial falls
+    back to the all-stars cone test.  Pure acceleration structure: detection never depends on it
+    (tests/test_oracle_trial.py checks grid == brute)."""
+
+    def __init__(self, cat_xyz, cone_rad, cell_deg=2.0):
+        cat_xyz = np.asarray(cat_xyz, dtype=np.float64)
+        self.cone_rad = float(cone_rad)
+        self.n_bands = int(round(180.0 / cell_deg))
+        self.band_h = np.pi / self.n_bands
+        dec_mid = -0.5 * np.pi + (np.arange(self.n_bands) + 0.5) * self.band_h
+        self.n_ra = np.maximum(1, np.round(2.0 * np.pi * np.cos(dec_mid) / self.band_h)).astype(np.int64)
+        self.cell_base = np.concatenate([[0], np.cumsum(self.n_ra)])
+        lists = []
+        for b in range(self.n_bands):
+            w = 2.0 * np.pi / self.n_ra[b]
+            ra_c = (np.arange(self.n_ra[b]) + 0.5) * w
+            centre = np.stack([np.cos(dec_mid[b]) * np.cos(ra_c), np.cos(dec_mid[b]) * np.sin(ra_c),
+                               np.full_like(ra_c, np.sin(dec_mid[b]))], -1)
+            # cell radius: the farthest corner from the centre (the wider of the band's two edges)
+            d_edge = np.array([dec_mid[b] - 0.5 * self.band_h, dec_mid[b] + 0.5 * self.band_h])
+            corner = np.cos(dec_mid[b]) * np.cos(d_edge) * np.cos(0.5 * w) + np.sin(dec_mid[b]) * np.sin(d_edge)
+            rho = np.arccos(np.clip(corner.min(), -1.0, 1.0))
+            lim = np.cos(min(np.pi, self.cone_rad + 1.05 * rho + 1e-3))
+            inside = (centre @ cat_xyz.T) >= lim
+            lists += [np.nonzero(row)[0] for row in inside]
+        self.length = np.array([len(x) for x in lists], dtype=np.int64)
+        self.table = np.full((len(lists), max(1, self.length.max())), -1, dtype=np.int32)
+        for i, x in enumerate(lists):
+            self.table[i, :len(x)] = x
+
+    def cell_of(self, bore):
+        dec = np.arcsin(np.clip(bore[:, 2], -1.0, 1.0))
+        ra = np.mod(np.arctan2(bore[:, 1], bore[:, 0]), 2.0 * np.pi)
+        band = np.clip(np.floor((dec + 0.5 * np.pi) / self.band_h).astype(np.int64), 0, self.n_bands - 1)
+        rc = np.minimum((ra / (2.0 * np.pi) * self.n_ra[band]).astype(np.int64), self.n_ra[band] - 1)
+        return self.cell_base[band] + rc
+
+
+_GRIDS: dict = {}
+
+
+def candidate_grid(cat_xyz, cone_rad=np.deg2rad(14.0), cell_deg=2.0) -> CandidateGrid:
+    """Cached CandidateGrid for this catalog array (keyed by identity + shape, cone and cell size)."""
+    key = (id(cat_xyz), np.asarray(cat_xyz).shape, round(float(cone_rad), 9), cell_deg)
+    if key not in _GRIDS:
+        _GRIDS[key] = CandidateGrid(cat_xyz, cone_rad, cell_deg)
+    return _GRIDS[key]
+
+
 def run_trials(cols, cat_xyz, cat_mag, f_ideal, seed, trial0=0, *, brute=False, chunk=512, n_min=N_MIN,
-               solver="q_method", return_aux=False, star_ids=None):
+               solver="q_method", return_aux=False, star_ids=None, grid=None):
     """The hot path (reference: Simulation.run_sim + quest_objective, called at monte_carlo.py:52 / sensitivity.py:77;
     bodies absent) per docs/MODEL.md §2-§5.
 
     cols: float64 [13, n] in COLUMNS order (pre-sampled rows).  Returns (err_arcsec f64 [n] with -1 = failed,
     n_det int32 [n]).  Trial i uses global trial index trial0 + i for its Philox stream; star_ids (default: row index)
     are the catalog-file indices that key each star's noise, independent of the order of cat_xyz's rows.
+    Candidate search: brute=True tests every star; default = a per-trial cone over all stars (one [n, S] product);
+    grid=CandidateGrid = the boresight cell's list (the fair CPU baseline, bench.py).
     """
     cols = np.ascontiguousarray(np.asarray(cols, dtype=np.float64))
     assert cols.shape[0] == 13
@@ -167,7 +222,7 @@ def run_trials(cols, cat_xyz, cat_mag, f_ideal, seed, trial0=0, *, brute=False, 
     for s0 in range(0, n, chunk):
         sl = slice(s0, min(n, s0 + chunk))
         e, d, a = _run_chunk(cols[:, sl], cat_xyz, cat_mag64, star_ids, float(f_ideal), seed,
-                             np.uint64(trial0) + np.arange(sl.start, sl.stop, dtype=np.uint64), brute, n_min, solver)
+                             np.uint64(trial0) + np.arange(sl.start, sl.stop, dtype=np.uint64), brute, n_min, solver, grid)
         err[sl], ndet[sl] = e, d
         if return_aux:
             aux["n_cand"] += a["n_cand"]
@@ -176,7 +231,7 @@ def run_trials(cols, cat_xyz, cat_mag, f_ideal, seed, trial0=0, *, brute=False, 
     return (err, ndet, aux) if return_aux else (err, ndet)
 
 
-def _run_chunk(cols, cat_xyz, cat_mag64, star_ids, f_ideal, seed, trial_idx, brute, n_min, solver):
+def _run_chunk(cols, cat_xyz, cat_mag64, star_ids, f_ideal, seed, trial_idx, brute, n_min, solver, grid=None):
     m = cols.shape[1]
     ra, dec, roll, f, ex, ey, ez, phi, theta, psi, devx, devy, maxmag = cols
     C = truth_attitude(ra, dec, roll)                      # [m,3,3] body->inertial
@@ -185,12 +240,32 @@ def _run_chunk(cols, cat_xyz, cat_mag64, star_ids, f_ideal, seed, trial_idx, bru
     p0 = np.stack([ex, ey, f + ez], -1)
 
     bore = C[:, :, 2]
-    dots = bore @ cat_xyz.T                                # [m,S]
-    if brute:
-        cand = np.ones_like(dots, dtype=bool)
+    if grid is not None and not brute:
+        lim = candidate_cos_limit(cols)
+        fits = lim >= np.cos(grid.cone_rad)                # the trial's own cone lies inside the lists' cone
+        cell = grid.cell_of(bore)
+        tab = grid.table[cell]                             # [m, Lmax] star indices, -1 = padding
+        valid = (tab >= 0) & fits[:, None]
+        ti, col = np.nonzero(valid)
+        si = tab[ti, col].astype(np.int64)
+        keep = np.einsum("pi,pi->p", bore[ti], cat_xyz[si]) >= lim[ti]      # the per-trial cone, on the listed stars only
+        ti, si = ti[keep], si[keep]
+        n_cand = int(valid.sum())
+        rest = np.nonzero(~fits)[0]                        # wider cones than the lists were built for: all-stars test
+        if rest.size:
+            t2, s2 = np.nonzero(bore[rest] @ cat_xyz.T >= lim[rest][:, None])
+            ti, si = np.concatenate([ti, rest[t2]]), np.concatenate([si, s2])
+            order = np.argsort(ti, kind="stable")
+            ti, si = ti[order], si[order]
+            n_cand += int(rest.size) * cat_xyz.shape[0]
     else:
-        cand = dots >= candidate_cos_limit(cols)[:, None]
-    ti, si = np.nonzero(cand)                              # flat (trial, star) pairs, trial-major
+        dots = bore @ cat_xyz.T                            # [m,S]
+        if brute:
+            cand = np.ones_like(dots, dtype=bool)
+        else:
+            cand = dots >= candidate_cos_limit(cols)[:, None]
+        ti, si = np.nonzero(cand)                          # flat (trial, star) pairs, trial-major
+        n_cand = int(cand.sum()) if brute else int(cand.size)
     s = cat_xyz[si]                                        # inertial reference vectors
     r = np.einsum("pji,pj->pi", C[ti], s)                  # r = C^T s
     n_dot_r = np.einsum("pi,pi->p", nrm[ti], r)
@@ -200,12 +275,17 @@ def _run_chunk(cols, cat_xyz, cat_mag64, star_ids, f_ideal, seed, trial_idx, bru
     u = np.einsum("pi,pi->p", e_u[ti], P)
     v = np.einsum("pi,pi->p", e_v[ti], P)
 
+    # Philox + Box-Muller only for the pairs a draw could still put on the array: |z| <= sqrt(-2 ln 2^-33) < 6.8, so a
+    # visible, bright-enough star farther than 6.8 sigma (+1 px) outside the array is undetectable for every draw
+    ax, ay = np.abs(devx[ti]), np.abs(devy[ti])
+    live = vis & (cat_mag64[si] <= maxmag[ti]) & (np.abs(u) <= HALF_U + 6.8 * ax + 1.0) & (np.abs(v) <= HALF_V + 6.8 * ay + 1.0)
+    ti, si, s, u, v, ax, ay = ti[live], si[live], s[live], u[live], v[live], ax[live], ay[live]
     x0, x1 = philox.star_words(seed, trial_idx[ti], star_ids[si])
     z1, z2 = philox.box_muller(x0, x1)
-    um = u + np.abs(devx[ti]) * z1
-    vm = v + np.abs(devy[ti]) * z2
+    um = u + ax * z1
+    vm = v + ay * z2
 
-    det = vis & (cat_mag64[si] <= maxmag[ti]) & (np.abs(um) <= HALF_U) & (np.abs(vm) <= HALF_V)
+    det = (np.abs(um) <= HALF_U) & (np.abs(vm) <= HALF_V)
     ndet = np.bincount(ti[det], minlength=m).astype(np.int32)
 
     td, sd = ti[det], s[det]
@@ -232,7 +312,7 @@ def _run_chunk(cols, cat_xyz, cat_mag64, star_ids, f_ideal, seed, trial_idx, bru
     # the faintest detected star, -inf when nothing is detected
     maxmag = np.full(m, -np.inf, dtype=np.float32)
     np.maximum.at(maxmag, td, cat_mag64[si[det]].astype(np.float32))
-    return err, ndet, {"n_cand": int(cand.sum()), "lam": lam_max, "maxmag": maxmag}
+    return err, ndet, {"n_cand": n_cand, "lam": lam_max, "maxmag": maxmag}
 
 
 # ---------------------------------------------------------------- native-RNG parameter sampling (MODEL.md §6)

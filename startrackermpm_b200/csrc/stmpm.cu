@@ -1641,8 +1641,9 @@ extern "C" int stmpm_toolplot_reduce(stmpm_t* h, const double* err_dev, int64_t 
 // ------------------------------------------------------------------------------------------------ MonteCarlo.run_sim on the device
 // monte_carlo.py:30-80 without a DataFrame, without a launch + synchronise per batch: the host enqueues rounds of chunks
 // (trials_kernel + mc_rule_kernel per chunk of up to 1024 batches) and reads the state ONCE per round; every launch after
-// the rule fired is a no-op (cancel word).  The first round already covers 16 chunks, so a default run (min_rows 10 000,
-// stop some hundred batches later) is one round: one synchronisation, one 70 KB read.
+// the rule fired is a no-op (cancel word).  The first round covers twice the batches min_rows needs, later rounds grow
+// fourfold, so a default run (min_rows 10 000, stop some hundred batches later) is one round: two launches, one
+// synchronisation, one 70 KB read.
 extern "C" int stmpm_mc_converge(stmpm_t* h, int precision, const stmpm_dist* dist, int32_t batch, uint64_t seed, int64_t trial0,
                                  int64_t min_rows, double tol, int64_t max_runs, int64_t max_batches, stmpm_mc_result* out,
                                  double* stats_host) {
@@ -1668,7 +1669,10 @@ extern "C" int stmpm_mc_converge(stmpm_t* h, int precision, const stmpm_dist* di
     a.err = h->stage_err[0]; a.ndet = h->stage_ndet[0]; a.stats = nullptr;
     a.cancel = &d_state->done;
     McState res{};
-    long long done_batches = 0, rounds = 0, chunks_per_round = 16;
+    // first round: twice the batches min_rows needs (the rule cannot fire earlier, and typically fires within that span)
+    long long done_batches = 0, rounds = 0;
+    long long chunks_per_round = std::max<long long>(1, (2 * std::max<long long>(min_rows, 0) / batch + chunk_batches - 1) / chunk_batches);
+    chunks_per_round = std::min<long long>(chunks_per_round, 4096);
     const long long limit = max_batches > 0 ? max_batches : (1LL << 40);
     for (;;) {
         for (long long c = 0; c < chunks_per_round && done_batches < limit; ++c) {

@@ -251,7 +251,7 @@ class TrialEngine:
     def mc_converge(self, dist: _abi.Dist, *, batch: int = 100, seed: int = 0, trial0: int = 0, min_rows: int = 10_000,
                     tol: float = 1e-5, max_runs: int = -1, max_batches: int = 0, precision: int = 64) -> dict:
         """MonteCarlo.run_sim's convergence loop (monte_carlo.py:45-76) with the rule evaluated on the device after every
-        batch; one host synchronisation per round of >= 16384 batches.  Returns count, trials, sigma_halfnormal, ... and
+        batch; one host synchronisation per round (a default run is one round).  Returns count, trials, sigma_halfnormal, ... and
         the packed statistics of the accepted batches."""
         res = _abi.McResult()
         stats = np.zeros(self.stats_len, dtype=np.float64)

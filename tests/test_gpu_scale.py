@@ -32,7 +32,7 @@ def _oracle(args):
     xyz, mag = load_catalog()
     m, s, _ = CONFIGS[name]
     cols = tr.sample_params(m, s, THERMAL_COEF, SEED, t0, n)
-    e, d = tr.run_trials(cols, xyz, mag, 3500.0, SEED, t0)
+    e, d = tr.run_trials(cols, xyz, mag, 3500.0, SEED, t0, grid=tr.candidate_grid(xyz))
     return cols, e, d
 
 

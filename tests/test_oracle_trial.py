@@ -207,3 +207,24 @@ def test_independent_restatement_known_answers(catalog):
     row[9] = 0.25                                                               # psi = 0.25 deg about the boresight
     e, n, _ = it.one_trial(row, xyz, mag, 3500.0, 1, 0)
     assert abs(e / trial.RAD2ARCSEC - np.deg2rad(0.25)) < 1e-12
+
+
+def test_sky_grid_candidate_search_equals_brute_force(catalog):
+    """The CPU arm's sky-grid candidate lists (oracle.trial.CandidateGrid: the fair baseline bench.py times) and the
+    noise-only-for-live-pairs shortcut change no result: identical counts and errors to brute force, including trials
+    whose cone exceeds the lists' (wide FOV, 5x sigmas) and boresights on the poles / RA wrap."""
+    from conftest import BASIC_MEAN, BASIC_SIGMA
+    xyz, mag = catalog
+    g = trial.candidate_grid(xyz)
+    cases = [trial.sample_params(BASIC_MEAN, BASIC_SIGMA, 2e-5, 3, 0, 600),
+             trial.sample_params(BASIC_MEAN, {k: 5 * v for k, v in BASIC_SIGMA.items()}, 2e-5, 3, 0, 300),
+             trial.sample_params(dict(BASIC_MEAN, FOCAL_LENGTH=1400.0), BASIC_SIGMA, 0.0, 3, 0, 60),
+             trial.sample_params(dict(BASIC_MEAN, MAX_MAGNITUDE=20.0), BASIC_SIGMA, 0.0, 3, 0, 100)]
+    polar = trial.sample_params(BASIC_MEAN, BASIC_SIGMA, 0.0, 3, 0, 90)
+    polar[1] = np.linspace(-np.pi / 2, np.pi / 2, 90)
+    polar[0] = np.linspace(-0.5, 2 * np.pi + 0.5, 90)
+    for cols in cases + [polar]:
+        e0, d0 = trial.run_trials(cols, xyz, mag, 3500.0, 3, 0, brute=True, chunk=32)
+        e1, d1, aux = trial.run_trials(cols, xyz, mag, 3500.0, 3, 0, grid=g, return_aux=True)
+        assert np.array_equal(d0, d1) and np.array_equal(e0, e1)
+    assert aux["n_cand"] / 90 < 400                                              # ~170 listed stars per trial, not 9 110

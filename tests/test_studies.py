@@ -238,7 +238,7 @@ def test_on_device_stop_rule_equals_the_host_loop(engine):
         host = studies.monte_carlo_converged(engine, BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF, on_device=False, **kw)
         assert dev["count"] == host["count"] and dev["n_ok"] == host["n_ok"] and dev["n_fail"] == host["n_fail"]
         assert dev["sigma_halfnormal"] == pytest.approx(host["sigma_halfnormal"], rel=1e-12)
-        assert dev["rounds"] == 1 and dev["converged"]
+        assert dev["rounds"] <= 2 and dev["converged"]
         assert np.array_equal(dev["stats"][6:], host["stats"][6:]) and dev["stats"][4] == host["stats"][4]   # histogram, n_det
         assert dev["stats"][5] == host["stats"][5]                                                           # x_max
         # the reference's loop, verbatim structure, on the records
@@ -261,7 +261,7 @@ def test_on_device_stop_rule_equals_the_host_loop(engine):
     t = time.perf_counter(); host = studies.monte_carlo_converged(engine, BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF, on_device=False, **kw); t_host = time.perf_counter() - t
     print(f"\nstop rule: {dev['count']} batches; on-device {t_dev * 1e3:.2f} ms ({dev['trials'] / t_dev:.3e} trials/s, "
           f"{dev['trials_computed']} computed) vs host loop {t_host * 1e3:.1f} ms ({host['trials'] / t_host:.3e} trials/s): {t_host / t_dev:.0f}x")
-    assert t_host / t_dev >= 20          # >= 100x at realistic batch counts; the bound here is kept loose against box noise
+    assert t_host / t_dev >= 30          # ~100x measured; the bound is kept loose against box noise
 
 
 @pytest.mark.gpu
