@@ -238,6 +238,8 @@ def run_ours(args):
     eng = TrialEngine(local, f_ideal=F_IDEAL)
     if args.window or args.key_radius_deg >= 0:
         eng.set_tuning(args.window, args.key_radius_deg)
+    if args.host_chunk:
+        eng.set_host_pipeline(args.host_chunk)
     d = make_dist(BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF)
     trial0 = rank * n                                      # weak scaling: every rank its own global trial-index range
     cols = torch.empty((13, n), dtype=torch.float64, device="cuda")
@@ -303,20 +305,48 @@ def run_ours(args):
                "trials_per_gpu_per_step": n_e2e, "steps": e2e_steps,
                "api": "stmpm_run_presampled_host (pinned host columns in, host records out, chunked H2D/kernel/D2H pipeline)",
                "records_match_device_run": bool(np.array_equal(he, err[:n_e2e].cpu().numpy()))}
+
+        def max_over_ranks(seconds):
+            t_ = torch.tensor([seconds], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            return float(t_.item())
+
+        def host_roofline(h2d, d2h, src, dst):
+            """copies only, same pipeline (stmpm_host_copy_roofline), all ranks at once; best of 2"""
+            best = None
+            for _ in range(2):
+                barrier()
+                sec = max_over_ranks(eng.host_copy_roofline(n_e2e, h2d, d2h, src, dst))
+                best = sec if best is None else min(best, sec)
+            return world * n_e2e / best
+
+        h_dst = torch.empty(12 * n_e2e, dtype=torch.uint8, pin_memory=True).numpy()
+        roof = host_roofline(BYTES_IN_PER_TRIAL, BYTES_OUT_PER_TRIAL, hc, h_dst)
+        e2e["host_roofline"] = {"value": roof, "unit": UNIT, "frac": e2e["value"] / roof,
+                                "gb_per_s": roof * (BYTES_IN_PER_TRIAL + BYTES_OUT_PER_TRIAL) / 1e9,
+                                "what": "the same host pipeline with the kernel removed: 104 B/trial H2D + 12 B/trial D2H through "
+                                        "the same chunks, streams and staging buffers, all ranks concurrently, max over ranks"}
         # the same workload through the native-RNG host entry (MonteCarlo.create_data + run_sim fused on the device):
-        # nothing but the distribution goes up, the per-trial records come down
-        eng.run_rng(d, n_e2e, SEED, trial0, 64, out_err=he, out_ndet=hn)
-        barrier()
-        tw = time.perf_counter()
-        for _ in range(e2e_steps):
-            eng.run_rng(d, n_e2e, SEED, trial0, 64, out_err=he, out_ndet=hn)
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - tw], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e["native_rng"] = {"value": world * n_e2e * e2e_steps / float(dt.item()), "unit": UNIT,
+        # nothing but the distribution goes up, the per-trial records come down (12 B, or 9 B with n_det as uint8)
+        native = {}
+        h_nd8 = torch.empty(n_e2e, dtype=torch.uint8, pin_memory=True).numpy()
+        for label, compact, nd, nbytes in (("records_12B", False, hn, 12), ("records_9B", True, h_nd8, 9)):
+            eng.run_rng(d, n_e2e, SEED, trial0, 64, out_err=he, out_ndet=nd, compact=compact)
+            barrier()
+            tw = time.perf_counter()
+            for _ in range(e2e_steps):
+                eng.run_rng(d, n_e2e, SEED, trial0, 64, out_err=he, out_ndet=nd, compact=compact)
+            torch.cuda.synchronize()
+            v = world * n_e2e * e2e_steps / max_over_ranks(time.perf_counter() - tw)
+            roof = host_roofline(0, nbytes, None, h_dst)
+            native[label] = {"value": v, "unit": UNIT, "d2h_bytes_per_step": nbytes * n_e2e,
+                             "host_roofline": {"value": roof, "unit": UNIT, "frac": v / roof, "gb_per_s": roof * nbytes / 1e9}}
+        assert np.array_equal(np.minimum(hn, 255).astype(np.uint8), h_nd8)
+        e2e["native_rng"] = {"value": native["records_12B"]["value"], "unit": UNIT,
                              "h2d_bytes_per_step": ctypes.sizeof(_abi.Dist), "d2h_bytes_per_step": BYTES_OUT_PER_TRIAL * n_e2e,
-                             "api": "stmpm_run_rng_host (parameters sampled on the device, host records + statistics out)"}
+                             "api": "stmpm_run_rng_host (parameters sampled on the device, host records + statistics out)",
+                             **native}
     except RuntimeError as ex:                                                   # pinned allocation refused
         e2e = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
 
@@ -384,6 +414,7 @@ def main():
                     help="oracle-port trials per host process: default 262144 for the cpu_baseline leg (~13 s), 65536 per step "
                          "for --impl reference (~3 s per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--host-chunk", type=int, default=0, help="tuning sweep: trials per stage of the host pipelines (0 = 2^22)")
     ap.add_argument("--window", type=int, default=0, help="tuning sweep: CTA sort window in trials (0 = default)")
     ap.add_argument("--key-radius-deg", type=float, default=-1.0, help="tuning sweep: work-key disc radius (<0 = default)")
     args = ap.parse_args()

@@ -164,6 +164,19 @@ int stmpm_run_rng_host(stmpm_t* h, int precision, int64_t n_segments, int64_t tr
                        int64_t trial0, const stmpm_dist* dists_host, double* err_arcsec_host, int32_t* n_det_host,
                        double* stats_host);
 
+/* stmpm_run_rng_host with compact records: n_det as uint8 saturated at 255 (9 bytes per trial instead of 12 come back over
+ * PCIe; the default sensor detects ~20 stars per trial, MAX_MAGNITUDE = 20 ~60). */
+int stmpm_run_rng_host_compact(stmpm_t* h, int precision, int64_t n_segments, int64_t trials_per_segment, uint64_t seed,
+                               int64_t trial0, const stmpm_dist* dists_host, double* err_arcsec_host, uint8_t* n_det_u8_host,
+                               double* stats_host);
+/* Trials per stage of the host pipelines (0 = default 2^22; staging buffers are re-allocated on the next host call). */
+int stmpm_set_host_pipeline(stmpm_t* h, int64_t chunk_trials);
+/* Host-side roofline of the host-buffer entry points: n trials' worth of bytes through the SAME chunking, streams and
+ * staging buffers, copies only, no kernel.  src_host: n * h2d_bytes_per_trial bytes (pinned), dst_host:
+ * n * d2h_bytes_per_trial bytes.  seconds: wall time of the pipeline.  (bench.py reports e2e against this.) */
+int stmpm_host_copy_roofline(stmpm_t* h, int64_t n, int32_t h2d_bytes_per_trial, int32_t d2h_bytes_per_trial,
+                             const void* src_host, void* dst_host, double* seconds);
+
 /* MonteCarlo.run_sim's convergence loop on the device (monte_carlo.py:45-76): batches of `batch`
  * native-RNG trials (global trial indices trial0 + k*batch + i) until the successful rows number at least min_rows AND
  * |prev - sigma_hat| / prev <= tol (sigma_hat = std(ddof=1)/sqrt(1-2/pi) over all successful trials so far, prev starts

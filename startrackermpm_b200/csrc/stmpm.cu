@@ -9,6 +9,7 @@
 #include "stmpm_device.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -52,6 +53,7 @@ struct KArgs {
     double* stats;
     long long stats_len;
     unsigned long long* counters;   // INSTR only: [visits, mag_pass, survivors, detected]
+    uint8_t* ndet8;                 // optional compact record: detected stars saturated at 255 (9-byte records with err)
     const int* cancel;              // optional: a non-zero word makes the launch a no-op (on-device MonteCarlo stop rule)
 };
 
@@ -613,6 +615,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                     if (INSTR == 1) ins[3] += (unsigned long long)n_det;
                     if (a.err) a.err[rec] = err;
                     if (a.ndet) a.ndet[rec] = n_det;
+                    if (a.ndet8) a.ndet8[rec] = (uint8_t)min(n_det, 255);
                     if (INSTR == 2 && a.maxmag) a.maxmag[rec] = mag_faintest;
                     if (want_stats) {
                         acc_ndet += (unsigned long long)n_det;
@@ -924,6 +927,8 @@ struct DeviceGuard {
     DeviceGuard& operator=(const DeviceGuard&) = delete;
 };
 
+static constexpr long long HOST_CHUNK = 1LL << 22;   // default trials per stage of the host pipelines (stmpm_set_host_pipeline)
+
 struct stmpm_handle {
     int device = 0;
     cudaDeviceProp prop{};
@@ -960,6 +965,7 @@ struct stmpm_handle {
     // tuning (stmpm_set_tuning): 0 / negative = the measured defaults
     int tune_window = 0;
     double tune_key_radius_deg = -1.0;
+    long long host_chunk = HOST_CHUNK;    // trials per stage of the host pipelines
 };
 
 // Tables of box_muller_tab (stmpm_device.cuh), computed with the host libm.
@@ -1216,6 +1222,17 @@ extern "C" int stmpm_set_tuning(stmpm_t* h, int32_t window, double key_radius_de
     return rebuild_lists(h);
 }
 
+extern "C" int stmpm_set_host_pipeline(stmpm_t* h, int64_t chunk_trials) {
+    if (!h) return fail(STMPM_E_ARG, "stmpm_set_host_pipeline: null handle");
+    if (chunk_trials != 0 && (chunk_trials < 1024 || chunk_trials > (1LL << 28)))
+        return fail(STMPM_E_ARG, "stmpm_set_host_pipeline: chunk_trials must be 0 (default 2^22) or in [1024, 2^28]");
+    DeviceGuard guard(h->device);
+    for (int i = 0; i < stmpm_handle::NBUF; ++i) CK(cudaStreamSynchronize(h->streams[i]));
+    h->host_chunk = chunk_trials ? chunk_trials : HOST_CHUNK;
+    free_stage(h);                                       // re-allocated at the new size by the next host call
+    return 0;
+}
+
 extern "C" int stmpm_stats_len(int32_t hist_log2_sub, int64_t* n) {
     if (!n) return fail(STMPM_E_ARG, "stmpm_stats_len: null");
     if (hist_log2_sub < 4 || hist_log2_sub > 8) return fail(STMPM_E_ARG, "hist_log2_sub must be in [4, 8]");
@@ -1435,7 +1452,6 @@ static int ensure_stats(stmpm_handle* h, long long n_doubles) {
     return 0;
 }
 
-static constexpr long long HOST_CHUNK = 1LL << 22;   // trials per pipeline stage
 
 extern "C" int stmpm_run_presampled_host(stmpm_t* h, int precision, int64_t n, uint64_t seed, int64_t trial0,
                                          const double* const* cols, double* err, int32_t* ndet, double* stats) {
@@ -1451,7 +1467,7 @@ extern "C" int stmpm_run_presampled_host_ex(stmpm_t* h, int precision, int64_t n
     for (int i = 0; i < STMPM_NCOLS; ++i) if (!cols[i]) return fail(STMPM_E_ARG, "null column pointer");
     if (n == 0) return 0;
     DeviceGuard guard(h->device);
-    const long long chunk = std::min<long long>(HOST_CHUNK, n);
+    const long long chunk = std::min<long long>(h->host_chunk, n);
     if (int rc = ensure_stage(h, chunk, true)) return rc;
     const long long slen = probe.stats_len;
     if (stats) {
@@ -1489,8 +1505,8 @@ extern "C" int stmpm_run_presampled_host_ex(stmpm_t* h, int precision, int64_t n
     return 0;
 }
 
-extern "C" int stmpm_run_rng_host(stmpm_t* h, int precision, int64_t n_segments, int64_t tps, uint64_t seed,
-                                  int64_t trial0, const stmpm_dist* dists, double* err, int32_t* ndet, double* stats) {
+static int run_rng_host_impl(stmpm_t* h, int precision, int64_t n_segments, int64_t tps, uint64_t seed, int64_t trial0,
+                             const stmpm_dist* dists, double* err, void* ndet, bool compact, double* stats) {
     KArgs probe;
     if (int rc = fill_common(h, probe, precision)) return rc;
     if (n_segments < 0 || tps < 0 || !dists) return fail(STMPM_E_ARG, "stmpm_run_rng_host: bad arguments");
@@ -1506,27 +1522,81 @@ extern "C" int stmpm_run_rng_host(stmpm_t* h, int precision, int64_t n_segments,
     if (!err) {   // stats only: one launch over all segments
         if (int rc = stmpm_trials_rng(h, precision, n_segments, tps, seed, trial0, dists, nullptr, nullptr,
                                       stats ? h->stage_stats : nullptr, s0)) return rc;
-    } else {      // records: per segment, chunked + double-buffered D2H
-        const long long chunk = std::min<long long>(HOST_CHUNK, tps);
+    } else {      // records: per segment, chunked + multi-buffered D2H
+        const long long chunk = std::min<long long>(h->host_chunk, tps);
         if (int rc = ensure_stage(h, chunk, false)) return rc;
         CK(cudaStreamSynchronize(s0));
+        const size_t nd_bytes = compact ? 1 : sizeof(int);
         int k = 0;
         for (long long s = 0; s < n_segments; ++s) {
             for (long long off = 0; off < tps; off += chunk, ++k) {
                 const int b = k % stmpm_handle::NBUF;
                 const long long m = std::min<long long>(chunk, tps - off);
                 cudaStream_t st = h->streams[b];
-                if (int rc = stmpm_trials_rng(h, precision, 1, m, seed, trial0 + s * tps + off, dists + s,
-                                              h->stage_err[b], h->stage_ndet[b],
-                                              stats ? h->stage_stats + s * slen : nullptr, st)) return rc;
+                KArgs a;
+                if (int rc = fill_common(h, a, precision)) return rc;
+                to_dev_dist(dists[s], a.dist0);
+                a.n_segments = 1; a.trials_per_segment = m; a.trial0 = trial0 + s * tps + off;
+                a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
+                a.err = h->stage_err[b];
+                if (compact) a.ndet8 = reinterpret_cast<uint8_t*>(h->stage_ndet[b]); else a.ndet = h->stage_ndet[b];
+                a.stats = stats ? h->stage_stats + s * slen : nullptr;
+                const int rc = precision == 64 ? launch_trials<1, 64>(h, a, st) : launch_trials<1, 32>(h, a, st);
+                if (rc) return rc;
                 CK(cudaMemcpyAsync(err + s * tps + off, h->stage_err[b], sizeof(double) * m, cudaMemcpyDeviceToHost, st));
-                CK(cudaMemcpyAsync(ndet + s * tps + off, h->stage_ndet[b], sizeof(int) * m, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(static_cast<char*>(ndet) + (size_t)(s * tps + off) * nd_bytes, h->stage_ndet[b], nd_bytes * m,
+                                   cudaMemcpyDeviceToHost, st));
             }
         }
     }
     for (int i = 0; i < stmpm_handle::NBUF; ++i) CK(cudaStreamSynchronize(h->streams[i]));
     if (stats) CK(cudaMemcpy(stats, h->stage_stats, sizeof(double) * slen * n_segments, cudaMemcpyDeviceToHost));
     return 0;
+}
+
+extern "C" int stmpm_run_rng_host(stmpm_t* h, int precision, int64_t n_segments, int64_t tps, uint64_t seed,
+                                  int64_t trial0, const stmpm_dist* dists, double* err, int32_t* ndet, double* stats) {
+    return run_rng_host_impl(h, precision, n_segments, tps, seed, trial0, dists, err, ndet, false, stats);
+}
+
+extern "C" int stmpm_run_rng_host_compact(stmpm_t* h, int precision, int64_t n_segments, int64_t tps, uint64_t seed,
+                                          int64_t trial0, const stmpm_dist* dists, double* err, uint8_t* ndet_u8, double* stats) {
+    return run_rng_host_impl(h, precision, n_segments, tps, seed, trial0, dists, err, ndet_u8, true, stats);
+}
+
+// Host-side roofline of the host-buffer entry points: the SAME chunking, streams and staging buffers, copies only — no
+// kernel.  h2d_bytes_per_trial / d2h_bytes_per_trial: 104 / 12 (pre-sampled), 0 / 12 or 0 / 9 (native RNG, compact).
+extern "C" int stmpm_host_copy_roofline(stmpm_t* h, int64_t n, int32_t h2d_bytes_per_trial, int32_t d2h_bytes_per_trial,
+                                        const void* src_host, void* dst_host, double* seconds) {
+    if (!h || n <= 0 || !seconds || h2d_bytes_per_trial < 0 || h2d_bytes_per_trial > 8 * STMPM_NCOLS || d2h_bytes_per_trial < 0 ||
+        d2h_bytes_per_trial > 12 || (h2d_bytes_per_trial && !src_host) || (d2h_bytes_per_trial && !dst_host))
+        return fail(STMPM_E_ARG, "stmpm_host_copy_roofline: bad arguments");
+    DeviceGuard guard(h->device);
+    const long long chunk = std::min<long long>(h->host_chunk, n);
+    if (int rc = ensure_stage(h, chunk, h2d_bytes_per_trial > 0)) return rc;
+    for (int i = 0; i < stmpm_handle::NBUF; ++i) CK(cudaStreamSynchronize(h->streams[i]));
+    const int rc = [&]() -> int {
+        const auto t0 = std::chrono::steady_clock::now();
+        int k = 0;
+        for (long long off = 0; off < n; off += chunk, ++k) {
+            const int b = k % stmpm_handle::NBUF;
+            const long long m = std::min<long long>(chunk, n - off);
+            cudaStream_t st = h->streams[b];
+            if (h2d_bytes_per_trial)
+                CK(cudaMemcpyAsync(h->stage_cols[b], static_cast<const char*>(src_host) + (size_t)off * h2d_bytes_per_trial,
+                                   (size_t)m * h2d_bytes_per_trial, cudaMemcpyHostToDevice, st));
+            if (d2h_bytes_per_trial) {
+                const size_t b8 = std::min<size_t>(8, d2h_bytes_per_trial), b4 = d2h_bytes_per_trial - b8;
+                CK(cudaMemcpyAsync(static_cast<char*>(dst_host) + (size_t)off * b8, h->stage_err[b], (size_t)m * b8, cudaMemcpyDeviceToHost, st));
+                if (b4) CK(cudaMemcpyAsync(static_cast<char*>(dst_host) + (size_t)n * b8 + (size_t)off * b4, h->stage_ndet[b], (size_t)m * b4,
+                                           cudaMemcpyDeviceToHost, st));
+            }
+        }
+        for (int i = 0; i < stmpm_handle::NBUF; ++i) CK(cudaStreamSynchronize(h->streams[i]));
+        *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        return 0;
+    }();
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------ misc

@@ -205,25 +205,38 @@ class TrialEngine:
         return arr, len(dists)
 
     def run_rng(self, dists, trials_per_segment: int, seed: int, trial0: int = 0, precision: int = 64,
-                records: bool = False, out_err=None, out_ndet=None):
+                records: bool = False, out_err=None, out_ndet=None, compact: bool = False):
         """HOST results.  Returns stats [n_segments, stats_len] (and err, n_det [n_segments*trials_per_segment] if records).
-        out_err / out_ndet: caller-owned (e.g. pinned) record buffers; giving them implies records."""
+        out_err / out_ndet: caller-owned (e.g. pinned) record buffers; giving them implies records.
+        compact=True: n_det comes back as uint8 saturated at 255 — 9 bytes per trial over PCIe instead of 12."""
         arr, ns = self._dist_array(dists)
         n = ns * int(trials_per_segment)
         if (out_err is None) != (out_ndet is None):
             raise ValueError("out_err and out_ndet go together")
+        nd_type = np.uint8 if compact else np.int32
         if out_err is not None:
-            if out_err.dtype != np.float64 or out_ndet.dtype != np.int32 or out_err.size != n or out_ndet.size != n \
-                    or not out_err.flags.c_contiguous or not out_ndet.flags.c_contiguous:
-                raise ValueError(f"out_err must be contiguous float64[{n}], out_ndet contiguous int32[{n}]")
+            _check_host_out(out_err, np.float64, n, "out_err")
+            _check_host_out(out_ndet, nd_type, n, "out_ndet")
             records = True
         err = out_err if out_err is not None else (np.empty(n, dtype=np.float64) if records else None)
-        ndet = out_ndet if out_ndet is not None else (np.empty(n, dtype=np.int32) if records else None)
+        ndet = out_ndet if out_ndet is not None else (np.empty(n, dtype=nd_type) if records else None)
         stats = np.zeros((ns, self.stats_len), dtype=np.float64)
-        _abi.check(self._lib.stmpm_run_rng_host(self._h, int(precision), ns, int(trials_per_segment),
-                                                int(seed) & (2**64 - 1), int(trial0), arr, _ptr(err), _ptr(ndet),
-                                                _ptr(stats)))
+        fn = self._lib.stmpm_run_rng_host_compact if compact else self._lib.stmpm_run_rng_host
+        _abi.check(fn(self._h, int(precision), ns, int(trials_per_segment), int(seed) & (2**64 - 1), int(trial0), arr,
+                      _ptr(err), _ptr(ndet), _ptr(stats)))
         return (stats, err, ndet) if records else stats
+
+    def set_host_pipeline(self, chunk_trials: int = 0) -> None:
+        """Trials per stage of the host pipelines (H2D / kernel / D2H overlap); 0 = default 2^22."""
+        _abi.check(self._lib.stmpm_set_host_pipeline(self._h, int(chunk_trials)))
+
+    def host_copy_roofline(self, n: int, h2d_bytes_per_trial: int, d2h_bytes_per_trial: int, src=None, dst=None) -> float:
+        """Seconds the host pipeline needs for the COPIES alone (same chunking, streams, staging buffers; no kernel):
+        the host-side roofline bench.py quotes e2e against.  src / dst: pinned host arrays of n * bytes_per_trial bytes."""
+        sec = C.c_double()
+        _abi.check(self._lib.stmpm_host_copy_roofline(self._h, int(n), int(h2d_bytes_per_trial), int(d2h_bytes_per_trial),
+                                                      _ptr(src), _ptr(dst), C.byref(sec)))
+        return float(sec.value)
 
     def run_rng_device(self, dists, trials_per_segment: int, stats, err=None, ndet=None, *, seed: int, trial0: int = 0,
                        precision: int = 64, stream: int = 0) -> None:

@@ -346,3 +346,23 @@ def test_records_do_not_depend_on_the_sort_window(engine):
             ek, dk = e3[k * 70_001:(k + 1) * 70_001], d3[k * 70_001:(k + 1) * 70_001]
             assert s3[k, 0] == (ek >= 0).sum() and s3[k, 1] == (ek < 0).sum() and s3[k, 4] == dk.sum()
     engine.set_tuning(window=0)
+
+
+def test_compact_records_and_host_pipeline_knob(engine):
+    """stmpm_run_rng_host_compact: n_det as uint8 (9-byte records) — same errors, same counts (saturated at 255); the
+    host-pipeline chunk size never changes a record; the copy-only roofline call moves the bytes it says."""
+    dist = make_dist(dict(BASIC_MEAN, MAX_MAGNITUDE=20.0), BASIC_SIGMA, THERMAL_COEF)       # ~60 detections per trial
+    n = 70_001
+    st, e, d = engine.run_rng(dist, n, 3, 11, records=True)
+    for chunk in (4096, 0):
+        engine.set_host_pipeline(chunk)
+        st8, e8, d8 = engine.run_rng(dist, n, 3, 11, records=True, compact=True)
+        assert d8.dtype == np.uint8 and np.array_equal(e8, e) and np.array_equal(d8, np.minimum(d, 255).astype(np.uint8))
+        assert np.array_equal(st8[0, :2], st[0, :2]) and np.array_equal(st8[0, 4:], st[0, 4:])
+    wide = make_dist(dict(BASIC_MEAN, MAX_MAGNITUDE=20.0, FOCAL_LENGTH=700.0), ZERO_SIGMA, 0.0)   # > 255 stars in the field
+    _, _, dw = engine.run_rng(wide, 2000, 3, 0, records=True)
+    _, _, dw8 = engine.run_rng(wide, 2000, 3, 0, records=True, compact=True)
+    assert dw.max() > 255 and dw8.max() == 255 and np.array_equal(dw8, np.minimum(dw, 255).astype(np.uint8))
+    src = torch.empty(104 * n, dtype=torch.uint8, pin_memory=True).numpy()
+    dst = torch.empty(12 * n, dtype=torch.uint8, pin_memory=True).numpy()
+    assert engine.host_copy_roofline(n, 104, 12, src, dst) > 0 and engine.host_copy_roofline(n, 0, 9, None, dst) > 0
