@@ -37,6 +37,16 @@ BASIC_MEAN = dict(FOCAL_LENGTH=3500.0, F_ARR_EPS_X=0.0, F_ARR_EPS_Y=0.0, F_ARR_E
                   F_ARR_THETA=0.0, F_ARR_PSI=0.0, BASE_DEV_X=0.0, BASE_DEV_Y=0.0, MAX_MAGNITUDE=6.0, D_TEMP=0.0)
 BASIC_SIGMA = dict(FOCAL_LENGTH=2.0, F_ARR_EPS_X=1.0, F_ARR_EPS_Y=1.0, F_ARR_EPS_Z=1.0, F_ARR_PHI=0.05,
                    F_ARR_THETA=0.05, F_ARR_PSI=0.05, BASE_DEV_X=0.1, BASE_DEV_Y=0.1, MAX_MAGNITUDE=0.25, D_TEMP=5.0)
+# --workload: "default" = BASELINE configs[1]; "all_visible" = the reference's sensitivity-sweep regime, where
+# Sense.create_data sets MAX_MAGNITUDE = 20 for every row (sensitivity.py:112): every star in the field is detected (~60)
+WORKLOADS = {
+    "default": (BASIC_MEAN, BASIC_SIGMA,
+                "configs[1]: default sensor config (cameraBasic + simpleCentroid), pre-sampled fp64 parameter columns -> "
+                "per-trial error records + streaming statistics"),
+    "all_visible": (dict(BASIC_MEAN, MAX_MAGNITUDE=20.0), dict(BASIC_SIGMA, MAX_MAGNITUDE=0.0),
+                    "star-rich fields: default sensor config with MAX_MAGNITUDE = 20 on every row (sensitivity.py:112, the "
+                    "reference's sweep regime, ~60 detections per trial), pre-sampled fp64 columns -> records + statistics"),
+}
 BYTES_IN_PER_TRIAL = 13 * 8          # pre-sampled columns
 BYTES_OUT_PER_TRIAL = 8 + 4          # error f64 + n_det i32
 
@@ -64,7 +74,8 @@ def _cpu_worker(args):
         xyz, mag = load_catalog()
         grid = trial.candidate_grid(xyz)
         _CPU_CAT = (xyz, mag, grid)
-    cols = trial.sample_params(BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF, SEED, t0, n)
+    mean, sigma, _ = WORKLOADS[os.environ.get("STMPM_BENCH_WORKLOAD", "default")]
+    cols = trial.sample_params(mean, sigma, THERMAL_COEF, SEED, t0, n)
     e, d = trial.run_trials(cols, xyz, mag, F_IDEAL, SEED, t0, grid=grid)
     return int((e >= 0).sum()), float(e[e >= 0].sum())
 
@@ -142,7 +153,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(n, args.gpus),
+        "config": workload_config(n, args.gpus, args.workload),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "c1_faithful": cpu_c1_faithful(),
                          "c2_vectorised_1core": {"value": c2, "unit": UNIT, "cores": 1, "sample": f"{max(20_000, per_core)} trials, {dt2:.1f} s"},
@@ -156,9 +167,8 @@ def run_reference_arm(args):
     return 0
 
 
-def workload_config(trials_per_gpu_step: int, n_gpus: int):
-    return {"workload": "configs[1]: default sensor config (cameraBasic + simpleCentroid), pre-sampled fp64 parameter "
-                        "columns -> per-trial error records + streaming statistics",
+def workload_config(trials_per_gpu_step: int, n_gpus: int, workload: str = "default"):
+    return {"workload": WORKLOADS[workload][2],
             "trials_per_gpu_per_step": int(trials_per_gpu_step), "catalog": "synthetic 9110 stars, seed 20231105",
             "f_ideal_px": F_IDEAL, "sensor_px": 1024, "precision": 64, "sharding": f"trial-index ranges x{n_gpus}",
             "l2_policy": "inputs (10.4 GB/step at 1e8 trials) larger than L2; no flush needed"}
@@ -236,11 +246,11 @@ def run_ours(args):
 
     n = int(args.trials)
     eng = TrialEngine(local, f_ideal=F_IDEAL)
-    if args.window or args.key_radius_deg >= 0:
-        eng.set_tuning(args.window, args.key_radius_deg)
+    if args.window or args.key_radius_deg >= 0 or args.no_stage:
+        eng.set_tuning(args.window, args.key_radius_deg, not args.no_stage)
     if args.host_chunk:
         eng.set_host_pipeline(args.host_chunk)
-    d = make_dist(BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF)
+    d = make_dist(WORKLOADS[args.workload][0], WORKLOADS[args.workload][1], THERMAL_COEF)
     trial0 = rank * n                                      # weak scaling: every rank its own global trial-index range
     cols = torch.empty((13, n), dtype=torch.float64, device="cuda")
     err = torch.empty(n, dtype=torch.float64, device="cuda")
@@ -376,7 +386,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(n, world),
+            "config": workload_config(n, world, args.workload),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {
                 "bound": "fp64", "kernel": "trials_kernel<presampled, fp64>",
@@ -414,10 +424,14 @@ def main():
                     help="oracle-port trials per host process: default 262144 for the cpu_baseline leg (~13 s), 65536 per step "
                          "for --impl reference (~3 s per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="default", choices=sorted(WORKLOADS),
+                    help="default = BASELINE configs[1]; all_visible = MAX_MAGNITUDE 20 (sensitivity.py:112), ~60 stars per trial")
     ap.add_argument("--host-chunk", type=int, default=0, help="tuning sweep: trials per stage of the host pipelines (0 = 2^22)")
+    ap.add_argument("--no-stage", action="store_true", help="tuning sweep: gather the pre-sampled columns (round 1) instead of staging them")
     ap.add_argument("--window", type=int, default=0, help="tuning sweep: CTA sort window in trials (0 = default)")
     ap.add_argument("--key-radius-deg", type=float, default=-1.0, help="tuning sweep: work-key disc radius (<0 = default)")
     args = ap.parse_args()
+    os.environ["STMPM_BENCH_WORKLOAD"] = args.workload          # the spawned CPU-arm workers read it
     if args.cpu_trials_per_core is None:
         args.cpu_trials_per_core = 65536 if args.impl == "reference" else 262144
     if args.impl == "reference":

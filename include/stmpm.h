@@ -113,8 +113,10 @@ int stmpm_set_sensor(stmpm_t* h, const stmpm_sensor_cfg* cfg);
 /* Performance knobs of the trial kernel; results never depend on them (tests/test_gpu_parity.py checks bit-identity).
  * window: trials per CTA sort window (multiple of 32, <= 2048; 0 = the measured default per mode).  key_radius_deg: radius
  * of the work-key disc (< 0 = default, 0 = whole candidate list); changing it synchronises the device and rebuilds the
- * key table.  Not to be called while launches on this handle are in flight. */
-int stmpm_set_tuning(stmpm_t* h, int32_t window, double key_radius_deg);
+ * key table.  stage_columns: non-zero (default) = pre-sampled launches re-write each sort window's columns in key order to
+ * an L2-resident scratch (allocated per launch in stream order) so that warps read them coalesced; 0 = gather them.
+ * Not to be called while launches on this handle are in flight. */
+int stmpm_set_tuning(stmpm_t* h, int32_t window, double key_radius_deg, int32_t stage_columns);
 
 /* Packed statistics buffer (MODEL.md §9): STMPM_STATS_HEAD doubles then 34 * 2^hist_log2_sub histogram bins; every entry
  * but x_max is a sum, so ranks merge with one allreduce(sum).  Host-only helpers (no GPU needed). */
@@ -214,6 +216,8 @@ int stmpm_work_counters(stmpm_t* h, int64_t n, uint64_t seed, int64_t trial0, co
 /* Diagnostic, host-only (no GPU): the table-based Box-Muller of the star loop (MODEL.md §5), compiled for the host from
  * the same source the kernels use, so its accuracy can be checked against libm without a GPU. */
 int stmpm_debug_box_muller(const uint32_t* wa, const uint32_t* wb, int64_t n, double* z1, double* z2);
+/* Same for fp32 mode's Box-Muller (host build: log2f / sqrtf stand in for the MUFU approximations). */
+int stmpm_debug_box_muller_f32(const uint32_t* wa, const uint32_t* wb, int64_t n, float* z1, float* z2);
 /* Number of kernels this library has launched on this handle (bench.py's gpu_launches claim). */
 int stmpm_launch_count(const stmpm_t* h, int64_t* n);
 

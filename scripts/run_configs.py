@@ -14,6 +14,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--scale", type=float, default=1.0, help="fraction of each config's trial count")
 ap.add_argument("--configs", type=int, nargs="*", default=[3, 4, 5])
 ap.add_argument("--precision", type=int, default=64)
+ap.add_argument("--all-visible", action="store_true",
+                help="config 3 with the reference sweep's own convention MAX_MAGNITUDE = 20 on every row (sensitivity.py:112)")
 args = ap.parse_args()
 world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", 1), ("RANK", 0), ("LOCAL_RANK", 0)))
 torch.cuda.set_device(local)
@@ -32,13 +34,15 @@ if 3 in args.configs:      # sensitivity grid 64 x 64 x 16, 1e6 trials per point
     tps = max(1000, int(1e6 * args.scale))
     ea, pa, da = studies.grid_axes(BASIC_SIGMA["F_ARR_EPS_X"], BASIC_SIGMA["F_ARR_PHI"], BASIC_SIGMA["BASE_DEV_X"])
     seg = list(range(*sharding.shard_range(64 * 64 * 16, rank, world)))   # contiguous block: 4096 points per launch
+    mean3, sig3 = (dict(BASIC_MEAN, MAX_MAGNITUDE=20.0), dict(BASIC_SIGMA, MAX_MAGNITUDE=0.0)) if args.all_visible else (BASIC_MEAN, BASIC_SIGMA)
     sync(); t = time.perf_counter()
-    st = studies.sensitivity_grid(eng, BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF, ea, pa, da, tps, seed=3,
+    st = studies.sensitivity_grid(eng, mean3, sig3, THERMAL_COEF, ea, pa, da, tps, seed=3,
                                   precision=args.precision, segments=seg)
     sync(); dt = time.perf_counter() - t
     s0, s1 = summarize(st[0], 5), summarize(st[-1], 5)
     emit(config=3, n_gpus=world, grid=[64, 64, 16], trials_per_point=tps, trials=65536 * tps, seconds=dt,
-         trials_per_sec=65536 * tps / dt, first_point_mean=s0["mean"], last_point_mean=s1["mean"], precision=args.precision)
+         trials_per_sec=65536 * tps / dt, first_point_mean=s0["mean"], last_point_mean=s1["mean"], precision=args.precision,
+         max_magnitude=20.0 if args.all_visible else BASIC_MEAN["MAX_MAGNITUDE"], mean_ndet=s0["mean_ndet"])
     eng.close()
 if 4 in args.configs:      # LEO lifetime: 60 monthly steps, 1e7 trials per step
     eng = TrialEngine(local, f_ideal=F_IDEAL)

@@ -53,6 +53,7 @@ struct KArgs {
     double* stats;
     long long stats_len;
     unsigned long long* counters;   // INSTR only: [visits, mag_pass, survivors, detected]
+    double* stage;                  // MODE 0: per-CTA scratch [gridDim][2][STMPM_NCOLS][WIN_MAX] — the window's columns in key order
     uint8_t* ndet8;                 // optional compact record: detected stars saturated at 255 (9-byte records with err)
     const int* cancel;              // optional: a non-zero word makes the launch a no-op (on-device MonteCarlo stop rule)
 };
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
 
     int build_w = (warp == 0 && n_windows > 0) ? 0 : -1;   // pending window to build (warp 0 builds the first one)
     bool have_group = false;
-    int grp_w = 0, grp_r = 0;
+    int grp_w = 0, grp_r = 0, grp_q = 0;
     for (;;) {
         if (build_w >= 0) {
             // ================= key pass + counting sort of window build_w into permutation buffer build_w & 1
@@ -386,7 +387,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                     // pull the round's other ten columns into L2 (one 32-byte sector = 4 trials per lane): the groups gather
                     // them in key order, 32 scattered sectors per load — as L2 hits those gathers hold their L1 miss slots
                     // a quarter as long as DRAM misses do, and the LSU pipe they share with shared memory stays fluid
-                    if (r0 + 4 * lane < nw) {
+                    if (r0 + 4 * lane < nw) {          // (with staging too: the copy below then reads L2 hits)
 #pragma unroll
                         for (int cI = 2; cI < 12; ++cI) prefetch_l2(a.cols[cI] + rec0 + r0 + 4 * lane);
                     }
@@ -452,10 +453,32 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                 }
             }
             __syncwarp();
-            for (int r = lane; r < win; r += 32) {
-                const int key = w_key[r];
-                const unsigned int old = atomicAdd(w_hist + (key >> 1), 1u << (16 * (key & 1)));
-                w_perm[(old >> (16 * (key & 1))) & 0xffffu] = (uint16_t)r;
+            if (MODE == 0 && a.stage != nullptr) {
+                // sorted parameter staging: the window's 13 columns are re-written in KEY ORDER to an L2-resident scratch
+                // (coalesced column reads, rank-scattered 8-byte writes, by this one warp), so that the 32 lanes of a group
+                // later read 13 x 256 contiguous bytes instead of gathering 13 x 32 scattered words — which is what kept
+                // pre-sampled windows at 256 trials in round 1 (the gathers saturated the LSU pipe at wider windows)
+                double* sg = a.stage + ((size_t)blockIdx.x * 2 + (size_t)(bw & 1)) * (size_t)(STMPM_NCOLS * WIN_MAX);
+                for (int r = lane; r < win; r += 32) {
+                    const int key = w_key[r];
+                    const unsigned int old = atomicAdd(w_hist + (key >> 1), 1u << (16 * (key & 1)));
+                    const unsigned int rank = (old >> (16 * (key & 1))) & 0xffffu;
+                    w_perm[rank] = (uint16_t)r;
+                    if (r < nw) {
+                        double v[STMPM_NCOLS];
+#pragma unroll
+                        for (int cI = 0; cI < STMPM_NCOLS; ++cI) v[cI] = __ldcs(a.cols[cI] + rec0 + r);
+#pragma unroll
+                        for (int cI = 0; cI < STMPM_NCOLS; ++cI) __stcg(sg + (size_t)cI * WIN_MAX + rank, v[cI]);
+                    }
+                }
+                __threadfence();
+            } else {
+                for (int r = lane; r < win; r += 32) {
+                    const int key = w_key[r];
+                    const unsigned int old = atomicAdd(w_hist + (key >> 1), 1u << (16 * (key & 1)));
+                    w_perm[(old >> (16 * (key & 1))) & 0xffffu] = (uint16_t)r;
+                }
             }
             __threadfence_block();
             __syncwarp();
@@ -474,10 +497,13 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                 while (v_sched[1] <= grp_w) { __nanosleep(64); if (++spins > (1u << 26)) __trap(); }
             }
             __threadfence_block();
-            grp_r = s_perm[(grp_w & 1) * WIN_MAX + gi * 32 + lane];
+            grp_q = gi * 32 + lane;                                   // position in key order
+            grp_r = s_perm[(grp_w & 1) * WIN_MAX + grp_q];
             __threadfence_block();                        // the entry is in a register before the slot is reported free
             __syncwarp();
-            if (lane == 0) atomicAdd(s_sched + 2 + (grp_w & 1), 1);
+            // (with sorted parameter staging the buffer also holds the group's staged columns: it is reported free only
+            // after those are in registers, below)
+            if (!(MODE == 0 && a.stage != nullptr) && lane == 0) atomicAdd(s_sched + 2 + (grp_w & 1), 1);
             have_group = true;
             if (gi == 0 && grp_w + 1 < n_windows) { build_w = grp_w + 1; continue; }   // build the next window first
         }
@@ -503,13 +529,33 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
             {
                 const int r = grp_r;
                 const bool valid = r < nw;
-                if (!__any_sync(0xffffffffu, valid)) continue;
+                if (!__any_sync(0xffffffffu, valid)) {
+                    if (MODE == 0 && a.stage != nullptr && lane == 0) atomicAdd(s_sched + 2 + (grp_w & 1), 1);
+                    continue;
+                }
                 const long long rec = rec0 + r;
                 const unsigned long long gidx = (unsigned long long)(a.trial0 + rec);
                 const uint32_t t_lo = (uint32_t)gidx, t_hi = (uint32_t)(gidx >> 32);
 
                 TrialParams p;
-                if (MODE == 0) {
+                if (MODE == 0 && a.stage != nullptr) {
+                    if (valid) {                                // coalesced: lane q reads word q of each staged column
+                        const double* sg = a.stage + ((size_t)blockIdx.x * 2 + (size_t)(grp_w & 1)) * (size_t)(STMPM_NCOLS * WIN_MAX) + grp_q;
+                        p.ra = __ldcg(sg);                      p.dec = __ldcg(sg + WIN_MAX);
+                        p.roll = __ldcg(sg + 2 * WIN_MAX);      p.f = __ldcg(sg + 3 * WIN_MAX);
+                        p.ex = __ldcg(sg + 4 * WIN_MAX);        p.ey = __ldcg(sg + 5 * WIN_MAX);
+                        p.ez = __ldcg(sg + 6 * WIN_MAX);        p.phi = __ldcg(sg + 7 * WIN_MAX);
+                        p.theta = __ldcg(sg + 8 * WIN_MAX);     p.psi = __ldcg(sg + 9 * WIN_MAX);
+                        p.devx = __ldcg(sg + 10 * WIN_MAX);     p.devy = __ldcg(sg + 11 * WIN_MAX);
+                        p.maxmag = __ldcg(sg + 12 * WIN_MAX);
+                    } else {
+                        p.ra = p.dec = p.roll = 0.0; p.f = 1000.0; p.ex = p.ey = p.ez = p.phi = p.theta = p.psi = 0.0;
+                        p.devx = p.devy = 0.0; p.maxmag = -100.0;
+                    }
+                    __threadfence_block();                      // the thirteen words are in registers: the buffer may be rebuilt
+                    __syncwarp();
+                    if (lane == 0) atomicAdd(s_sched + 2 + (grp_w & 1), 1);
+                } else if (MODE == 0) {
                     if (valid) {
                         // ld.global.cg: the 32 lanes gather from 32 different lines of the window; cached in L1 each of the 13
                         // loads would claim 32 of its ~220 lines at once and stall the LSU pipe (shared-memory loads queue
@@ -965,6 +1011,8 @@ struct stmpm_handle {
     // tuning (stmpm_set_tuning): 0 / negative = the measured defaults
     int tune_window = 0;
     double tune_key_radius_deg = -1.0;
+    int tune_stage = 1;                   // sorted parameter staging for pre-sampled launches (0 = round 1's gathers)
+    cudaMemPool_t pool = nullptr;         // stream-ordered per-launch storage (staging scratch, distribution arrays)
     long long host_chunk = HOST_CHUNK;    // trials per stage of the host pipelines
 };
 
@@ -980,6 +1028,11 @@ static void stmpm_host_tables(MathTables* t) {
         const double a = 2.0 * M_PI * (j + 0.5) / 1024.0;
         t->sc_tab[j][0] = std::sin(a);
         t->sc_tab[j][1] = std::cos(a);
+    }
+    for (int j = 0; j < 128; ++j) {
+        const double a = 2.0 * M_PI * (j + 0.5) / 128.0;
+        t->sc32[j][0] = (float)std::sin(a);
+        t->sc32[j][1] = (float)std::cos(a);
     }
 }
 
@@ -1103,6 +1156,15 @@ extern "C" int stmpm_create(stmpm_t** out, int device) {
         stmpm_host_tables(&mt);
         CK(cudaMalloc(&h->tables, sizeof(MathTables)));
         CK(cudaMemcpy(h->tables, &mt, sizeof(MathTables), cudaMemcpyHostToDevice));
+        // the handle's own stream-ordered pool: blocks freed in stream order are kept for the next launch, not returned to the OS
+        cudaMemPoolProps pp{};
+        pp.allocType = cudaMemAllocationTypePinned;
+        pp.handleTypes = cudaMemHandleTypeNone;
+        pp.location.type = cudaMemLocationTypeDevice;
+        pp.location.id = device;
+        CK(cudaMemPoolCreate(&h->pool, &pp));
+        unsigned long long keep = ~0ull;
+        CK(cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &keep));
         return 0;
     }();
     if (rc) { stmpm_destroy(h); return rc; }          // nothing leaks on a failed create
@@ -1127,6 +1189,7 @@ extern "C" int stmpm_destroy(stmpm_t* h) {
     cudaFree(h->lk_key);
     free_stage(h);
     for (int i = 0; i < stmpm_handle::NBUF; ++i) if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
+    if (h->pool) { cudaDeviceSynchronize(); cudaMemPoolDestroy(h->pool); }
     delete h;
     return 0;
 }
@@ -1210,8 +1273,9 @@ extern "C" int stmpm_set_sensor(stmpm_t* h, const stmpm_sensor_cfg* cfg) {
     return rebuild_lists(h);
 }
 
-extern "C" int stmpm_set_tuning(stmpm_t* h, int32_t window, double key_radius_deg) {
+extern "C" int stmpm_set_tuning(stmpm_t* h, int32_t window, double key_radius_deg, int32_t stage_columns) {
     if (!h) return fail(STMPM_E_ARG, "stmpm_set_tuning: null handle");
+    h->tune_stage = stage_columns != 0;
     if (window < 0 || window > WIN_MAX || window % 32) return fail(STMPM_E_ARG, "stmpm_set_tuning: window must be 0 (default) or a multiple of 32 up to 2048");
     const bool rebuild = key_radius_deg != h->tune_key_radius_deg;
     h->tune_window = window;
@@ -1310,7 +1374,9 @@ static int launch_trials(stmpm_handle* h, KArgs& a, cudaStream_t st) {
     // the window so that more CTAs have work.
     const long long tps = a.trials_per_segment;
     const long long total = tps * a.n_segments;
-    long long win = MODE == 0 ? WIN_PRESAMPLED : WIN_RNG;
+    // sorted parameter staging (pre-sampled mode): worth its scratch from a few windows per CTA on
+    const bool stage = MODE == 0 && h->tune_stage && total >= 4LL * WIN_STAGED * n_sm;
+    long long win = MODE == 0 ? (stage ? WIN_STAGED : WIN_PRESAMPLED) : WIN_RNG;
     if (h->tune_window > 0) win = std::max(32, std::min(WIN_MAX, h->tune_window / 32 * 32));   // stmpm_set_tuning
     const long long per_cta = (total + n_sm - 1) / n_sm;
     if (per_cta < win) win = std::max(32LL, (per_cta + 31) / 32 * 32);
@@ -1328,8 +1394,16 @@ static int launch_trials(stmpm_handle* h, KArgs& a, cudaStream_t st) {
     if (grid <= 0) return 0;
     if (rounds_per_part > 0x7fffffffLL || ((n_units + grid - 1) / grid) * rounds_per_part * (win / 32) > 0x7fffffffLL)
         return fail(STMPM_E_ARG, "launch too large: more than 2^31 trial groups per CTA (split the call)");
+    void* scratch = nullptr;
+    a.stage = nullptr;
+    if (stage) {   // [grid][2 buffers][13 columns][WIN_MAX] doubles, allocated and freed in stream order: concurrent launches never share it
+        CK(cudaMallocFromPoolAsync(&scratch, (size_t)grid * 2 * STMPM_NCOLS * WIN_MAX * sizeof(double), h->pool, st));
+        a.stage = static_cast<double*>(scratch);
+    }
     kern<<<grid, TPB, smem_bytes, st>>>(a);
-    CK(cudaGetLastError());
+    const cudaError_t le = cudaGetLastError();
+    if (scratch) cudaFreeAsync(scratch, st);
+    if (le != cudaSuccess) return fail((int)le, std::string("trials_kernel launch: ") + cudaGetErrorString(le));
     ++h->launches;
     return 0;
 }
@@ -1400,7 +1474,7 @@ extern "C" int stmpm_trials_rng(stmpm_t* h, int precision, int64_t n_segments, i
         // every call owns its distribution array: allocated, filled and freed in stream order on the caller's stream, so
         // concurrent multi-segment calls on different streams never share storage (the host array is pageable memory:
         // cudaMemcpyAsync has staged it before it returns, the caller may reuse it at once)
-        CK(cudaMallocAsync(&d_dists, sizeof(DistDev) * n_segments, (cudaStream_t)stream));
+        CK(cudaMallocFromPoolAsync(&d_dists, sizeof(DistDev) * n_segments, h->pool, (cudaStream_t)stream));
         cudaError_t e = cudaMemcpyAsync(d_dists, dists, sizeof(DistDev) * n_segments, cudaMemcpyHostToDevice, (cudaStream_t)stream);
         if (e != cudaSuccess) { cudaFreeAsync(d_dists, (cudaStream_t)stream); return fail((int)e, std::string("dists upload: ") + cudaGetErrorString(e)); }
         a.dists = d_dists;
@@ -1650,6 +1724,14 @@ extern "C" int stmpm_work_counters(stmpm_t* h, int64_t n, uint64_t seed, int64_t
     CK(cudaMemcpyAsync(c, h->counters, sizeof(c), cudaMemcpyDeviceToHost, h->streams[0]));
     CK(cudaStreamSynchronize(h->streams[0]));
     for (int i = 0; i < 4; ++i) per_trial4[i] = (double)c[i] / (double)n;
+    return 0;
+}
+
+extern "C" int stmpm_debug_box_muller_f32(const uint32_t* wa, const uint32_t* wb, int64_t n, float* z1, float* z2) {
+    if (!wa || !wb || !z1 || !z2 || n < 0) return fail(STMPM_E_ARG, "stmpm_debug_box_muller_f32: bad arguments");
+    MathTables mt;
+    stmpm_host_tables(&mt);
+    for (int64_t i = 0; i < n; ++i) box_muller_f32(TabPtr{&mt}, wa[i], wb[i], z1[i], z2[i]);
     return 0;
 }
 

@@ -10,7 +10,10 @@
 //                 -> phase B: exact per-star projection + Philox centroid noise + detection + B accumulation
 //                 -> QUEST Newton solve in the body frame + error angle.
 #pragma once
+#include <cmath>
+#include <cstddef>
 #include <cstdint>
+#include <cstring>
 #include <cuda_runtime.h>
 
 #if defined(__CUDACC__)
@@ -26,6 +29,7 @@ constexpr int LIST_CAP = 48;      // per-thread survivor list in shared memory (
 constexpr int WIN_MAX = 2048;     // largest CTA sort window (trials)
 constexpr int WIN_PRESAMPLED = 256;   // default window, pre-sampled columns: wider windows sort better but every column gather then
                                       // touches 32 different lines, and the LSU pipe (shared with shared memory) saturates
+constexpr int WIN_STAGED = 2048;      // default window, pre-sampled columns staged in key order (round 2): as wide as native RNG
 constexpr int WIN_RNG = 2048;         // default window, native RNG: no gathers, so the widest sort wins
 constexpr int KEY_LEVELS = 128;   // work-key table: candidate visits per lookup cell at magnitude levels KEY_M0 + (k+1)/16
 constexpr float KEY_M0 = 1.0f;
@@ -104,6 +108,7 @@ struct __align__(16) MathTables {
     double log_tab[256][2];                 // {1 / c_j, -2 ln c_j},  c_j = 1 + (j + 0.5) / 256   (one 16-byte load)
     double sc_tab[1024][2];                 // {sin, cos} of 2 pi (j + 0.5) / 1024: the full circle, no quadrant logic
     double k_ln2[34];                       // 2 k ln 2
+    float sc32[128][2];                     // fp32 mode: {sin, cos} of 2 pi (j + 0.5) / 128   (1 KB: what shared memory has left)
 };
 STMPM_HD void load2(const double* p, double& a, double& b) {
 #if defined(__CUDA_ARCH__)
@@ -164,6 +169,7 @@ struct TabPtr {
     STMPM_HD void log(int j, double& a, double& b) const { load2(T->log_tab[j], a, b); }
     STMPM_HD void sc(int j, double& a, double& b) const { load2(T->sc_tab[j], a, b); }
     STMPM_HD double k2(int k) const { return T->k_ln2[k]; }
+    STMPM_HD void sc32(int j, float& a, float& b) const { a = T->sc32[j][0]; b = T->sc32[j][1]; }
 };
 #if defined(__CUDACC__)
 __device__ __forceinline__ void lds_d2(uint32_t addr, double& a, double& b) {
@@ -178,7 +184,11 @@ struct TabSmem {
         asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + 4096u + 16384u + (uint32_t)k * 8u));
         return v;
     }
+    __device__ __forceinline__ void sc32(int j, float& a, float& b) const {
+        asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(base + 4096u + 16384u + 272u + (uint32_t)j * 8u));
+    }
 };
+static_assert(offsetof(MathTables, sc32) == 4096 + 16384 + 272, "TabSmem::sc32 offset");
 #endif
 STMPM_HD void box_muller_tab(const MathTables* __restrict__ T, uint32_t wa, uint32_t wb, double& z1, double& z2);
 
@@ -223,15 +233,73 @@ STMPM_HD void box_muller_tab(const MathTables* __restrict__ T, uint32_t wa, uint
     box_muller_t(TabPtr{T}, wa, wb, z1, z2);
 }
 
+// ------------------------------------------------------------------------------------------------ fp32-mode Box-Muller
+// The same draw (MODEL.md §5) in fp32, |dz| <~ 3e-6: two orders inside what the 1e-6 rad bar needs (a centroid moved by
+// sigma_c * 3e-6 px).  No int -> float conversions (XU pipe): integers enter through the 2^23 magic number.  Two MUFU
+// operations (lg2, sqrt); sin / cos from a 128-entry fp32 table + a cubic / quartic remainder.
+STMPM_HD float uint_as_float(uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(b);
+#else
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+#endif
+}
+STMPM_HD float lg2_fast(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return log2f(x);
+#endif
+}
+STMPM_HD float sqrt_fast(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return sqrtf(x);
+#endif
+}
+template <class Tab>
+STMPM_HD void box_muller_f32(const Tab T, uint32_t wa, uint32_t wb, float& z1, float& z2) {
+    // u1 = (wa + 0.5) 2^-32 from two exact pieces (wa >> 9, (wa & 511) + 0.5), one rounding
+    const float hi = uint_as_float(0x4B000000u | (wa >> 9)) - 8388608.0f;
+    const float lo = uint_as_float(0x4B000000u | (wa & 511u)) - 8388607.5f;
+    const float u1 = fmaf(hi, 512.0f, lo) * 2.3283064365386963e-10f;
+    float L = -1.3862943611198906f * lg2_fast(u1);                       // -2 ln u1
+    // within 2^-10 of one the nearest float has lost eps = 1 - u1: take eps = (2^32 - wa - 0.5) 2^-32 exactly, and
+    // -2 ln(1 - eps) = eps (2 + eps (1 + 2 eps / 3)) + O(eps^4)
+    const uint32_t c = ~wa;
+    const float eps = (uint_as_float(0x4B000000u | (c & 0x3FFFFFu)) - 8388607.5f) * 2.3283064365386963e-10f;
+    const float Ls = eps * fmaf(eps, fmaf(eps, 0.66666669f, 1.0f), 2.0f);
+    L = (c < (1u << 22)) ? Ls : L;
+    const float R = sqrt_fast(L);
+    // angle 2 pi u2 = 2 pi (j + 0.5) / 128 + d,  j = top 7 bits of wb, d from the next 23 bits (the last 2 bits move the
+    // angle by < 6e-9 rad), |d| <= pi / 128
+    const int j = (int)(wb >> 25);
+    const float t = uint_as_float(0x4B000000u | ((wb >> 2) & 0x7FFFFFu)) - 12582912.0f;     // in [-2^22, 2^22)
+    const float d = fmaf(t, 5.8516723170686385e-9f, 2.9258361585343192e-9f);               // (t + 0.5) * 8 pi / 2^32
+    const float d2 = d * d;
+    const float sd = fmaf(d * d2, -0.16666667f, d);                         // d^5 / 120 < 8e-11
+    const float cm = d2 * fmaf(d2, 0.041666668f, -0.5f);                    // cos d - 1; d^6 / 720 < 4e-13
+    float S, C;
+    T.sc32(j, S, C);
+    z1 = R * fmaf(C, cm, fmaf(-S, sd, C));
+    z2 = R * fmaf(S, cm, fmaf(C, sd, S));
+}
+
 #if defined(__CUDACC__)
-__device__ __forceinline__ void box_muller_f(uint32_t wa, uint32_t wb, float& z1, float& z2) {
-    // u in (0,1): (w + 0.5) * 2^-32 rounded to float can reach 1.0f -> clamp below 1 so that R stays finite and real
-    const float u1 = fminf(((float)wa + 0.5f) * 2.3283064365386963e-10f, 0.99999994f);
-    const float r = sqrtf(-2.0f * logf(u1));
-    float s, c;
-    sincospif(2.0f * (((float)wb + 0.5f) * 2.3283064365386963e-10f), &s, &c);
-    z1 = r * c;
-    z2 = r * s;
+// float -> double by integer operations (exact for normal floats; a zero or denormal input becomes ~1e-38, harmless as
+// an additive centroid noise): F2F conversions run on the 16-lane XU pipe, six of them per star made fp32 mode slower
+// than fp64 mode in round 1.
+__device__ __forceinline__ double f2d_bits(float f) {
+    const uint32_t b = __float_as_uint(f);
+    const uint32_t hi = (((b & 0x7fffffffu) >> 3) + 0x38000000u) | (b & 0x80000000u);
+    return __hiloint2double((int)hi, (int)(b << 29));
 }
 
 // Everything phase B needs.  Inertial-frame plane vectors: NI = C n, EU = C e_u, EV = C e_v, so that for a catalog vector
@@ -241,10 +309,12 @@ struct Ctx64 {
     double NI[3], EU[3], EV[3];
     double np0, cu, cv;           // n.p0, e_u.p0, e_v.p0
     double sx, sy;                // |BASE_DEV_X|, |BASE_DEV_Y|
+    double guard;                 // fp32 mode: re-decide on the exact path within this distance of an array edge
 };
 // Everything phase A (the conservative fp32 candidate scan) needs.
 struct Ctx32 {
     float NI[3], EU[3], EV[3], np0, cu, cv, limu, limv, magf;
+    float sxf, syf;               // fp32 mode: |BASE_DEV_X|, |BASE_DEV_Y|
     float ra0, dec0, cone;        // boresight (lookup-cell key) and scan-cone half angle
 };
 
@@ -297,6 +367,7 @@ __device__ __forceinline__ void setup64(const TrialParams& p, Ctx64& c) {
     }
     c.sx = fabs(p.devx);
     c.sy = fabs(p.devy);
+    c.guard = fma(1e-4, c.sx + c.sy, 1e-7);
 }
 
 // pre-filter window and scan cone shared by both fp32 set-ups.  Window = array + 6.8 sigma_centroid (Box-Muller with a
@@ -307,6 +378,8 @@ __device__ __forceinline__ void window_and_cone(const TrialParams& p, float half
     const float noise = 6.8f * fmaxf(fabsf((float)p.devx), fabsf((float)p.devy)) + 0.05f + 1e-5f * ff;
     c.limu = opaque(half_u + noise);
     c.limv = opaque(half_v + noise);
+    c.sxf = opaque(fabsf((float)p.devx));
+    c.syf = opaque(fabsf((float)p.devy));
     // (double)mag <= maxmag  <=>  mag <= round-down-to-float(maxmag); clamped to a finite value so that the +inf
     // magnitude of the candidate lists' terminator entry never passes
     c.magf = opaque(fminf(__double2float_rd(p.maxmag), 3.0e38f));
@@ -434,34 +507,33 @@ __device__ __forceinline__ bool star_exact(const Ctx64& c, const Tab T, const St
     return det;
 }
 
-// fp32 star evaluation (precision = 32): projection, noise and back-projection in fp32.  Two things stay fp64 because
-// they decide the parity bars: (a) the detection decision is re-taken in fp64 when the fp32
-// centroid lies inside a guard band around the array edge, so detection counts stay bit-exact with the fp64 oracle;
-// (b) B is accumulated in fp64 against the fp64 reference vector — roll about the boresight is ~1/sin(FOV/2) less
-// observable than pointing, and fp32 partial sums of B (ulp ~1e-6 at |B| ~ 16) would cost ~1e-6 rad of roll.
+// fp32 star evaluation (precision = 32, bar 1e-6 rad).  What stays fp64 and why: the three
+// plane-triad dot products and the projection scale (an fp32 dot product's 6e-8 absolute error times f = 3500 px is 2e-4 px,
+// which 3-4-star geometries amplify past the bar through the roll lever arm) and B (roll observability).  What drops to fp32:
+// the whole noise draw (Philox -> fp32 Box-Muller: no table polynomials on the FP64 pipe, no Newton steps), entering the
+// fp64 centroid through an integer-op float -> double.  The back-projection uses the bare MUFU reciprocal square root (a
+// common scale error ~5e-7 of one star's b: a Wahba weight change, ~1e-10 rad).  Detection counts stay bit-exact: a measured
+// centroid within `guard` of an array edge re-takes the whole evaluation on the exact fp64 path.
 template <class Tab>
 __device__ __forceinline__ bool star_f32(const Ctx64& c, const Ctx32& cf, const Tab T,
                                          const StarRec& s, uint32_t x0, uint32_t x1, double f_ideal, double half_u,
                                          double half_v, double* __restrict__ B) {
-    // the three plane-triad dot products in fp64: an fp32 dot product of O(1) terms carries ~6e-8 absolute error, which the
-    // projection scale (n.p0 / n.r ~ f) turns into ~2e-4 px — enough to break the 1e-6 rad bar for weak star geometries
-    const float dn = (float)(c.NI[0] * s.x + c.NI[1] * s.y + c.NI[2] * s.z);
-    const float du = (float)(c.EU[0] * s.x + c.EU[1] * s.y + c.EU[2] * s.z);
-    const float dv = (float)(c.EV[0] * s.x + c.EV[1] * s.y + c.EV[2] * s.z);
-    const float lam = cf.np0 / dn;
+    const double dn = c.NI[0] * s.x + c.NI[1] * s.y + c.NI[2] * s.z;
+    const double du = c.EU[0] * s.x + c.EU[1] * s.y + c.EU[2] * s.z;
+    const double dv = c.EV[0] * s.x + c.EV[1] * s.y + c.EV[2] * s.z;
+    const double lam = fast_div(c.np0, fmax(dn, 1e-3));
     float z1, z2;
-    box_muller_f(x0, x1, z1, z2);
-    const float um = fmaf((float)c.sx, z1, fmaf(lam, du, -cf.cu));
-    const float vm = fmaf((float)c.sy, z2, fmaf(lam, dv, -cf.cv));
-    const float hu = (float)half_u, hv = (float)half_v;
-    const float guard = 0.05f + 1e-5f * fabsf(cf.np0) + 1e-4f * ((float)c.sx + (float)c.sy);
-    if (!(dn > 0.02f) || fabsf(fabsf(um) - hu) <= guard || fabsf(fabsf(vm) - hv) <= guard)
-        return star_exact(c, T, s, x0, x1, f_ideal, half_u, half_v, B);   // rare: exact decision + exact b
-    const bool det = (fabsf(um) <= hu) && (fabsf(vm) <= hv);
+    box_muller_f32(T, x0, x1, z1, z2);
+    const double um = fma(lam, du, -c.cu) + f2d_bits(cf.sxf * z1);
+    const double vm = fma(lam, dv, -c.cv) + f2d_bits(cf.syf * z2);
+    const double eu = fabs(um) - half_u, ev = fabs(vm) - half_v;       // signed distance past the array edge
+    // |dz| <~ 3e-6 -> the fp32 centroid is within 3e-6 sigma_c of the exact one; guard = 1e-4 sigma_c (+ 1e-7 px)
+    if (fabs(eu) <= c.guard || fabs(ev) <= c.guard)
+        return star_exact(c, T, s, x0, x1, f_ideal, half_u, half_v, B);   // rare (~1e-7 of the stars): exact decision + exact b
+    const bool det = (dn > 0.0) && (eu <= 0.0) && (ev <= 0.0);
     if (det) {
-        const float fi = (float)f_ideal;
-        const float inv = rsqrtf(um * um + vm * vm + fi * fi);
-        const double bx = (double)(um * inv), by = (double)(vm * inv), bz = (double)(fi * inv);
+        const double y = seed_rsqrt(fma(vm, vm, fma(um, um, f_ideal * f_ideal)));
+        const double bx = um * y, by = vm * y, bz = f_ideal * y;
         B[0] = fma(bx, s.x, B[0]); B[1] = fma(bx, s.y, B[1]); B[2] = fma(bx, s.z, B[2]);
         B[3] = fma(by, s.x, B[3]); B[4] = fma(by, s.y, B[4]); B[5] = fma(by, s.z, B[5]);
         B[6] = fma(bz, s.x, B[6]); B[7] = fma(bz, s.y, B[7]); B[8] = fma(bz, s.z, B[8]);

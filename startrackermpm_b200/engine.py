@@ -80,10 +80,11 @@ class TrialEngine:
         self.hist_log2_sub = int(hist_log2_sub)
         self.stats_len = stats_len(hist_log2_sub)
 
-    def set_tuning(self, window: int = 0, key_radius_deg: float = -1.0) -> None:
-        """Performance knobs (results never depend on them): CTA sort window in trials (0 = default) and work-key disc
-        radius in degrees (< 0 = default).  Replaces round 1's STMPM_WIN / STMPM_KEY_RADIUS_DEG environment variables."""
-        _abi.check(self._lib.stmpm_set_tuning(self._h, int(window), float(key_radius_deg)))
+    def set_tuning(self, window: int = 0, key_radius_deg: float = -1.0, stage_columns: bool = True) -> None:
+        """Performance knobs (results never depend on them): CTA sort window in trials (0 = default), work-key disc
+        radius in degrees (< 0 = default), sorted parameter staging of pre-sampled columns (default on).  Replaces round
+        1's STMPM_WIN / STMPM_KEY_RADIUS_DEG environment variables."""
+        _abi.check(self._lib.stmpm_set_tuning(self._h, int(window), float(key_radius_deg), int(bool(stage_columns))))
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:

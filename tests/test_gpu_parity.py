@@ -366,3 +366,38 @@ def test_compact_records_and_host_pipeline_knob(engine):
     src = torch.empty(104 * n, dtype=torch.uint8, pin_memory=True).numpy()
     dst = torch.empty(12 * n, dtype=torch.uint8, pin_memory=True).numpy()
     assert engine.host_copy_roofline(n, 104, 12, src, dst) > 0 and engine.host_copy_roofline(n, 0, 9, None, dst) > 0
+
+
+def test_sorted_parameter_staging_changes_no_record(engine):
+    """Round 2's sorted parameter staging (pre-sampled windows re-written in key order to an L2 scratch, read coalesced) only
+    changes HOW a warp gets its thirteen parameters: records and statistics are bit-identical to the gather path, for
+    ragged sizes and every window width."""
+    n = 1_400_003                                          # above the staging threshold (4 x 2048 trials per SM), ragged
+    d = make_dist(BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF)
+    s = torch.cuda.current_stream().cuda_stream
+    cols = torch.empty((13, n), dtype=torch.float64, device="cuda")
+    engine.fill_presampled_device(cols, d, seed=91, trial0=5, stream=s)
+    ref_e = torch.empty(n, dtype=torch.float64, device="cuda")
+    ref_d = torch.empty(n, dtype=torch.int32, device="cuda")
+    ref_s = torch.zeros(engine.stats_len, dtype=torch.float64, device="cuda")
+    engine.set_tuning(stage_columns=False)
+    engine.run_presampled_device(cols, ref_e, ref_d, ref_s, seed=91, trial0=5, stream=s)
+    torch.cuda.synchronize()
+    try:
+        for win in (0, 2048, 1024, 480, 64):
+            for prec in (64, 32):
+                engine.set_tuning(window=win, stage_columns=True)
+                e = torch.full((n,), -7.0, dtype=torch.float64, device="cuda")
+                nd = torch.full((n,), -7, dtype=torch.int32, device="cuda")
+                st = torch.zeros(engine.stats_len, dtype=torch.float64, device="cuda")
+                engine.run_presampled_device(cols, e, nd, st, seed=91, trial0=5, precision=prec, stream=s)
+                torch.cuda.synchronize()
+                assert torch.equal(nd, ref_d), (win, prec)
+                if prec == 64:
+                    assert torch.equal(e, ref_e), win
+                    assert torch.equal(st[:2], ref_s[:2]) and torch.equal(st[4:], ref_s[4:])      # counts, n_det, max, histogram
+                else:
+                    ok = ref_e >= 0
+                    assert torch.equal(e < 0, ~ok) and float((e[ok] - ref_e[ok]).abs().max()) / ARCSEC < 1e-6
+    finally:
+        engine.set_tuning()
