@@ -39,7 +39,7 @@ struct KArgs {
     const uint8_t* lk_key;        // [n_lk_cells][KEY_LEVELS]: candidates with mag <= KEY_M0 + (k+1)/16, saturated at 255
     int win;                      // trials per CTA sort window (multiple of 32, <= WIN_MAX)
     int windows_per_unit;         // ceil(part_len / win)
-    double f_ideal, half_u, half_v;
+    double f_ideal, f_ideal2, half_u, half_v;
     int n_min, hist_shift, n_bins;   // hist_shift = 52 - log2(sub-bins per octave)
     long long n_segments, trials_per_segment, trial0, part_len;
     int parts_per_segment;
@@ -236,8 +236,8 @@ __device__ __noinline__ void band_walk_trial(const Ctx64* cp, const Ctx32* cfp, 
             uint32_t x0, x1;
             philox2x32_10(s.star_id, kb, ka, x0, x1);
             bool det;
-            if (PREC == 64) det = star_exact(c, tabs, s, x0, x1, f_ideal, half_u, half_v, B);
-            else det = star_f32(c, cf, tabs, s, x0, x1, f_ideal, half_u, half_v, B);
+            if (PREC == 64) det = star_exact(c, tabs, s, x0, x1, f_ideal, f_ideal * f_ideal, half_u, half_v, B);
+            else det = star_f32(c, cf, tabs, s, x0, x1, f_ideal, f_ideal * f_ideal, half_u, half_v, B);
             n_det += det ? 1 : 0;
             if (INSTR == 2 && det) mag_faintest = fmaxf(mag_faintest, s.mag);
         }
@@ -624,8 +624,8 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                         uint32_t x0, x1;
                         philox2x32_10(s.star_id, kb, ka, x0, x1);
                         bool det;
-                        if (PREC == 64) det = star_exact(c, tabs, s, x0, x1, a.f_ideal, a.half_u, a.half_v, B);
-                        else det = star_f32(c, cf, tabs, s, x0, x1, a.f_ideal, a.half_u, a.half_v, B);
+                        if (PREC == 64) det = star_exact(c, tabs, s, x0, x1, a.f_ideal, a.f_ideal2, a.half_u, a.half_v, B);
+                        else det = star_f32(c, cf, tabs, s, x0, x1, a.f_ideal, a.f_ideal2, a.half_u, a.half_v, B);
                         n_det += det ? 1 : 0;
                         if (INSTR == 2 && det) mag_faintest = fmaxf(mag_faintest, s.mag);
                     }
@@ -1420,7 +1420,7 @@ static int fill_common(stmpm_handle* h, KArgs& a, int precision) {
     a.lk_band_tab = h->lk_band_tab; a.lk_off = h->lk_off; a.lk_list = h->lk_list; a.lk_bands = h->lk_bands;
     a.lk_inv_band_h = (float)((double)h->lk_bands / M_PI); a.lk_cone = h->lk_cone; a.tables = h->tables;
     a.lk_key = h->lk_key;
-    a.f_ideal = h->cfg.f_ideal; a.half_u = h->cfg.half_u; a.half_v = h->cfg.half_v; a.n_min = h->cfg.n_min;
+    a.f_ideal = h->cfg.f_ideal; a.f_ideal2 = h->cfg.f_ideal * h->cfg.f_ideal; a.half_u = h->cfg.half_u; a.half_v = h->cfg.half_v; a.n_min = h->cfg.n_min;
     a.hist_shift = 52 - h->cfg.hist_log2_sub; a.n_bins = h->n_bins;
     a.stats_len = STMPM_STATS_HEAD + h->n_bins;
     return 0;

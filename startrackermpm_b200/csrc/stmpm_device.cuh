@@ -309,12 +309,12 @@ struct Ctx64 {
     double NI[3], EU[3], EV[3];
     double np0, cu, cv;           // n.p0, e_u.p0, e_v.p0
     double sx, sy;                // |BASE_DEV_X|, |BASE_DEV_Y|
-    double guard;                 // fp32 mode: re-decide on the exact path within this distance of an array edge
 };
 // Everything phase A (the conservative fp32 candidate scan) needs.
 struct Ctx32 {
     float NI[3], EU[3], EV[3], np0, cu, cv, limu, limv, magf;
     float sxf, syf;               // fp32 mode: |BASE_DEV_X|, |BASE_DEV_Y|
+    int guard_hi;                 // fp32 mode: high word of the guard distance around the array edges (see star_f32)
     float ra0, dec0, cone;        // boresight (lookup-cell key) and scan-cone half angle
 };
 
@@ -367,7 +367,6 @@ __device__ __forceinline__ void setup64(const TrialParams& p, Ctx64& c) {
     }
     c.sx = fabs(p.devx);
     c.sy = fabs(p.devy);
-    c.guard = fma(1e-4, c.sx + c.sy, 1e-7);
 }
 
 // pre-filter window and scan cone shared by both fp32 set-ups.  Window = array + 6.8 sigma_centroid (Box-Muller with a
@@ -380,6 +379,8 @@ __device__ __forceinline__ void window_and_cone(const TrialParams& p, float half
     c.limv = opaque(half_v + noise);
     c.sxf = opaque(fabsf((float)p.devx));
     c.syf = opaque(fabsf((float)p.devy));
+    c.guard_hi = __double2hiint(fma(1e-4, fabs(p.devx) + fabs(p.devy), 1e-7));
+    asm volatile("" : "+r"(c.guard_hi));
     // (double)mag <= maxmag  <=>  mag <= round-down-to-float(maxmag); clamped to a finite value so that the +inf
     // magnitude of the candidate lists' terminator entry never passes
     c.magf = opaque(fminf(__double2float_rd(p.maxmag), 3.0e38f));
@@ -481,7 +482,7 @@ __device__ __forceinline__ bool prefilter_geom(const Ctx32& c, const float4 s) {
 // (x0, x1) = the star's Philox2x32-10 words (MODEL.md §5), computed by the caller.
 template <class Tab>
 __device__ __forceinline__ bool star_exact(const Ctx64& c, const Tab T, const StarRec& s,
-                                           uint32_t x0, uint32_t x1, double f_ideal, double half_u, double half_v,
+                                           uint32_t x0, uint32_t x1, double f_ideal, double f_ideal2, double half_u, double half_v,
                                            double* __restrict__ B) {
     const double dn = c.NI[0] * s.x + c.NI[1] * s.y + c.NI[2] * s.z;
     const double du = c.EU[0] * s.x + c.EU[1] * s.y + c.EU[2] * s.z;
@@ -496,7 +497,7 @@ __device__ __forceinline__ bool star_exact(const Ctx64& c, const Tab T, const St
     const bool det = (dn > 0.0) && (fabs(um) <= half_u) && (fabs(vm) <= half_v);
     if (det) {
         // b = (um, vm, f) / |.|: seed y ~ 1/|.|, one Newton factor w; (um y), (vm y), (f y) run beside the Newton chain
-        const double n2 = fma(vm, vm, fma(um, um, f_ideal * f_ideal));
+        const double n2 = fma(vm, vm, fma(um, um, f_ideal2));
         const double y = seed_rsqrt(n2);
         const double w = fma(-0.5 * n2 * y, y, 1.5);
         const double bx = (um * y) * w, by = (vm * y) * w, bz = (f_ideal * y) * w;
@@ -516,7 +517,7 @@ __device__ __forceinline__ bool star_exact(const Ctx64& c, const Tab T, const St
 // centroid within `guard` of an array edge re-takes the whole evaluation on the exact fp64 path.
 template <class Tab>
 __device__ __forceinline__ bool star_f32(const Ctx64& c, const Ctx32& cf, const Tab T,
-                                         const StarRec& s, uint32_t x0, uint32_t x1, double f_ideal, double half_u,
+                                         const StarRec& s, uint32_t x0, uint32_t x1, double f_ideal, double f_ideal2, double half_u,
                                          double half_v, double* __restrict__ B) {
     const double dn = c.NI[0] * s.x + c.NI[1] * s.y + c.NI[2] * s.z;
     const double du = c.EU[0] * s.x + c.EU[1] * s.y + c.EU[2] * s.z;
@@ -527,12 +528,15 @@ __device__ __forceinline__ bool star_f32(const Ctx64& c, const Ctx32& cf, const 
     const double um = fma(lam, du, -c.cu) + f2d_bits(cf.sxf * z1);
     const double vm = fma(lam, dv, -c.cv) + f2d_bits(cf.syf * z2);
     const double eu = fabs(um) - half_u, ev = fabs(vm) - half_v;       // signed distance past the array edge
-    // |dz| <~ 3e-6 -> the fp32 centroid is within 3e-6 sigma_c of the exact one; guard = 1e-4 sigma_c (+ 1e-7 px)
-    if (fabs(eu) <= c.guard || fabs(ev) <= c.guard)
-        return star_exact(c, T, s, x0, x1, f_ideal, half_u, half_v, B);   // rare (~1e-7 of the stars): exact decision + exact b
-    const bool det = (dn > 0.0) && (eu <= 0.0) && (ev <= 0.0);
+    // |dz| <~ 3e-6 -> the fp32 centroid is within 3e-6 sigma_c of the exact one; guard ~ 1e-4 sigma_c (+ 1e-7 px).  The
+    // comparisons run on the high words (integer pipe, not the 16-lane FP64 pipe): |x| <= g  <=  hi(|x|) <= hi(g), which
+    // over-covers by less than one unit of g's leading word — the guard only has to be wide enough
+    const int hu = __double2hiint(eu), hv = __double2hiint(ev);
+    if ((hu & 0x7fffffff) <= cf.guard_hi || (hv & 0x7fffffff) <= cf.guard_hi)
+        return star_exact(c, T, s, x0, x1, f_ideal, f_ideal2, half_u, half_v, B);   // rare (~1e-7 of the stars): exact decision + exact b
+    const bool det = (__double2hiint(dn) > 0) && ((hu & hv) < 0);      // n.r > 0 and both distances negative (zero is in the guard)
     if (det) {
-        const double y = seed_rsqrt(fma(vm, vm, fma(um, um, f_ideal * f_ideal)));
+        const double y = seed_rsqrt(fma(vm, vm, fma(um, um, f_ideal2)));
         const double bx = um * y, by = vm * y, bz = f_ideal * y;
         B[0] = fma(bx, s.x, B[0]); B[1] = fma(bx, s.y, B[1]); B[2] = fma(bx, s.z, B[2]);
         B[3] = fma(by, s.x, B[3]); B[4] = fma(by, s.y, B[4]); B[5] = fma(by, s.z, B[5]);

@@ -285,10 +285,43 @@ def write_result_pickle(df, name: str, data_dir: str = "data") -> str:
     return path
 
 
+def tail_statistics(engine: TrialEngine, dist: _abi.Dist, n_trials: int, seed: int, *, trial0: int = 0,
+                    chunk: int = 1 << 30, checkpoint: str | None = None, precision: int = 64, stop_after_chunks: int = 0):
+    """Config-5-style statistics-only run of `n_trials` global trial indices [trial0, trial0 + n_trials) in chunks, with
+    checkpoint / resume (trial i is a pure function of (seed, i), so a checkpoint is just
+    (seed, next trial index, packed statistics) — 70 KB).  After every chunk the state is written atomically to
+    `checkpoint` (.npz); a later call with the same arguments resumes after the last finished chunk and ends with exactly
+    the statistics an uninterrupted run produces (integer entries bit-identical; the two float sums to rounding order).
+    `stop_after_chunks` > 0 returns early (tests / time-boxed jobs).  Returns (packed stats, next trial index)."""
+    import os
+    total = np.zeros(engine.stats_len)
+    nxt = int(trial0)
+    if checkpoint and os.path.exists(checkpoint):
+        with np.load(checkpoint) as ck:
+            if int(ck["seed"]) != int(seed) & (2**64 - 1) or int(ck["trial0"]) != int(trial0) or int(ck["hist_log2_sub"]) != engine.hist_log2_sub \
+                    or not np.array_equal(ck["dist"], np.frombuffer(bytes(dist), dtype=np.float64)):
+                raise ValueError(f"{checkpoint} belongs to a different run (seed / trial0 / distribution / histogram differ)")
+            total, nxt = ck["stats"].copy(), int(ck["next_trial"])
+    end, done = int(trial0) + int(n_trials), 0
+    while nxt < end:
+        m = min(int(chunk), end - nxt)
+        _merge(total, engine.run_rng(dist, m, seed, nxt, precision)[0])
+        nxt += m
+        done += 1
+        if checkpoint:
+            tmp = checkpoint + ".tmp.npz"
+            np.savez(tmp, stats=total, next_trial=np.int64(nxt), seed=np.uint64(int(seed) & (2**64 - 1)), trial0=np.int64(trial0),
+                     hist_log2_sub=np.int64(engine.hist_log2_sub), dist=np.frombuffer(bytes(dist), dtype=np.float64))
+            os.replace(tmp, checkpoint)
+        if stop_after_chunks and done >= stop_after_chunks:
+            break
+    return total, nxt
+
+
 def summaries(stats: np.ndarray, hist_log2_sub: int = 8) -> list[dict]:
     return [summarize(s, hist_log2_sub) for s in np.atleast_2d(stats)]
 
 
 __all__ = ["monte_carlo_converged", "grid_axes", "sensitivity_grid_dists", "sensitivity_grid", "leo_lifetime_dists",
            "run_segments", "summaries", "study_matrix", "STUDY_TAGS", "NORMAL_PARAMS", "result_frame",
-           "write_result_pickle", "QUEST_OUTPUT", "N_DET_OUTPUT", "MAG_OUTPUT", "radiative_equilibrium", "orbit_dtemp_amplitude"]
+           "write_result_pickle", "tail_statistics", "QUEST_OUTPUT", "N_DET_OUTPUT", "MAG_OUTPUT", "radiative_equilibrium", "orbit_dtemp_amplitude"]

@@ -300,3 +300,24 @@ def test_toolplot_modes_s_and_c_on_device(engine):
     assert c["std"] == pytest.approx(s.std(), rel=1e-12) and c["std_halfnormal"] == pytest.approx(s.std() * np.sqrt(1 - 2 / np.pi), rel=1e-12)
     h = np.histogram(s, bins=50, density=True)
     assert np.allclose(c["density"], h[0], rtol=1e-12, atol=0)
+
+
+@pytest.mark.gpu
+def test_tail_statistics_checkpoint_and_resume(engine, tmp_path):
+    """SURVEY.md §5 checkpoint/resume: an interrupted chunked run resumed from its 70 KB checkpoint ends with the statistics
+    of an uninterrupted run (counts and histogram bit-identical), and refuses a checkpoint of a different run."""
+    from startrackermpm_b200 import studies
+    from startrackermpm_b200.engine import make_dist
+    d = make_dist(BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF)
+    n, chunk, ck = 1_000_003, 300_000, str(tmp_path / "tail.npz")
+    ref = engine.run_rng(d, n, 17, 1000)[0]
+    part, nxt = studies.tail_statistics(engine, d, n, 17, trial0=1000, chunk=chunk, checkpoint=ck, stop_after_chunks=2)
+    assert nxt == 1000 + 2 * chunk and part[0] + part[1] == 2 * chunk
+    full, nxt = studies.tail_statistics(engine, d, n, 17, trial0=1000, chunk=chunk, checkpoint=ck)        # resumes
+    assert nxt == 1000 + n
+    assert np.array_equal(full[:2], ref[:2]) and np.array_equal(full[4:], ref[4:])
+    assert np.allclose(full[2:4], ref[2:4], rtol=1e-12)
+    again, _ = studies.tail_statistics(engine, d, n, 17, trial0=1000, chunk=chunk, checkpoint=ck)         # nothing left to do
+    assert np.array_equal(again, full)
+    with pytest.raises(ValueError):
+        studies.tail_statistics(engine, d, n, 18, trial0=1000, chunk=chunk, checkpoint=ck)
