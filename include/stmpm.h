@@ -21,6 +21,7 @@ extern "C" {
 #define STMPM_E_ARG      10001   /* bad argument */
 #define STMPM_E_STATE    10002   /* catalog / sensor not set */
 #define STMPM_E_NOGPU    10003   /* no CUDA device */
+#define STMPM_E_WATCHDOG 10004   /* a trial kernel's internal scheduler wait exceeded 20 s of wall time: results incomplete */
 
 #define STMPM_NCOLS      13      /* pre-sampled input columns, order below */
 #define STMPM_NNORMAL    11      /* normal-distributed parameters in native-RNG mode */
@@ -98,6 +99,9 @@ int stmpm_version(void);
 
 int stmpm_create(stmpm_t** h, int device);
 int stmpm_destroy(stmpm_t* h);
+/* After the caller has synchronised a stream it passed to the asynchronous entry points: 0, or STMPM_E_WATCHDOG if a kernel of
+ * this handle gave up on its internal scheduler (the host-buffer entry points below check this themselves). */
+int stmpm_check(stmpm_t* h);
 /* sm_count, max dynamic shared memory per block, SM clock kHz, memory clock kHz */
 int stmpm_device_info(stmpm_t* h, int32_t* sm_count, int64_t* smem_per_block, int32_t* sm_khz, int32_t* mem_khz);
 

@@ -55,6 +55,7 @@ struct KArgs {
     unsigned long long* counters;   // INSTR only: [visits, mag_pass, survivors, detected]
     double* stage;                  // MODE 0: per-CTA scratch [gridDim][2][STMPM_NCOLS][WIN_MAX] — the window's columns in key order
     uint8_t* ndet8;                 // optional compact record: detected stars saturated at 255 (9-byte records with err)
+    int* status;                    // host-mapped word: a scheduler wait that exceeds WATCHDOG_NS writes STMPM_E_WATCHDOG here
     const int* cancel;              // optional: a non-zero word makes the launch a no-op (on-device MonteCarlo stop rule)
 };
 
@@ -89,6 +90,16 @@ __device__ __forceinline__ double4 ld_rec(const StarRec* p) {
 // fire-and-forget fp64 add (RED, no response): atomicAdd with an unused result compiles to ATOMG ... RZ here
 __device__ __forceinline__ void red_add_f64(double* p, double v) {
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
+}
+// Scheduler watchdog: the window / group waits below are bounded by WALL TIME (%globaltimer), not by a poll count — a poll
+// budget can run out under compute-sanitizer, cuda-gdb or preemption without any deadlock.  On expiry the warp records
+// STMPM_E_WATCHDOG in a host-mapped status word and leaves its trial loop cleanly (no __trap: a trap is a sticky,
+// context-fatal error that would also take the caller's torch context down); the host entry points report the code.
+constexpr unsigned long long WATCHDOG_NS = 20ull * 1000000000ull;
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -344,7 +355,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
     long long cur_seg = -1;
 
     int build_w = (warp == 0 && n_windows > 0) ? 0 : -1;   // pending window to build (warp 0 builds the first one)
-    bool have_group = false;
+    bool have_group = false, aborted = false;
     int grp_w = 0, grp_r = 0, grp_q = 0;
     for (;;) {
         if (build_w >= 0) {
@@ -354,8 +365,14 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
             uint16_t* w_perm = s_perm + (bw & 1) * WIN_MAX;
             {   // the buffer is free once every group of window bw - 2 has copied its permutation entries out
                 const int need = gpw * (bw >> 1);
-                unsigned int spins = 0;
-                while (v_sched[2 + (bw & 1)] < need) { __nanosleep(32); if (++spins > (1u << 26)) __trap(); }
+                if (v_sched[2 + (bw & 1)] < need) {
+                    const unsigned long long t0 = global_ns();
+                    while (v_sched[2 + (bw & 1)] < need) {
+                        __nanosleep(32);
+                        if (global_ns() - t0 > WATCHDOG_NS) { aborted = true; break; }
+                    }
+                }
+                if (aborted) break;
                 __threadfence_block();
             }
             const long long ku = bw / a.windows_per_unit;
@@ -492,10 +509,14 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
             if (g >= n_groups) break;
             grp_w = g / gpw;
             const int gi = g - grp_w * gpw;
-            {
-                unsigned int spins = 0;
-                while (v_sched[1] <= grp_w) { __nanosleep(64); if (++spins > (1u << 26)) __trap(); }
+            if (v_sched[1] <= grp_w) {
+                const unsigned long long t0 = global_ns();
+                while (v_sched[1] <= grp_w) {
+                    __nanosleep(64);
+                    if (global_ns() - t0 > WATCHDOG_NS) { aborted = true; break; }
+                }
             }
+            if (aborted) break;
             __threadfence_block();
             grp_q = gi * 32 + lane;                                   // position in key order
             grp_r = s_perm[(grp_w & 1) * WIN_MAX + grp_q];
@@ -686,6 +707,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
         }
     }
 
+    if (aborted && a.status != nullptr && lane == 0) *reinterpret_cast<volatile int*>(a.status) = STMPM_E_WATCHDOG;
     if (INSTR == 1) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) atomicAdd(a.counters + k, ins[k]);
@@ -1012,6 +1034,8 @@ struct stmpm_handle {
     int tune_window = 0;
     double tune_key_radius_deg = -1.0;
     int tune_stage = 1;                   // sorted parameter staging for pre-sampled launches (0 = round 1's gathers)
+    int* status_host = nullptr;           // pinned + mapped: the kernels' watchdog word (stmpm_check)
+    int* status_dev = nullptr;
     cudaMemPool_t pool = nullptr;         // stream-ordered per-launch storage (staging scratch, distribution arrays)
     long long host_chunk = HOST_CHUNK;    // trials per stage of the host pipelines
 };
@@ -1156,6 +1180,9 @@ extern "C" int stmpm_create(stmpm_t** out, int device) {
         stmpm_host_tables(&mt);
         CK(cudaMalloc(&h->tables, sizeof(MathTables)));
         CK(cudaMemcpy(h->tables, &mt, sizeof(MathTables), cudaMemcpyHostToDevice));
+        CK(cudaHostAlloc(&h->status_host, sizeof(int), cudaHostAllocMapped));
+        *h->status_host = 0;
+        CK(cudaHostGetDevicePointer(&h->status_dev, h->status_host, 0));
         // the handle's own stream-ordered pool: blocks freed in stream order are kept for the next launch, not returned to the OS
         cudaMemPoolProps pp{};
         pp.allocType = cudaMemAllocationTypePinned;
@@ -1190,6 +1217,7 @@ extern "C" int stmpm_destroy(stmpm_t* h) {
     free_stage(h);
     for (int i = 0; i < stmpm_handle::NBUF; ++i) if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
     if (h->pool) { cudaDeviceSynchronize(); cudaMemPoolDestroy(h->pool); }
+    if (h->status_host) cudaFreeHost(h->status_host);
     delete h;
     return 0;
 }
@@ -1423,7 +1451,21 @@ static int fill_common(stmpm_handle* h, KArgs& a, int precision) {
     a.f_ideal = h->cfg.f_ideal; a.f_ideal2 = h->cfg.f_ideal * h->cfg.f_ideal; a.half_u = h->cfg.half_u; a.half_v = h->cfg.half_v; a.n_min = h->cfg.n_min;
     a.hist_shift = 52 - h->cfg.hist_log2_sub; a.n_bins = h->n_bins;
     a.stats_len = STMPM_STATS_HEAD + h->n_bins;
+    a.status = h->status_dev;
     return 0;
+}
+
+// after a synchronisation: did a kernel of this handle hit its scheduler watchdog?
+static int check_status(stmpm_handle* h) {
+    const int code = *reinterpret_cast<volatile int*>(h->status_host);
+    if (code == 0) return 0;
+    *h->status_host = 0;
+    return fail(code, "trial kernel scheduler watchdog: a window / group wait exceeded 20 s (results of this call are incomplete)");
+}
+
+extern "C" int stmpm_check(stmpm_t* h) {
+    if (!h) return fail(STMPM_E_ARG, "stmpm_check: null handle");
+    return check_status(h);
 }
 
 extern "C" int stmpm_trials_presampled(stmpm_t* h, int precision, int64_t n, uint64_t seed, int64_t trial0,
@@ -1576,7 +1618,7 @@ extern "C" int stmpm_run_presampled_host_ex(stmpm_t* h, int precision, int64_t n
     }
     for (int i = 0; i < stmpm_handle::NBUF; ++i) CK(cudaStreamSynchronize(h->streams[i]));
     if (stats) CK(cudaMemcpy(stats, h->stage_stats, sizeof(double) * slen, cudaMemcpyDeviceToHost));
-    return 0;
+    return check_status(h);
 }
 
 static int run_rng_host_impl(stmpm_t* h, int precision, int64_t n_segments, int64_t tps, uint64_t seed, int64_t trial0,
@@ -1625,7 +1667,7 @@ static int run_rng_host_impl(stmpm_t* h, int precision, int64_t n_segments, int6
     }
     for (int i = 0; i < stmpm_handle::NBUF; ++i) CK(cudaStreamSynchronize(h->streams[i]));
     if (stats) CK(cudaMemcpy(stats, h->stage_stats, sizeof(double) * slen * n_segments, cudaMemcpyDeviceToHost));
-    return 0;
+    return check_status(h);
 }
 
 extern "C" int stmpm_run_rng_host(stmpm_t* h, int precision, int64_t n_segments, int64_t tps, uint64_t seed,
@@ -1854,7 +1896,7 @@ extern "C" int stmpm_mc_converge(stmpm_t* h, int precision, const stmpm_dist* di
     out->mean_halfnormal = res.prev * std::sqrt(2.0 / M_PI);                 // driver.py:291,323
     out->fail_rate = (res.n_ok + res.n_fail) > 0 ? res.n_fail / (res.n_ok + res.n_fail) : 0.0;
     out->rounds = rounds; out->trials_computed = done_batches * batch;
-    return 0;
+    return check_status(h);
 }
 
 extern "C" int stmpm_toolplot_failrate(stmpm_t* h, const double* err_dev, const double* mag_dev, int64_t n,

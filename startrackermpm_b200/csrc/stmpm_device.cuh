@@ -488,8 +488,12 @@ __device__ __forceinline__ bool star_exact(const Ctx64& c, const Tab T, const St
     const double du = c.EU[0] * s.x + c.EU[1] * s.y + c.EU[2] * s.z;
     const double dv = c.EV[0] * s.x + c.EV[1] * s.y + c.EV[2] * s.z;
     // pre-filter survivors have dn > 0.02 (anything else is not detectable: dn <= 0 fails the test below, and a star
-    // with 0 < dn <= 0.02 lands > 50 f from the array centre); clamp so the seed + Newton reciprocal stays in range
+    // with 0 < dn <= 0.02 lands > 50 f from the array centre), so the MUFU-seeded reciprocal is in range without a clamp
+#if defined(STMPM_DN_CLAMP)
     const double lam = fast_div(c.np0, fmax(dn, 1e-3));
+#else
+    const double lam = fast_div(c.np0, dn);      // dn <= 0 gives a negative / infinite / NaN scale: every comparison below is then false
+#endif
     double z1, z2;
     box_muller_t(T, x0, x1, z1, z2);
     const double um = fma(c.sx, z1, fma(lam, du, -c.cu));
@@ -522,7 +526,11 @@ __device__ __forceinline__ bool star_f32(const Ctx64& c, const Ctx32& cf, const 
     const double dn = c.NI[0] * s.x + c.NI[1] * s.y + c.NI[2] * s.z;
     const double du = c.EU[0] * s.x + c.EU[1] * s.y + c.EU[2] * s.z;
     const double dv = c.EV[0] * s.x + c.EV[1] * s.y + c.EV[2] * s.z;
+#if defined(STMPM_DN_CLAMP)
     const double lam = fast_div(c.np0, fmax(dn, 1e-3));
+#else
+    const double lam = fast_div(c.np0, dn);
+#endif
     float z1, z2;
     box_muller_f32(T, x0, x1, z1, z2);
     const double um = fma(lam, du, -c.cu) + f2d_bits(cf.sxf * z1);

@@ -86,6 +86,10 @@ class TrialEngine:
         1's STMPM_WIN / STMPM_KEY_RADIUS_DEG environment variables."""
         _abi.check(self._lib.stmpm_set_tuning(self._h, int(window), float(key_radius_deg), int(bool(stage_columns))))
 
+    def check(self) -> None:
+        """After synchronising a stream handed to the *_device calls: raises if a kernel hit its scheduler watchdog."""
+        _abi.check(self._lib.stmpm_check(self._h))
+
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:
             self._lib.stmpm_destroy(self._h)
