@@ -291,6 +291,21 @@ def run_ours(args):
     ms_total = float(t.item())
     value = world * n * args.steps / (ms_total * 1e-3)
 
+    # ---- the fp32 instantiation on the same device-resident batch (north_star: FP32 and FP64 pipe fractions)
+    fp32_ms = None
+    if rank == 0 or world > 1:
+        for _ in range(2):
+            eng.run_presampled_device(cols, err, ndet, None, seed=SEED, trial0=trial0, precision=32, stream=stream)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(2):
+            eng.run_presampled_device(cols, err, ndet, None, seed=SEED, trial0=trial0, precision=32, stream=stream)
+        f1.record()
+        torch.cuda.synchronize()
+        fp32_ms = f0.elapsed_time(f1) / 2
+        eng.run_presampled_device(cols, err, ndet, None, seed=SEED, trial0=trial0, precision=64, stream=stream)   # records back to fp64
+
     # ---- e2e: host pinned buffers through the host C-ABI call, copies inside the timed region
     n_e2e = min(n, int(args.e2e_trials))
     e2e = None
@@ -376,12 +391,16 @@ def run_ours(args):
         k_s = kernel_ms * 1e-3
         achieved_tf = flops_trial * n / k_s / 1e12
         achieved_gbs = (BYTES_IN_PER_TRIAL + BYTES_OUT_PER_TRIAL) * n / k_s / 1e9
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_trial")
+        traffic, traffic_src, pipes = None, None, None
+        try:   # static: DRAM bytes and pipe utilisation come from the committed ncu capture of this kernel, not from this run
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tj.get("dram_bytes_per_trial")
             traffic = traffic * n if traffic is not None else None
+            traffic_src = f"profiles/traffic.json (ncu --set full capture {tj.get('capture', '?')}; static, not measured in this run)"
+            pipes = tj.get("pipes")
         except (OSError, ValueError):
             pass
+        peak32 = eng.fma_peak(32)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -395,7 +414,16 @@ def run_ours(args):
                                "(MEASURED_PEAKS.json holds no FP64 figure)",
                 "flops_per_trial": flops_trial, "work_model": "430 + 7*N_visit + 81*N_star (DESIGN.md §4)",
                 "n_visit": wc["visits"], "n_mag_pass": wc["mag_pass"], "n_survivors": wc["survivors"],
-                "n_star": wc["detected"], "kernel_ms": kernel_ms, "traffic": traffic,
+                "n_star": wc["detected"], "kernel_ms": kernel_ms, "traffic": traffic, "traffic_source": traffic_src,
+                "pipes_pct_of_peak": pipes,
+                "peak_fp32": {"value": peak32, "unit": "TFLOP/s", "source": "stmpm_fma_peak(32), measured live"},
+                "fp32_mode": None if not fp32_ms else {
+                    "kernel": "trials_kernel<presampled, fp32>", "kernel_ms": fp32_ms, "trials_per_s": n / (fp32_ms * 1e-3),
+                    "vs_fp64_mode": kernel_ms / fp32_ms,
+                    "achieved": flops_trial * n / (fp32_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+                    "frac_of_fp64_peak": flops_trial * n / (fp32_ms * 1e-3) / 1e12 / peak64 if peak64 else None,
+                    "frac_of_fp32_peak": flops_trial * n / (fp32_ms * 1e-3) / 1e12 / peak32 if peak32 else None,
+                    "note": "same algorithmic flops; the dot products, projection scale and B stay fp64, the noise draw is fp32 (DESIGN.md §6)"},
                 "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                         "bytes_per_trial": BYTES_IN_PER_TRIAL + BYTES_OUT_PER_TRIAL,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},

@@ -36,7 +36,8 @@ struct KArgs {
     int lk_bands;
     float lk_inv_band_h, lk_cone; // a trial whose scan cone exceeds lk_cone takes the sky-grid scan instead
     const MathTables* tables;
-    const uint8_t* lk_key;        // [n_lk_cells][KEY_LEVELS]: candidates with mag <= KEY_M0 + (k+1)/16, saturated at 255
+    const uint8_t* lk_key;        // [n_lk_cells][KEY_ROLLS][KEY_LEVELS]: stars with mag <= KEY_M0 + (k+1)/16 on the array footprint, saturated at 255
+    float key_roll_inv;           // 1 / symmetry period of the footprint's orientation (2/pi for a square array, 1/pi otherwise)
     int win;                      // trials per CTA sort window (multiple of 32, <= WIN_MAX)
     int windows_per_unit;         // ceil(part_len / win)
     double f_ideal, f_ideal2, half_u, half_v;
@@ -182,6 +183,19 @@ __device__ __forceinline__ int lookup_cell(const int2* __restrict__ s_lkband, in
     const int lb = min(lk_bands - 1, max(0, (int)floorf((dec0 + 1.57079633f) * lk_inv_band_h)));
     const int2 bt = s_lkband[lb];
     return bt.x + min(bt.y - 1, max(0, (int)floorf(ra0 * 0.159154943f * (float)bt.y)));
+}
+
+// work key of a trial: stars brighter than its MAX_MAGNITUDE level on the array footprint centred on its lookup cell, in its
+// roll bin (host table, rebuild_lists).  Any finite input gives a valid index; the key only orders the work.
+__device__ __forceinline__ int work_key(const KArgs& a, const int2* __restrict__ s_lkband, float raf, float decf, float rollf, float mm) {
+    raf -= 6.28318531f * floorf(raf * 0.159154943f);
+    decf = fminf(fmaxf(decf, -1.57079633f), 1.57079633f);
+    const int cell = lookup_cell(s_lkband, a.lk_bands, a.lk_inv_band_h, raf, decf);
+    float t = rollf * a.key_roll_inv;
+    t -= floorf(t);
+    const int rb = min(KEY_ROLLS - 1, max(0, (int)(t * (float)KEY_ROLLS)));
+    const int lev = min(KEY_LEVELS - 1, (int)floorf((mm - KEY_M0) * 16.0f));
+    return lev < 0 ? 0 : (int)__ldg(a.lk_key + ((size_t)cell * KEY_ROLLS + rb) * KEY_LEVELS + lev);
 }
 
 // ------------------------------------------------------------------------------------------------ fallback trial
@@ -392,13 +406,14 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                 // 128 trials per round: the four slots' column loads are issued before the first use, then the four
                 // key-table loads — two exposed memory latencies per round
                 for (int r0 = 0; r0 < win; r0 += 128) {
-                    double kra[4], kdec[4], kmm[4];
+                    double kra[4], kdec[4], kroll[4], kmm[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const int r = r0 + lane + 32 * q;
-                        kra[q] = kdec[q] = 0.0; kmm[q] = -100.0;
+                        kra[q] = kdec[q] = kroll[q] = 0.0; kmm[q] = -100.0;
                         if (r < nw) {
-                            kra[q] = __ldg(a.cols[0] + rec0 + r); kdec[q] = __ldg(a.cols[1] + rec0 + r); kmm[q] = __ldg(a.cols[12] + rec0 + r);
+                            kra[q] = __ldg(a.cols[0] + rec0 + r); kdec[q] = __ldg(a.cols[1] + rec0 + r);
+                            kroll[q] = __ldg(a.cols[2] + rec0 + r); kmm[q] = __ldg(a.cols[12] + rec0 + r);
                         }
                     }
                     // pull the round's other ten columns into L2 (one 32-byte sector = 4 trials per lane): the groups gather
@@ -406,18 +421,12 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                     // a quarter as long as DRAM misses do, and the LSU pipe they share with shared memory stays fluid
                     if (r0 + 4 * lane < nw) {          // (with staging too: the copy below then reads L2 hits)
 #pragma unroll
-                        for (int cI = 2; cI < 12; ++cI) prefetch_l2(a.cols[cI] + rec0 + r0 + 4 * lane);
+                        for (int cI = 3; cI < 12; ++cI) prefetch_l2(a.cols[cI] + rec0 + r0 + 4 * lane);
                     }
                     int kkey[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float raf = (float)kra[q], decf = (float)kdec[q];
-                        raf -= 6.28318531f * floorf(raf * 0.159154943f);
-                        decf = fminf(fmaxf(decf, -1.57079633f), 1.57079633f);
-                        const int cell = lookup_cell(s_lkband, a.lk_bands, a.lk_inv_band_h, raf, decf);
-                        const int lev = min(KEY_LEVELS - 1, (int)floorf(((float)kmm[q] - KEY_M0) * 16.0f));
-                        kkey[q] = lev < 0 ? 0 : (int)__ldg(a.lk_key + (size_t)cell * KEY_LEVELS + lev);
-                    }
+                    for (int q = 0; q < 4; ++q)
+                        kkey[q] = work_key(a, s_lkband, (float)kra[q], (float)kdec[q], (float)kroll[q], (float)kmm[q]);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const int r = r0 + lane + 32 * q;
@@ -432,16 +441,10 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                 for (int r = lane; r < win; r += 32) {
                     int key = KEY_BINS - 1;                               // padding slots sort last
                     if (r < nw) {
-                        double ra, dec, mm;
+                        double ra, dec, roll, mm;
                         const unsigned long long gi = (unsigned long long)(a.trial0 + rec0 + r);
-                        sample_key_params(*dist, s_tab, (uint32_t)gi, (uint32_t)(gi >> 32), a.k0, a.k1, ra, dec, mm);
-                        // boresight (ra, dec) -> lookup cell (any finite input gives a valid cell; the key is only a hint)
-                        float raf = (float)ra, decf = (float)dec;
-                        raf -= 6.28318531f * floorf(raf * 0.159154943f);
-                        decf = fminf(fmaxf(decf, -1.57079633f), 1.57079633f);
-                        const int cell = lookup_cell(s_lkband, a.lk_bands, a.lk_inv_band_h, raf, decf);
-                        const int lev = min(KEY_LEVELS - 1, (int)floorf(((float)mm - KEY_M0) * 16.0f));
-                        key = lev < 0 ? 0 : (int)__ldg(a.lk_key + (size_t)cell * KEY_LEVELS + lev);
+                        sample_key_params(*dist, s_tab, (uint32_t)gi, (uint32_t)(gi >> 32), a.k0, a.k1, ra, dec, roll, mm);
+                        key = work_key(a, s_lkband, (float)ra, (float)dec, (float)roll, (float)mm);
                     }
                     w_key[r] = (uint8_t)key;
                     atomicAdd(w_hist + (key >> 1), 1u << (16 * (key & 1)));
@@ -1014,7 +1017,8 @@ struct stmpm_handle {
     int lk_bands = 0;
     float lk_cone = -1.0f;
     MathTables* tables = nullptr;
-    uint8_t* lk_key = nullptr;    // work-key table [n_lk_cells][KEY_LEVELS]
+    uint8_t* lk_key = nullptr;    // work-key table [n_lk_cells][KEY_ROLLS][KEY_LEVELS]
+    float key_roll_inv = 0.63661977f;
     bool have_catalog = false, have_sensor = false;
     stmpm_sensor_cfg cfg{};
     int n_bins = 0;
@@ -1069,10 +1073,21 @@ static int rebuild_lists(stmpm_handle* h) {
     const double pad = cfg.scan_pad_px > 0 ? cfg.scan_pad_px : 32.0;
     const double cone = std::atan(std::sqrt(2.0) * (std::max(cfg.half_u, cfg.half_v) + pad) / cfg.f_ideal) + 0.002;
     const int S = h->n_stars;
-    // radius of the work-key disc: 1.07 x the disc of the array's area (measured optimum, flat within +-10 %:
-    // scripts/sweep_keyradius.sh); stmpm_set_tuning overrides it for that sweep (0 = count the whole candidate list)
-    double key_radius = std::atan(1.07 * std::sqrt(4.0 * cfg.half_u * cfg.half_v / M_PI) / cfg.f_ideal);
-    if (h->tune_key_radius_deg >= 0.0) key_radius = h->tune_key_radius_deg * M_PI / 180.0;
+    // Work key (round 2): the stars ON THE ARRAY FOOTPRINT — the ideal array centred on the lookup cell, in KEY_ROLLS
+    // orientation bins of the roll angle (a square array repeats every 90 degrees) — instead of round 1's disc of equal
+    // area: the disc / square mismatch was the larger part of the spread of the actual star count at a given key
+    // (lane occupancy of the star loop in 2 048-trial windows, simulated on the oracle: 0.82 -> 0.86).
+    // stmpm_set_tuning(key_radius_deg >= 0) brings the disc back for comparison (0 = count the whole candidate list).
+    const bool key_disc = h->tune_key_radius_deg >= 0.0;
+    const double key_radius = key_disc ? h->tune_key_radius_deg * M_PI / 180.0 : 0.0;
+    const double roll_period = (cfg.half_u == cfg.half_v) ? M_PI / 2 : M_PI;
+    h->key_roll_inv = (float)(1.0 / roll_period);
+    float roll_c[KEY_ROLLS], roll_s[KEY_ROLLS];
+    for (int k = 0; k < KEY_ROLLS; ++k) {
+        roll_c[k] = (float)std::cos((k + 0.5) * roll_period / KEY_ROLLS);
+        roll_s[k] = (float)std::sin((k + 0.5) * roll_period / KEY_ROLLS);
+    }
+    const float tan_u = (float)(cfg.half_u / cfg.f_ideal), tan_v = (float)(cfg.half_v / cfg.f_ideal);
     // stars in magnitude order, SoA floats
     std::vector<int> order(S);
     for (int i = 0; i < S; ++i) order[i] = i;
@@ -1094,7 +1109,7 @@ static int rebuild_lists(stmpm_handle* h) {
     std::vector<uint32_t> off(n_cells + 1, 0);
     std::vector<uint16_t> list;
     list.reserve((size_t)n_cells * 160);
-    std::vector<uint8_t> key_tab((size_t)n_cells * KEY_LEVELS, 0);   // candidate visits per cell at magnitude levels
+    std::vector<uint8_t> key_tab((size_t)n_cells * KEY_ROLLS * KEY_LEVELS, 0);   // footprint stars per cell, roll bin and magnitude level
     std::vector<float> smag(S);
     for (int i = 0; i < S; ++i) smag[i] = h->h_mag[order[i]];
     for (int b = 0; b < nb; ++b) {
@@ -1115,8 +1130,7 @@ static int rebuild_lists(stmpm_handle* h) {
         }
         const double reach = std::min(M_PI, cone + 1.1 * rho + 0.002);
         const float thresh = (float)std::cos(reach) - 4e-6f;
-        // work key: stars inside a disc of the field of view's area around the cell centre, i.e. the expected number of
-        // pre-filter SURVIVORS (a star evaluation costs ~6 candidate visits, so the sort equalises those)
+        // (disc variant of the key: stars inside a disc of `key_radius` around the cell centre)
         const float key_thresh = key_radius > 0 ? (float)std::cos(std::min(reach, key_radius)) : thresh;
         for (int rc = 0; rc < n_ra; ++rc) {
             const double ra = (rc + 0.5) * w;
@@ -1125,16 +1139,34 @@ static int rebuild_lists(stmpm_handle* h) {
             for (int i = 0; i < S; ++i) dots[i] = cx * sx[i] + cy * sy[i] + cz * sz[i];
             const size_t start = list.size();
             {
-                uint8_t* kt = key_tab.data() + (size_t)(bt[b].x + rc) * KEY_LEVELS;
-                int lev = 0, n_in = 0;
+                // body axes of a boresight at the cell centre with roll 0: C = Rz(ra) Ry(pi/2 - dec) Rz(0) (MODEL.md §2)
+                const float sd = (float)std::sin(dm), cdm = (float)std::cos(dm), sra = (float)std::sin(ra), cra = (float)std::cos(ra);
+                const float xb[3] = {cra * sd, sra * sd, -cdm}, yb[3] = {-sra, cra, 0.0f};
+                uint8_t* kt = key_tab.data() + (size_t)(bt[b].x + rc) * KEY_ROLLS * KEY_LEVELS;
+                int lev = 0, n_in[KEY_ROLLS] = {0};
+                auto close_levels = [&](float m) {   // stars come in magnitude order: close every level this star is fainter than
+                    while (lev < KEY_LEVELS && m > KEY_M0 + (lev + 1) / 16.0f) {
+                        for (int k = 0; k < KEY_ROLLS; ++k) kt[(size_t)k * KEY_LEVELS + lev] = (uint8_t)std::min(n_in[k], 255);
+                        ++lev;
+                    }
+                };
                 for (int i = 0; i < S; ++i) {
                     if (dots[i] < thresh) continue;
-                    // stars come in magnitude order: close every level this star is fainter than
-                    while (lev < KEY_LEVELS && smag[i] > KEY_M0 + (lev + 1) / 16.0f) kt[lev++] = (uint8_t)std::min(n_in, 255);
+                    close_levels(smag[i]);
                     list.push_back((uint16_t)order[i]);
-                    if (dots[i] >= key_thresh) ++n_in;
+                    if (key_disc) {
+                        if (dots[i] >= key_thresh) for (int k = 0; k < KEY_ROLLS; ++k) ++n_in[k];
+                    } else if (dots[i] > 0.05f) {
+                        // gnomonic coordinates (tangent of the field angles) on the roll-0 axes, rotated into each bin
+                        const float inv = 1.0f / dots[i];
+                        const float x0 = (xb[0] * sx[i] + xb[1] * sy[i] + xb[2] * sz[i]) * inv, y0 = (yb[0] * sx[i] + yb[1] * sy[i]) * inv;
+                        for (int k = 0; k < KEY_ROLLS; ++k) {
+                            const float xr = x0 * roll_c[k] + y0 * roll_s[k], yr = y0 * roll_c[k] - x0 * roll_s[k];
+                            if (std::fabs(xr) <= tan_u && std::fabs(yr) <= tan_v) ++n_in[k];
+                        }
+                    }
                 }
-                while (lev < KEY_LEVELS) kt[lev++] = (uint8_t)std::min(n_in, 255);
+                close_levels(INFINITY);
             }
             list.push_back((uint16_t)S);                                    // terminator: the +inf dummy star
             while ((list.size() - start) % PACK_N) list.push_back((uint16_t)S);
@@ -1447,7 +1479,7 @@ static int fill_common(stmpm_handle* h, KArgs& a, int precision) {
     a.inv_band_h = (float)((double)h->n_bands / M_PI);
     a.lk_band_tab = h->lk_band_tab; a.lk_off = h->lk_off; a.lk_list = h->lk_list; a.lk_bands = h->lk_bands;
     a.lk_inv_band_h = (float)((double)h->lk_bands / M_PI); a.lk_cone = h->lk_cone; a.tables = h->tables;
-    a.lk_key = h->lk_key;
+    a.lk_key = h->lk_key; a.key_roll_inv = h->key_roll_inv;
     a.f_ideal = h->cfg.f_ideal; a.f_ideal2 = h->cfg.f_ideal * h->cfg.f_ideal; a.half_u = h->cfg.half_u; a.half_v = h->cfg.half_v; a.n_min = h->cfg.n_min;
     a.hist_shift = 52 - h->cfg.hist_log2_sub; a.n_bins = h->n_bins;
     a.stats_len = STMPM_STATS_HEAD + h->n_bins;

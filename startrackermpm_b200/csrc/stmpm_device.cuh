@@ -33,6 +33,7 @@ constexpr int WIN_STAGED = 2048;      // default window, pre-sampled columns sta
 constexpr int WIN_RNG = 2048;         // default window, native RNG: no gathers, so the widest sort wins
 constexpr int KEY_LEVELS = 128;   // work-key table: candidate visits per lookup cell at magnitude levels KEY_M0 + (k+1)/16
 constexpr float KEY_M0 = 1.0f;
+constexpr int KEY_ROLLS = 8;      // work-key table: orientation bins of the array footprint (roll modulo its symmetry period)
 constexpr int KEY_BINS = 256;     // sort bins (= candidate visits, saturated)
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u, PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
 constexpr uint32_t PHILOX2_M = 0xD256D193u;
@@ -630,13 +631,14 @@ __device__ __forceinline__ void sample_params(const DistDev& d, const MathTables
 // ra, dec, MAX_MAGNITUDE of a native-RNG trial only (the work key needs nothing else): Philox blocks 0 and 3
 __device__ __forceinline__ void sample_key_params(const DistDev& d, const MathTables* __restrict__ T, uint32_t t_lo,
                                                   uint32_t t_hi, uint32_t k0, uint32_t k1, double& ra, double& dec,
-                                                  double& maxmag) {
+                                                  double& roll, double& maxmag) {
     uint32_t w0, w1, w2, w3, v0, v1, v2, v3;
     philox4x32_10(t_lo, t_hi, 0u, TAG_PARA, k0, k1, w0, w1, w2, w3);
     philox4x32_10(t_lo, t_hi, 3u, TAG_PARA, k0, k1, v0, v1, v2, v3);
     const double fov = 0.17453292519943295, PI = 3.141592653589793;
     ra = fov + (2.0 * PI - 2.0 * fov) * u01(w0);
     dec = (-0.5 * PI + fov) + (PI - 2.0 * fov) * u01(w1);
+    roll = -PI + 2.0 * PI * u01(w2);
     double z8, z9;
     box_muller_tab(T, v0, v1, z8, z9);      // words 12, 13 -> normals 8, 9
     maxmag = d.mean[9] + d.sigma[9] * z9;
