@@ -9,6 +9,7 @@
 #include "stmpm_device.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -1418,16 +1419,18 @@ static int launch_trials(stmpm_handle* h, KArgs& a, cudaStream_t st) {
     auto kern = trials_kernel<MODE, PREC, INSTR>;
     // the attribute belongs to the FUNCTION (per device), not to a handle: keep a per-instantiation, per-device maximum so a
     // second engine with a smaller catalog can never lower it under a live one
-    static size_t attr_set[64] = {};
-    static std::mutex attr_mutex;                       // handles on different host threads may launch concurrently
-    std::lock_guard<std::mutex> attr_lock(attr_mutex);
-    size_t& cached = attr_set[h->device & 63];
-    if (cached < smem_bytes) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        // leave the rest of the unified array to L1: register spills and the permuted input gathers live there
-        const int pct = (int)std::min<size_t>(100, (smem_bytes + 1024) * 100 / (size_t)h->prop.sharedMemPerMultiprocessor + 1);
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-        cached = smem_bytes;
+    static std::atomic<size_t> attr_set[64];            // zero-initialised
+    static std::mutex attr_mutex;                       // taken only to RAISE the attribute (first launch per catalog size)
+    std::atomic<size_t>& cached = attr_set[h->device & 63];
+    if (cached.load(std::memory_order_acquire) < smem_bytes) {
+        std::lock_guard<std::mutex> attr_lock(attr_mutex);
+        if (cached.load(std::memory_order_relaxed) < smem_bytes) {
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+            // leave the rest of the unified array to L1: register spills and the permuted input gathers live there
+            const int pct = (int)std::min<size_t>(100, (smem_bytes + 1024) * 100 / (size_t)h->prop.sharedMemPerMultiprocessor + 1);
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+            cached.store(smem_bytes, std::memory_order_release);
+        }
     }
     const int n_sm = h->prop.multiProcessorCount;
     // work units: (segment, part).  A unit is consumed in CTA-wide sort windows of `win` trials; small launches shrink
