@@ -246,8 +246,8 @@ def run_ours(args):
 
     n = int(args.trials)
     eng = TrialEngine(local, f_ideal=F_IDEAL)
-    if args.window or args.key_radius_deg >= 0 or args.no_stage:
-        eng.set_tuning(args.window, args.key_radius_deg, not args.no_stage)
+    if args.window or args.key_radius_deg >= 0 or args.stage or args.key_table >= 0:
+        eng.set_tuning(args.window, args.key_radius_deg, args.stage, args.key_table)
     if args.host_chunk:
         eng.set_host_pipeline(args.host_chunk)
     d = make_dist(WORKLOADS[args.workload][0], WORKLOADS[args.workload][1], THERMAL_COEF)
@@ -455,7 +455,8 @@ def main():
     ap.add_argument("--workload", default="default", choices=sorted(WORKLOADS),
                     help="default = BASELINE configs[1]; all_visible = MAX_MAGNITUDE 20 (sensitivity.py:112), ~60 stars per trial")
     ap.add_argument("--host-chunk", type=int, default=0, help="tuning sweep: trials per stage of the host pipelines (0 = 2^22)")
-    ap.add_argument("--no-stage", action="store_true", help="tuning sweep: gather the pre-sampled columns (round 1) instead of staging them")
+    ap.add_argument("--stage", action="store_true", help="tuning sweep: stage the pre-sampled columns in key order (measured slower)")
+    ap.add_argument("--key-table", type=int, default=-1, help="tuning sweep: -1 per mode, 0 disc, 1 array footprint")
     ap.add_argument("--window", type=int, default=0, help="tuning sweep: CTA sort window in trials (0 = default)")
     ap.add_argument("--key-radius-deg", type=float, default=-1.0, help="tuning sweep: work-key disc radius (<0 = default)")
     args = ap.parse_args()

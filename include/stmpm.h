@@ -117,10 +117,12 @@ int stmpm_set_sensor(stmpm_t* h, const stmpm_sensor_cfg* cfg);
 /* Performance knobs of the trial kernel; results never depend on them (tests/test_gpu_parity.py checks bit-identity).
  * window: trials per CTA sort window (multiple of 32, <= 2048; 0 = the measured default per mode).  key_radius_deg: radius
  * of the work-key disc (< 0 = default, 0 = whole candidate list); changing it synchronises the device and rebuilds the
- * key table.  stage_columns: non-zero (default) = pre-sampled launches re-write each sort window's columns in key order to
- * an L2-resident scratch (allocated per launch in stream order) so that warps read them coalesced; 0 = gather them.
+ * key table.  stage_columns: non-zero = pre-sampled launches re-write each sort window's columns in key order to an
+ * L2-resident scratch (allocated per launch in stream order) and read them coalesced; 0 (default: staging measured
+ * slower) = gather them.  key_table: -1 (default) = disc table for pre-sampled launches, array-footprint
+ * table for native-RNG launches; 0 / 1 force the disc / footprint table.
  * Not to be called while launches on this handle are in flight. */
-int stmpm_set_tuning(stmpm_t* h, int32_t window, double key_radius_deg, int32_t stage_columns);
+int stmpm_set_tuning(stmpm_t* h, int32_t window, double key_radius_deg, int32_t stage_columns, int32_t key_table);
 
 /* Packed statistics buffer (MODEL.md §9): STMPM_STATS_HEAD doubles then 34 * 2^hist_log2_sub histogram bins; every entry
  * but x_max is a sum, so ranks merge with one allreduce(sum).  Host-only helpers (no GPU needed). */

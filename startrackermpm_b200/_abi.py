@@ -82,7 +82,7 @@ def load():
     lib.stmpm_device_info.argtypes = [vp, P(i32), P(i64), P(i32), P(i32)]
     lib.stmpm_set_catalog.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
     lib.stmpm_set_sensor.argtypes = [vp, P(SensorCfg)]
-    lib.stmpm_set_tuning.argtypes = [vp, i32, dbl, i32]
+    lib.stmpm_set_tuning.argtypes = [vp, i32, dbl, i32, i32]
     lib.stmpm_stats_len.argtypes = [i32, P(i64)]
     lib.stmpm_stats_finalize.argtypes = [i32, vp, P(Summary)]
     lib.stmpm_trials_presampled.argtypes = [vp, C.c_int, i64, u64, i64, P(vp), vp, vp, vp, vp]

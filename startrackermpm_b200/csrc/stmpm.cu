@@ -38,6 +38,7 @@ struct KArgs {
     float lk_inv_band_h, lk_cone; // a trial whose scan cone exceeds lk_cone takes the sky-grid scan instead
     const MathTables* tables;
     const uint8_t* lk_key;        // [n_lk_cells][KEY_ROLLS][KEY_LEVELS]: stars with mag <= KEY_M0 + (k+1)/16 on the array footprint, saturated at 255
+    int key_rolls;                // orientation bins of the table handed to this launch (1 = the disc table, KEY_ROLLS = the footprint table)
     float key_roll_inv;           // 1 / symmetry period of the footprint's orientation (2/pi for a square array, 1/pi otherwise)
     int win;                      // trials per CTA sort window (multiple of 32, <= WIN_MAX)
     int windows_per_unit;         // ceil(part_len / win)
@@ -93,6 +94,16 @@ __device__ __forceinline__ double4 ld_rec(const StarRec* p) {
 __device__ __forceinline__ void red_add_f64(double* p, double v) {
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
 }
+// staged-column accesses: cache-global by default; STMPM_STAGE_CS = streaming (evict-first) hints, an experiment against
+// L2 pollution by the 63 MB of windows in flight
+#if defined(STMPM_STAGE_CS)
+#define STAGE_ST __stcs
+#define STAGE_LD __ldcs
+#else
+#define STAGE_ST __stcg
+#define STAGE_LD __ldcg
+#endif
+
 // Scheduler watchdog: the window / group waits below are bounded by WALL TIME (%globaltimer), not by a poll count — a poll
 // budget can run out under compute-sanitizer, cuda-gdb or preemption without any deadlock.  On expiry the warp records
 // STMPM_E_WATCHDOG in a host-mapped status word and leaves its trial loop cleanly (no __trap: a trap is a sticky,
@@ -194,9 +205,9 @@ __device__ __forceinline__ int work_key(const KArgs& a, const int2* __restrict__
     const int cell = lookup_cell(s_lkband, a.lk_bands, a.lk_inv_band_h, raf, decf);
     float t = rollf * a.key_roll_inv;
     t -= floorf(t);
-    const int rb = min(KEY_ROLLS - 1, max(0, (int)(t * (float)KEY_ROLLS)));
+    const int rb = min(a.key_rolls - 1, max(0, (int)(t * (float)a.key_rolls)));
     const int lev = min(KEY_LEVELS - 1, (int)floorf((mm - KEY_M0) * 16.0f));
-    return lev < 0 ? 0 : (int)__ldg(a.lk_key + ((size_t)cell * KEY_ROLLS + rb) * KEY_LEVELS + lev);
+    return lev < 0 ? 0 : (int)__ldg(a.lk_key + ((size_t)cell * a.key_rolls + rb) * KEY_LEVELS + lev);
 }
 
 // ------------------------------------------------------------------------------------------------ fallback trial
@@ -414,7 +425,8 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                         kra[q] = kdec[q] = kroll[q] = 0.0; kmm[q] = -100.0;
                         if (r < nw) {
                             kra[q] = __ldg(a.cols[0] + rec0 + r); kdec[q] = __ldg(a.cols[1] + rec0 + r);
-                            kroll[q] = __ldg(a.cols[2] + rec0 + r); kmm[q] = __ldg(a.cols[12] + rec0 + r);
+                            if (a.key_rolls > 1) kroll[q] = __ldg(a.cols[2] + rec0 + r);
+                            kmm[q] = __ldg(a.cols[12] + rec0 + r);
                         }
                     }
                     // pull the round's other ten columns into L2 (one 32-byte sector = 4 trials per lane): the groups gather
@@ -422,7 +434,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                     // a quarter as long as DRAM misses do, and the LSU pipe they share with shared memory stays fluid
                     if (r0 + 4 * lane < nw) {          // (with staging too: the copy below then reads L2 hits)
 #pragma unroll
-                        for (int cI = 3; cI < 12; ++cI) prefetch_l2(a.cols[cI] + rec0 + r0 + 4 * lane);
+                        for (int cI = 2; cI < 12; ++cI) prefetch_l2(a.cols[cI] + rec0 + r0 + 4 * lane);
                     }
                     int kkey[4];
 #pragma unroll
@@ -490,7 +502,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
 #pragma unroll
                         for (int cI = 0; cI < STMPM_NCOLS; ++cI) v[cI] = __ldcs(a.cols[cI] + rec0 + r);
 #pragma unroll
-                        for (int cI = 0; cI < STMPM_NCOLS; ++cI) __stcg(sg + (size_t)cI * WIN_MAX + rank, v[cI]);
+                        for (int cI = 0; cI < STMPM_NCOLS; ++cI) STAGE_ST(sg + (size_t)cI * WIN_MAX + rank, v[cI]);
                     }
                 }
                 __threadfence();
@@ -566,13 +578,13 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                 if (MODE == 0 && a.stage != nullptr) {
                     if (valid) {                                // coalesced: lane q reads word q of each staged column
                         const double* sg = a.stage + ((size_t)blockIdx.x * 2 + (size_t)(grp_w & 1)) * (size_t)(STMPM_NCOLS * WIN_MAX) + grp_q;
-                        p.ra = __ldcg(sg);                      p.dec = __ldcg(sg + WIN_MAX);
-                        p.roll = __ldcg(sg + 2 * WIN_MAX);      p.f = __ldcg(sg + 3 * WIN_MAX);
-                        p.ex = __ldcg(sg + 4 * WIN_MAX);        p.ey = __ldcg(sg + 5 * WIN_MAX);
-                        p.ez = __ldcg(sg + 6 * WIN_MAX);        p.phi = __ldcg(sg + 7 * WIN_MAX);
-                        p.theta = __ldcg(sg + 8 * WIN_MAX);     p.psi = __ldcg(sg + 9 * WIN_MAX);
-                        p.devx = __ldcg(sg + 10 * WIN_MAX);     p.devy = __ldcg(sg + 11 * WIN_MAX);
-                        p.maxmag = __ldcg(sg + 12 * WIN_MAX);
+                        p.ra = STAGE_LD(sg);                      p.dec = STAGE_LD(sg + WIN_MAX);
+                        p.roll = STAGE_LD(sg + 2 * WIN_MAX);      p.f = STAGE_LD(sg + 3 * WIN_MAX);
+                        p.ex = STAGE_LD(sg + 4 * WIN_MAX);        p.ey = STAGE_LD(sg + 5 * WIN_MAX);
+                        p.ez = STAGE_LD(sg + 6 * WIN_MAX);        p.phi = STAGE_LD(sg + 7 * WIN_MAX);
+                        p.theta = STAGE_LD(sg + 8 * WIN_MAX);     p.psi = STAGE_LD(sg + 9 * WIN_MAX);
+                        p.devx = STAGE_LD(sg + 10 * WIN_MAX);     p.devy = STAGE_LD(sg + 11 * WIN_MAX);
+                        p.maxmag = STAGE_LD(sg + 12 * WIN_MAX);
                     } else {
                         p.ra = p.dec = p.roll = 0.0; p.f = 1000.0; p.ex = p.ey = p.ez = p.phi = p.theta = p.psi = 0.0;
                         p.devx = p.devy = 0.0; p.maxmag = -100.0;
@@ -1018,7 +1030,9 @@ struct stmpm_handle {
     int lk_bands = 0;
     float lk_cone = -1.0f;
     MathTables* tables = nullptr;
-    uint8_t* lk_key = nullptr;    // work-key table [n_lk_cells][KEY_ROLLS][KEY_LEVELS]
+    uint8_t* lk_key = nullptr;    // footprint work-key table [n_lk_cells][KEY_ROLLS][KEY_LEVELS]
+    uint8_t* lk_key_disc = nullptr;   // disc work-key table [n_lk_cells][KEY_LEVELS]
+    int tune_key_table = -1;      // -1 = per mode (disc for pre-sampled, footprint for native RNG), 0 = disc, 1 = footprint
     float key_roll_inv = 0.63661977f;
     bool have_catalog = false, have_sensor = false;
     stmpm_sensor_cfg cfg{};
@@ -1038,7 +1052,7 @@ struct stmpm_handle {
     // tuning (stmpm_set_tuning): 0 / negative = the measured defaults
     int tune_window = 0;
     double tune_key_radius_deg = -1.0;
-    int tune_stage = 1;                   // sorted parameter staging for pre-sampled launches (0 = round 1's gathers)
+    int tune_stage = 0;                   // sorted parameter staging for pre-sampled launches: measured slower, off by default
     int* status_host = nullptr;           // pinned + mapped: the kernels' watchdog word (stmpm_check)
     int* status_dev = nullptr;
     cudaMemPool_t pool = nullptr;         // stream-ordered per-launch storage (staging scratch, distribution arrays)
@@ -1074,13 +1088,18 @@ static int rebuild_lists(stmpm_handle* h) {
     const double pad = cfg.scan_pad_px > 0 ? cfg.scan_pad_px : 32.0;
     const double cone = std::atan(std::sqrt(2.0) * (std::max(cfg.half_u, cfg.half_v) + pad) / cfg.f_ideal) + 0.002;
     const int S = h->n_stars;
-    // Work key (round 2): the stars ON THE ARRAY FOOTPRINT — the ideal array centred on the lookup cell, in KEY_ROLLS
-    // orientation bins of the roll angle (a square array repeats every 90 degrees) — instead of round 1's disc of equal
-    // area: the disc / square mismatch was the larger part of the spread of the actual star count at a given key
-    // (lane occupancy of the star loop in 2 048-trial windows, simulated on the oracle: 0.82 -> 0.86).
-    // stmpm_set_tuning(key_radius_deg >= 0) brings the disc back for comparison (0 = count the whole candidate list).
-    const bool key_disc = h->tune_key_radius_deg >= 0.0;
-    const double key_radius = key_disc ? h->tune_key_radius_deg * M_PI / 180.0 : 0.0;
+    // Two work-key tables (the key = the number of stars a trial is expected to evaluate; it only orders the work):
+    //  * DISC table [cell][level] (5 MB, L2-resident): stars inside a disc of 1.07 x the radius of the array's area around the
+    //    cell centre (measured optimum, flat within +-10 %: scripts/sweep_keyradius.sh; stmpm_set_tuning overrides the radius,
+    //    0 = count the whole candidate list).  Used by pre-sampled launches: their 256-trial windows turn over every eight
+    //    groups, so the key pass is latency-critical and must hit L2.
+    //  * FOOTPRINT table [cell][KEY_ROLLS][level] (42 MB): the stars ON THE ARRAY — the ideal array centred on the cell, in
+    //    KEY_ROLLS orientation bins of the roll angle (a square array repeats every 90 degrees).  The disc / square mismatch is
+    //    the larger part of the spread of the actual star count at a given key (star-loop lane occupancy in 2 048-trial
+    //    windows, simulated on the oracle: 0.82 -> 0.86).  Used by native-RNG launches (2 048-trial windows: one key pass per
+    //    64 groups, its DRAM misses are hidden): +2.4 % measured; on pre-sampled launches it measured -4.7 % (round 2).
+    double key_radius = std::atan(1.07 * std::sqrt(4.0 * cfg.half_u * cfg.half_v / M_PI) / cfg.f_ideal);
+    if (h->tune_key_radius_deg >= 0.0) key_radius = h->tune_key_radius_deg * M_PI / 180.0;
     const double roll_period = (cfg.half_u == cfg.half_v) ? M_PI / 2 : M_PI;
     h->key_roll_inv = (float)(1.0 / roll_period);
     float roll_c[KEY_ROLLS], roll_s[KEY_ROLLS];
@@ -1111,6 +1130,7 @@ static int rebuild_lists(stmpm_handle* h) {
     std::vector<uint16_t> list;
     list.reserve((size_t)n_cells * 160);
     std::vector<uint8_t> key_tab((size_t)n_cells * KEY_ROLLS * KEY_LEVELS, 0);   // footprint stars per cell, roll bin and magnitude level
+    std::vector<uint8_t> key_disc((size_t)n_cells * KEY_LEVELS, 0);               // disc stars per cell and magnitude level
     std::vector<float> smag(S);
     for (int i = 0; i < S; ++i) smag[i] = h->h_mag[order[i]];
     for (int b = 0; b < nb; ++b) {
@@ -1144,10 +1164,12 @@ static int rebuild_lists(stmpm_handle* h) {
                 const float sd = (float)std::sin(dm), cdm = (float)std::cos(dm), sra = (float)std::sin(ra), cra = (float)std::cos(ra);
                 const float xb[3] = {cra * sd, sra * sd, -cdm}, yb[3] = {-sra, cra, 0.0f};
                 uint8_t* kt = key_tab.data() + (size_t)(bt[b].x + rc) * KEY_ROLLS * KEY_LEVELS;
-                int lev = 0, n_in[KEY_ROLLS] = {0};
+                uint8_t* kd = key_disc.data() + (size_t)(bt[b].x + rc) * KEY_LEVELS;
+                int lev = 0, n_in[KEY_ROLLS] = {0}, n_disc = 0;
                 auto close_levels = [&](float m) {   // stars come in magnitude order: close every level this star is fainter than
                     while (lev < KEY_LEVELS && m > KEY_M0 + (lev + 1) / 16.0f) {
                         for (int k = 0; k < KEY_ROLLS; ++k) kt[(size_t)k * KEY_LEVELS + lev] = (uint8_t)std::min(n_in[k], 255);
+                        kd[lev] = (uint8_t)std::min(n_disc, 255);
                         ++lev;
                     }
                 };
@@ -1155,9 +1177,8 @@ static int rebuild_lists(stmpm_handle* h) {
                     if (dots[i] < thresh) continue;
                     close_levels(smag[i]);
                     list.push_back((uint16_t)order[i]);
-                    if (key_disc) {
-                        if (dots[i] >= key_thresh) for (int k = 0; k < KEY_ROLLS; ++k) ++n_in[k];
-                    } else if (dots[i] > 0.05f) {
+                    if (dots[i] >= key_thresh) ++n_disc;
+                    if (dots[i] > 0.05f) {
                         // gnomonic coordinates (tangent of the field angles) on the roll-0 axes, rotated into each bin
                         const float inv = 1.0f / dots[i];
                         const float x0 = (xb[0] * sx[i] + xb[1] * sy[i] + xb[2] * sz[i]) * inv, y0 = (yb[0] * sx[i] + yb[1] * sy[i]) * inv;
@@ -1187,8 +1208,11 @@ static int rebuild_lists(stmpm_handle* h) {
     h->lk_bands = nb;
     h->lk_cone = (float)cone;
     cudaFree(h->lk_key); h->lk_key = nullptr;
+    cudaFree(h->lk_key_disc); h->lk_key_disc = nullptr;
     CK(cudaMalloc(&h->lk_key, key_tab.size()));
     CK(cudaMemcpy(h->lk_key, key_tab.data(), key_tab.size(), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&h->lk_key_disc, key_disc.size()));
+    CK(cudaMemcpy(h->lk_key_disc, key_disc.data(), key_disc.size(), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -1246,7 +1270,7 @@ extern "C" int stmpm_destroy(stmpm_t* h) {
     cudaFree(h->cat32); cudaFree(h->cat64); cudaFree(h->cell_start); cudaFree(h->band_tab);
     cudaFree(h->stage_stats); cudaFree(h->counters);
     cudaFree(h->lk_band_tab); cudaFree(h->lk_off); cudaFree(h->lk_list); cudaFree(h->tables);
-    cudaFree(h->lk_key);
+    cudaFree(h->lk_key); cudaFree(h->lk_key_disc);
     free_stage(h);
     for (int i = 0; i < stmpm_handle::NBUF; ++i) if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
     if (h->pool) { cudaDeviceSynchronize(); cudaMemPoolDestroy(h->pool); }
@@ -1334,9 +1358,11 @@ extern "C" int stmpm_set_sensor(stmpm_t* h, const stmpm_sensor_cfg* cfg) {
     return rebuild_lists(h);
 }
 
-extern "C" int stmpm_set_tuning(stmpm_t* h, int32_t window, double key_radius_deg, int32_t stage_columns) {
+extern "C" int stmpm_set_tuning(stmpm_t* h, int32_t window, double key_radius_deg, int32_t stage_columns, int32_t key_table) {
     if (!h) return fail(STMPM_E_ARG, "stmpm_set_tuning: null handle");
+    if (key_table < -1 || key_table > 1) return fail(STMPM_E_ARG, "stmpm_set_tuning: key_table must be -1 (per mode), 0 (disc) or 1 (footprint)");
     h->tune_stage = stage_columns != 0;
+    h->tune_key_table = key_table;
     if (window < 0 || window > WIN_MAX || window % 32) return fail(STMPM_E_ARG, "stmpm_set_tuning: window must be 0 (default) or a multiple of 32 up to 2048");
     const bool rebuild = key_radius_deg != h->tune_key_radius_deg;
     h->tune_window = window;
@@ -1435,6 +1461,9 @@ static int launch_trials(stmpm_handle* h, KArgs& a, cudaStream_t st) {
     const int n_sm = h->prop.multiProcessorCount;
     // work units: (segment, part).  A unit is consumed in CTA-wide sort windows of `win` trials; small launches shrink
     // the window so that more CTAs have work.
+    const bool footprint_key = h->tune_key_table < 0 ? (MODE == 1) : (h->tune_key_table == 1);
+    a.lk_key = footprint_key ? h->lk_key : h->lk_key_disc;
+    a.key_rolls = footprint_key ? KEY_ROLLS : 1;
     const long long tps = a.trials_per_segment;
     const long long total = tps * a.n_segments;
     // sorted parameter staging (pre-sampled mode): worth its scratch from a few windows per CTA on
@@ -1482,7 +1511,7 @@ static int fill_common(stmpm_handle* h, KArgs& a, int precision) {
     a.inv_band_h = (float)((double)h->n_bands / M_PI);
     a.lk_band_tab = h->lk_band_tab; a.lk_off = h->lk_off; a.lk_list = h->lk_list; a.lk_bands = h->lk_bands;
     a.lk_inv_band_h = (float)((double)h->lk_bands / M_PI); a.lk_cone = h->lk_cone; a.tables = h->tables;
-    a.lk_key = h->lk_key; a.key_roll_inv = h->key_roll_inv;
+    a.lk_key = h->lk_key; a.key_rolls = KEY_ROLLS; a.key_roll_inv = h->key_roll_inv;   // launch_trials picks the table per mode
     a.f_ideal = h->cfg.f_ideal; a.f_ideal2 = h->cfg.f_ideal * h->cfg.f_ideal; a.half_u = h->cfg.half_u; a.half_v = h->cfg.half_v; a.n_min = h->cfg.n_min;
     a.hist_shift = 52 - h->cfg.hist_log2_sub; a.n_bins = h->n_bins;
     a.stats_len = STMPM_STATS_HEAD + h->n_bins;

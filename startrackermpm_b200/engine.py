@@ -80,11 +80,13 @@ class TrialEngine:
         self.hist_log2_sub = int(hist_log2_sub)
         self.stats_len = stats_len(hist_log2_sub)
 
-    def set_tuning(self, window: int = 0, key_radius_deg: float = -1.0, stage_columns: bool = True) -> None:
+    def set_tuning(self, window: int = 0, key_radius_deg: float = -1.0, stage_columns: bool = False, key_table: int = -1) -> None:
         """Performance knobs (results never depend on them): CTA sort window in trials (0 = default), work-key disc
-        radius in degrees (< 0 = default), sorted parameter staging of pre-sampled columns (default on).  Replaces round
-        1's STMPM_WIN / STMPM_KEY_RADIUS_DEG environment variables."""
-        _abi.check(self._lib.stmpm_set_tuning(self._h, int(window), float(key_radius_deg), int(bool(stage_columns))))
+        radius in degrees (< 0 = default), sorted parameter staging of pre-sampled columns (default off: measured slower),
+        work-key table (-1 = per mode, 0 = disc, 1 = array footprint).  Replaces round 1's STMPM_WIN /
+        STMPM_KEY_RADIUS_DEG environment variables."""
+        _abi.check(self._lib.stmpm_set_tuning(self._h, int(window), float(key_radius_deg), int(bool(stage_columns)),
+                                              int(key_table)))
 
     def check(self) -> None:
         """After synchronising a stream handed to the *_device calls: raises if a kernel hit its scheduler watchdog."""

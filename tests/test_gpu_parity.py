@@ -386,7 +386,7 @@ def test_sorted_parameter_staging_changes_no_record(engine):
     try:
         for win in (0, 2048, 1024, 480, 64):
             for prec in (64, 32):
-                engine.set_tuning(window=win, stage_columns=True)
+                engine.set_tuning(window=win, stage_columns=True, key_table=1 - (win // 64) % 2)
                 e = torch.full((n,), -7.0, dtype=torch.float64, device="cuda")
                 nd = torch.full((n,), -7, dtype=torch.int32, device="cuda")
                 st = torch.zeros(engine.stats_len, dtype=torch.float64, device="cuda")
