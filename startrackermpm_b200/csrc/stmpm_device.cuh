@@ -594,7 +594,17 @@ __device__ __forceinline__ double quest_error_arcsec(const double* __restrict__ 
     const double X1 = alpha * Z1 + beta * SZ1 + (S01 * SZ0 + S11 * SZ1 + S12 * SZ2);
     const double X2 = alpha * Z2 + beta * SZ2 + (S02 * SZ0 + S12 * SZ1 + S22 * SZ2);
     const double vn = sqrt(X0 * X0 + X1 * X1 + X2 * X2);
-    return 2.0 * atan2(vn, fabs(gamma)) * RAD2ARCSEC;
+    // theta = 2 atan2(|q_v|, |q_w|).  Attitude errors are arcseconds to a few degrees: for t = |q_v| / |q_w| <= 0.03 the
+    // odd series to t^9 is exact to 5e-17 relative (next term t^10 / 11) and replaces libm's ~90-instruction atan2; anything
+    // larger (or a zero / non-finite gamma: the comparison is then false) takes libm.
+    const double ag = fabs(gamma);
+    const double t = fast_div(vn, ag);
+    if (t <= 0.03) {
+        const double t2 = t * t;
+        const double p = fma(t2, fma(t2, fma(t2, fma(t2, 1.0 / 9.0, -1.0 / 7.0), 0.2), -1.0 / 3.0), 1.0);
+        return (2.0 * RAD2ARCSEC) * (t * p);
+    }
+    return 2.0 * atan2(vn, ag) * RAD2ARCSEC;
 }
 
 // MODEL.md §6: native-RNG parameter draw for one trial.
