@@ -250,6 +250,8 @@ def run_ours(args):
         eng.set_tuning(args.window, args.key_radius_deg, args.stage, args.key_table)
     if args.host_chunk:
         eng.set_host_pipeline(args.host_chunk)
+    if args.pipeline >= 0:
+        eng.set_pipeline(args.pipeline)
     d = make_dist(WORKLOADS[args.workload][0], WORKLOADS[args.workload][1], THERMAL_COEF)
     trial0 = rank * n                                      # weak scaling: every rank its own global trial-index range
     cols = torch.empty((13, n), dtype=torch.float64, device="cuda")
@@ -455,6 +457,7 @@ def main():
     ap.add_argument("--workload", default="default", choices=sorted(WORKLOADS),
                     help="default = BASELINE configs[1]; all_visible = MAX_MAGNITUDE 20 (sensitivity.py:112), ~60 stars per trial")
     ap.add_argument("--host-chunk", type=int, default=0, help="tuning sweep: trials per stage of the host pipelines (0 = 2^22)")
+    ap.add_argument("--pipeline", type=int, default=-1, help="tuning sweep: -1 auto, 0 single kernel, 1 split pipeline")
     ap.add_argument("--stage", action="store_true", help="tuning sweep: stage the pre-sampled columns in key order (measured slower)")
     ap.add_argument("--key-table", type=int, default=-1, help="tuning sweep: -1 per mode, 0 disc, 1 array footprint")
     ap.add_argument("--window", type=int, default=0, help="tuning sweep: CTA sort window in trials (0 = default)")

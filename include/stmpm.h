@@ -124,6 +124,12 @@ int stmpm_set_sensor(stmpm_t* h, const stmpm_sensor_cfg* cfg);
  * Not to be called while launches on this handle are in flight. */
 int stmpm_set_tuning(stmpm_t* h, int32_t window, double key_radius_deg, int32_t stage_columns, int32_t key_table);
 
+/* Pre-sampled launches of one segment run either as ONE persistent kernel or as the two-kernel split pipeline (candidate scan
+ * -> counting sort of the trials by survivor count -> exact star loop + solve over warps of identical star counts; DESIGN.md
+ * §3).  -1 (default) = the split pipeline for launches of >= 2^21 trials, until a chunk falls back (star-rich / wide-cone
+ * workloads, decided on the device), 0 = always the single kernel, 1 = always try the split.  Records are identical. */
+int stmpm_set_pipeline(stmpm_t* h, int32_t pipeline);
+
 /* Packed statistics buffer (MODEL.md §9): STMPM_STATS_HEAD doubles then 34 * 2^hist_log2_sub histogram bins; every entry
  * but x_max is a sum, so ranks merge with one allreduce(sum).  Host-only helpers (no GPU needed). */
 int stmpm_stats_len(int32_t hist_log2_sub, int64_t* n_doubles);

@@ -22,7 +22,7 @@ NORMAL_PARAMS = ("FOCAL_LENGTH", "F_ARR_EPS_X", "F_ARR_EPS_Y", "F_ARR_EPS_Z", "F
 
 # every symbol include/stmpm.h declares (tests check that the library exports each one)
 EXPORTS = ("stmpm_last_error", "stmpm_version", "stmpm_create", "stmpm_destroy", "stmpm_check", "stmpm_device_info",
-           "stmpm_set_catalog", "stmpm_set_sensor", "stmpm_set_tuning", "stmpm_stats_len", "stmpm_stats_finalize",
+           "stmpm_set_catalog", "stmpm_set_sensor", "stmpm_set_tuning", "stmpm_set_pipeline", "stmpm_stats_len", "stmpm_stats_finalize",
            "stmpm_trials_presampled", "stmpm_trials_presampled_ex", "stmpm_trials_rng", "stmpm_fill_presampled", "stmpm_run_presampled_host", "stmpm_run_presampled_host_ex",
            "stmpm_run_rng_host", "stmpm_run_rng_host_compact", "stmpm_set_host_pipeline", "stmpm_host_copy_roofline", "stmpm_mc_converge", "stmpm_toolplot_failrate", "stmpm_column_hist", "stmpm_toolplot_reduce", "stmpm_fma_peak", "stmpm_work_counters", "stmpm_debug_box_muller", "stmpm_debug_box_muller_f32", "stmpm_launch_count")
 
@@ -83,6 +83,7 @@ def load():
     lib.stmpm_set_catalog.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
     lib.stmpm_set_sensor.argtypes = [vp, P(SensorCfg)]
     lib.stmpm_set_tuning.argtypes = [vp, i32, dbl, i32, i32]
+    lib.stmpm_set_pipeline.argtypes = [vp, i32]
     lib.stmpm_stats_len.argtypes = [i32, P(i64)]
     lib.stmpm_stats_finalize.argtypes = [i32, vp, P(Summary)]
     lib.stmpm_trials_presampled.argtypes = [vp, C.c_int, i64, u64, i64, P(vp), vp, vp, vp, vp]

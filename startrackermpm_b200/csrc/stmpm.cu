@@ -746,6 +746,8 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
         flush_moments(a.stats + cur_seg * a.stats_len, lane, acc_ok, acc_fail, acc_ndet, acc_x, acc_xx, acc_max);
 }
 
+#include "stmpm_split.cuh"
+
 // ------------------------------------------------------------------------------------------------ generator kernel
 __global__ void __launch_bounds__(256) fill_presampled_kernel(long long n, long long trial0, uint32_t k0, uint32_t k1,
                                                               DistDev dist, const MathTables* __restrict__ tab, double* c0, double* c1, double* c2,
@@ -1067,8 +1069,9 @@ struct stmpm_handle {
     int tune_window = 0;
     double tune_key_radius_deg = -1.0;
     int tune_stage = 0;                   // sorted parameter staging for pre-sampled launches: measured slower, off by default
-    int* status_host = nullptr;           // pinned + mapped: the kernels' watchdog word (stmpm_check)
+    int* status_host = nullptr;           // pinned + mapped: [0] the kernels' watchdog word (stmpm_check), [1] split-pipeline fallbacks seen
     int* status_dev = nullptr;
+    int tune_pipeline = -1;               // -1 auto, 0 single kernel, 1 two-kernel split pipeline (pre-sampled, one segment)
     cudaMemPool_t pool = nullptr;         // stream-ordered per-launch storage (staging scratch, distribution arrays)
     long long host_chunk = HOST_CHUNK;    // trials per stage of the host pipelines
 };
@@ -1251,8 +1254,8 @@ extern "C" int stmpm_create(stmpm_t** out, int device) {
         stmpm_host_tables(&mt);
         CK(cudaMalloc(&h->tables, sizeof(MathTables)));
         CK(cudaMemcpy(h->tables, &mt, sizeof(MathTables), cudaMemcpyHostToDevice));
-        CK(cudaHostAlloc(&h->status_host, sizeof(int), cudaHostAllocMapped));
-        *h->status_host = 0;
+        CK(cudaHostAlloc(&h->status_host, 2 * sizeof(int), cudaHostAllocMapped));
+        h->status_host[0] = h->status_host[1] = 0;
         CK(cudaHostGetDevicePointer(&h->status_dev, h->status_host, 0));
         // the handle's own stream-ordered pool: blocks freed in stream order are kept for the next launch, not returned to the OS
         cudaMemPoolProps pp{};
@@ -1369,7 +1372,16 @@ extern "C" int stmpm_set_sensor(stmpm_t* h, const stmpm_sensor_cfg* cfg) {
     h->cfg = *cfg;
     h->n_bins = STMPM_HIST_OCTAVES << cfg->hist_log2_sub;
     h->have_sensor = true;
+    if (h->status_host) h->status_host[1] = 0;          // a new sensor: the split pipeline gets another chance
     return rebuild_lists(h);
+}
+
+extern "C" int stmpm_set_pipeline(stmpm_t* h, int32_t pipeline) {
+    if (!h) return fail(STMPM_E_ARG, "stmpm_set_pipeline: null handle");
+    if (pipeline < -1 || pipeline > 1) return fail(STMPM_E_ARG, "stmpm_set_pipeline: -1 (auto), 0 (single kernel) or 1 (split pipeline)");
+    h->tune_pipeline = pipeline;
+    h->status_host[1] = 0;
+    return 0;
 }
 
 extern "C" int stmpm_set_tuning(stmpm_t* h, int32_t window, double key_radius_deg, int32_t stage_columns, int32_t key_table) {
@@ -1514,6 +1526,74 @@ static int launch_trials(stmpm_handle* h, KArgs& a, cudaStream_t st) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ split pipeline launcher
+// Pre-sampled, one segment, no instrumentation: scan kernel -> counting sort by survivor count -> solve kernel, in chunks of
+// 2^24 trials (3.8 GB of records from the handle's pool), all in stream order.  The single kernel is enqueued behind every
+// chunk with a device-side cancel word: it runs only when the scan could not hand over more than 1/64 of the chunk (star-
+// rich or wide-cone workloads), and the host then stops choosing the split for this catalog / sensor.
+template <int PREC>
+static int launch_split(stmpm_handle* h, const KArgs& a0, cudaStream_t st) {
+    const size_t smem_bytes = smem_total(a0.n_stars);
+    if (smem_bytes > (size_t)h->prop.sharedMemPerBlockOptin) return fail(STMPM_E_ARG, "catalog too large for shared-memory staging");
+    static std::atomic<size_t> attr_set[64];
+    static std::mutex attr_mutex;
+    std::atomic<size_t>& cached = attr_set[h->device & 63];
+    if (cached.load(std::memory_order_acquire) < smem_bytes) {
+        std::lock_guard<std::mutex> lock(attr_mutex);
+        if (cached.load(std::memory_order_relaxed) < smem_bytes) {
+            CK(cudaFuncSetAttribute(split_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+            cached.store(smem_bytes, std::memory_order_release);
+        }
+    }
+    const int n_sm = h->prop.multiProcessorCount;
+    const long long n = a0.trials_per_segment;
+    const long long chunk = std::min<long long>(n, 1LL << 24);
+    struct PoolBuf {
+        void* p = nullptr; cudaStream_t st;
+        ~PoolBuf() { if (p) cudaFreeAsync(p, st); }
+    } b_rec{nullptr, st}, b_cnt{nullptr, st}, b_perm{nullptr, st}, b_ctl{nullptr, st};
+    const long long n_chunks = (n + chunk - 1) / chunk;
+    CK(cudaMallocFromPoolAsync(&b_rec.p, sizeof(TrialRec) * (size_t)chunk, h->pool, st));
+    CK(cudaMallocFromPoolAsync(&b_cnt.p, (size_t)chunk, h->pool, st));
+    CK(cudaMallocFromPoolAsync(&b_perm.p, sizeof(uint32_t) * (size_t)chunk, h->pool, st));
+    CK(cudaMallocFromPoolAsync(&b_ctl.p, sizeof(SplitCtl) * (size_t)n_chunks, h->pool, st));
+    CK(cudaMemsetAsync(b_ctl.p, 0, sizeof(SplitCtl) * (size_t)n_chunks, st));
+    TrialRec* rec = static_cast<TrialRec*>(b_rec.p);
+    uint8_t* cnt = static_cast<uint8_t*>(b_cnt.p);
+    uint32_t* perm = static_cast<uint32_t*>(b_perm.p);
+    for (long long ci = 0; ci < n_chunks; ++ci) {
+        const long long off = ci * chunk, m = std::min<long long>(chunk, n - off);
+        SplitCtl* ctl = static_cast<SplitCtl*>(b_ctl.p) + ci;
+        KArgs k = a0;
+        for (int c = 0; c < STMPM_NCOLS; ++c) k.cols[c] = a0.cols[c] + off;
+        if (k.err) k.err += off;
+        if (k.ndet) k.ndet += off;
+        if (k.ndet8) k.ndet8 += off;
+        k.trial0 = a0.trial0 + off;
+        k.trials_per_segment = m;
+        const int grid_scan = (int)std::min<long long>(n_sm, (m + TPB_SCAN - 1) / TPB_SCAN);
+        split_scan_kernel<<<grid_scan, TPB_SCAN, smem_bytes, st>>>(k, rec, cnt, m);
+        const int grid_sort = (int)std::min<long long>((m + 255) / 256, (long long)n_sm * 8);
+        split_hist_kernel<<<grid_sort, 256, 0, st>>>(cnt, m, ctl);
+        split_offsets_kernel<<<1, SORT_BINS, 0, st>>>(ctl, m, h->status_dev + 1);
+        split_scatter_kernel<<<(unsigned)((m + 256 * SCATTER_ITEMS - 1) / (256 * SCATTER_ITEMS)), 256, 0, st>>>(cnt, m, ctl, perm);
+        const int grid_solve = (int)std::min<long long>(n_sm, (m + TPB - 1) / TPB);
+        split_solve_kernel<PREC><<<grid_solve, TPB, 0, st>>>(k, rec, perm, m, ctl);
+        CK(cudaGetLastError());
+        h->launches += 5;
+        KArgs kl = k;                                    // the single kernel, behind a cancel word: runs only on a fall-back
+        kl.cancel = &ctl->skip_single;
+        if (int rc = launch_trials<0, PREC, 0>(h, kl, st)) return rc;
+    }
+    return 0;
+}
+
+static bool want_split(const stmpm_handle* h, const KArgs& a) {
+    if (h->tune_pipeline == 0 || a.n_segments != 1 || a.maxmag != nullptr) return false;
+    if (h->tune_pipeline == 1) return true;
+    return a.trials_per_segment >= (1LL << 21) && h->status_host[1] == 0;
+}
+
 static int fill_common(stmpm_handle* h, KArgs& a, int precision) {
     if (!h) return fail(STMPM_E_ARG, "null handle");
     if (!h->have_catalog || !h->have_sensor)
@@ -1569,6 +1649,8 @@ extern "C" int stmpm_trials_presampled_ex(stmpm_t* h, int precision, int64_t n, 
     a.err = err; a.ndet = ndet; a.maxmag = maxmag; a.stats = stats;
     if (maxmag) return precision == 64 ? launch_trials<0, 64, 2>(h, a, (cudaStream_t)stream)
                                        : launch_trials<0, 32, 2>(h, a, (cudaStream_t)stream);
+    if (want_split(h, a)) return precision == 64 ? launch_split<64>(h, a, (cudaStream_t)stream)
+                                                 : launch_split<32>(h, a, (cudaStream_t)stream);
     return precision == 64 ? launch_trials<0, 64>(h, a, (cudaStream_t)stream)
                            : launch_trials<0, 32>(h, a, (cudaStream_t)stream);
 }

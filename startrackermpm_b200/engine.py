@@ -88,6 +88,10 @@ class TrialEngine:
         _abi.check(self._lib.stmpm_set_tuning(self._h, int(window), float(key_radius_deg), int(bool(stage_columns)),
                                               int(key_table)))
 
+    def set_pipeline(self, pipeline: int = -1) -> None:
+        """-1 auto, 0 single persistent kernel, 1 two-kernel split pipeline (pre-sampled, one segment); records identical."""
+        _abi.check(self._lib.stmpm_set_pipeline(self._h, int(pipeline)))
+
     def check(self) -> None:
         """After synchronising a stream handed to the *_device calls: raises if a kernel hit its scheduler watchdog."""
         _abi.check(self._lib.stmpm_check(self._h))

@@ -401,3 +401,51 @@ def test_sorted_parameter_staging_changes_no_record(engine):
                     assert torch.equal(e < 0, ~ok) and float((e[ok] - ref_e[ok]).abs().max()) / ARCSEC < 1e-6
     finally:
         engine.set_tuning()
+
+
+@pytest.mark.parametrize("prec", [64, 32])
+def test_split_pipeline_equals_single_kernel(engine, catalog, prec):
+    """Round 2's two-kernel pipeline (candidate scan -> counting sort by survivor count -> star loop + solve over warps of
+    identical star counts) must reproduce the single persistent kernel: detection counts and failure flags identical,
+    errors bit-identical wherever both walk the candidate list (every trial of the default configuration), within 1e-13 rad
+    for trials the scan hands to the sky-grid walk (> 56 survivors or a cone wider than the lists); statistics account
+    for every trial.  Also against the oracle, and on the workloads that trigger the device-side fall-back."""
+    xyz, mag = catalog
+    s = torch.cuda.current_stream().cuda_stream
+    cases = {
+        "default": (BASIC_MEAN, BASIC_SIGMA, 300_001),
+        "sigma_x5": (BASIC_MEAN, {k: 5 * v for k, v in BASIC_SIGMA.items()}, 200_003),        # ~0.3 % slow trials (wide cones)
+        "all_visible": (dict(BASIC_MEAN, MAX_MAGNITUDE=20.0), BASIC_SIGMA, 100_000),          # every trial overflows: fall-back
+        "few": (dict(BASIC_MEAN, MAX_MAGNITUDE=4.0), BASIC_SIGMA, 100_000),                   # many failed / zero-star trials
+    }
+    try:
+        for name, (mean, sigma, n) in cases.items():
+            d = make_dist(mean, sigma, THERMAL_COEF)
+            cols = torch.empty((13, n), dtype=torch.float64, device="cuda")
+            engine.fill_presampled_device(cols, d, seed=77, trial0=3, stream=s)
+            out = {}
+            for pipe in (0, 1):
+                engine.set_pipeline(pipe)
+                e = torch.full((n,), -7.0, dtype=torch.float64, device="cuda")
+                nd = torch.full((n,), -7, dtype=torch.int32, device="cuda")
+                st = torch.zeros(engine.stats_len, dtype=torch.float64, device="cuda")
+                engine.run_presampled_device(cols, e, nd, st, seed=77, trial0=3, precision=prec, stream=s)
+                torch.cuda.synchronize()
+                engine.check()
+                out[pipe] = (e.cpu().numpy(), nd.cpu().numpy(), st.cpu().numpy())
+            (e0, d0, s0), (e1, d1, s1) = out[0], out[1]
+            assert np.array_equal(d0, d1), name
+            assert np.array_equal(e0 < 0, e1 < 0), name
+            ok = e0 >= 0
+            diff = np.abs(e0[ok] - e1[ok]) / ARCSEC
+            assert diff.max() <= 1e-13, (name, diff.max())
+            if name in ("default", "few"):
+                assert np.array_equal(e0, e1), name                                             # bit-identical records
+            assert np.array_equal(s0[:2], s1[:2]) and s0[4] == s1[4] and s1[6] + s1[7] + s1[8:].sum() == ok.sum()
+            if name != "all_visible":
+                assert np.array_equal(s0[5:], s1[5:]) or diff.max() > 0                         # same maximum and histogram
+            m = min(n, 20_000)
+            e_ref, d_ref = trial.run_trials(cols[:, :m].cpu().numpy(), xyz, mag, F, 77, 3, grid=trial.candidate_grid(xyz))
+            compare(e1[:m], d1[:m], e_ref, d_ref, prec)
+    finally:
+        engine.set_pipeline(-1)
