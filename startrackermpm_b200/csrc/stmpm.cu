@@ -1551,15 +1551,13 @@ static int launch_split(stmpm_handle* h, const KArgs& a0, cudaStream_t st) {
     struct PoolBuf {
         void* p = nullptr; cudaStream_t st;
         ~PoolBuf() { if (p) cudaFreeAsync(p, st); }
-    } b_rec{nullptr, st}, b_cnt{nullptr, st}, b_perm{nullptr, st}, b_ctl{nullptr, st};
+    } b_rec{nullptr, st}, b_perm{nullptr, st}, b_ctl{nullptr, st};
     const long long n_chunks = (n + chunk - 1) / chunk;
     CK(cudaMallocFromPoolAsync(&b_rec.p, sizeof(TrialRec) * (size_t)chunk, h->pool, st));
-    CK(cudaMallocFromPoolAsync(&b_cnt.p, (size_t)chunk, h->pool, st));
     CK(cudaMallocFromPoolAsync(&b_perm.p, sizeof(uint32_t) * (size_t)chunk, h->pool, st));
     CK(cudaMallocFromPoolAsync(&b_ctl.p, sizeof(SplitCtl) * (size_t)n_chunks, h->pool, st));
     CK(cudaMemsetAsync(b_ctl.p, 0, sizeof(SplitCtl) * (size_t)n_chunks, st));
     TrialRec* rec = static_cast<TrialRec*>(b_rec.p);
-    uint8_t* cnt = static_cast<uint8_t*>(b_cnt.p);
     uint32_t* perm = static_cast<uint32_t*>(b_perm.p);
     for (long long ci = 0; ci < n_chunks; ++ci) {
         const long long off = ci * chunk, m = std::min<long long>(chunk, n - off);
@@ -1572,15 +1570,12 @@ static int launch_split(stmpm_handle* h, const KArgs& a0, cudaStream_t st) {
         k.trial0 = a0.trial0 + off;
         k.trials_per_segment = m;
         const int grid_scan = (int)std::min<long long>(n_sm, (m + TPB_SCAN - 1) / TPB_SCAN);
-        split_scan_kernel<<<grid_scan, TPB_SCAN, smem_bytes, st>>>(k, rec, cnt, m);
-        const int grid_sort = (int)std::min<long long>((m + 255) / 256, (long long)n_sm * 8);
-        split_hist_kernel<<<grid_sort, 256, 0, st>>>(cnt, m, ctl);
-        split_offsets_kernel<<<1, SORT_BINS, 0, st>>>(ctl, m, h->status_dev + 1);
-        split_scatter_kernel<<<(unsigned)((m + 256 * SCATTER_ITEMS - 1) / (256 * SCATTER_ITEMS)), 256, 0, st>>>(cnt, m, ctl, perm);
+        split_scan_kernel<<<grid_scan, TPB_SCAN, smem_bytes, st>>>(k, rec, perm, m, ctl);
+        split_decide_kernel<<<1, 1, 0, st>>>(ctl, m, h->status_dev + 1);
         const int grid_solve = (int)std::min<long long>(n_sm, (m + TPB - 1) / TPB);
         split_solve_kernel<PREC><<<grid_solve, TPB, 0, st>>>(k, rec, perm, m, ctl);
         CK(cudaGetLastError());
-        h->launches += 5;
+        h->launches += 3;
         KArgs kl = k;                                    // the single kernel, behind a cancel word: runs only on a fall-back
         kl.cancel = &ctl->skip_single;
         if (int rc = launch_trials<0, PREC, 0>(h, kl, st)) return rc;

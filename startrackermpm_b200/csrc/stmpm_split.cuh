@@ -7,9 +7,11 @@
 //   scan kernel   1 024 threads per SM (64 registers): fp32 set-up + candidate scan, trials in input order (coalesced
 //                 column reads); writes one 224-byte record per trial — the 13 parameters, the survivor count, the
 //                 survivors' catalog indices.
-//   counting sort (three small kernels) of the trials by survivor count -> a permutation.
+//                 Every block of 1 024 trials is counting-sorted by survivor count in shared memory (a permutation, written
+//                 next to the records).
 //   solve kernel  512 threads per SM: fp64 set-up, star loop, QUEST solve, records + statistics — over the permutation, so the
-//                 32 trials of a warp have the SAME number of stars: no idle lanes, no scheduler, no shared-memory catalog.
+//                 32 trials of a warp have (nearly) the SAME number of stars: no idle lanes, no scheduler, no shared-memory
+//                 catalog.
 // A trial the scan cannot hand over (scan cone wider than the candidate lists, more than REC_CAP survivors, angles beyond
 // the fp32 set-up's range) is marked CNT_SLOW and evaluated in full by the solve kernel on a sky-grid walk through global
 // memory; when more than 1/64 of a chunk is marked, the chunk is given to the single-kernel path instead (device-side
@@ -21,26 +23,27 @@
 constexpr int TPB_SCAN = 1024;
 constexpr int REC_CAP = 56;            // survivor indices a record holds
 constexpr uint32_t CNT_SLOW = 255;     // record not handed over: full evaluation in the solve kernel
-constexpr int SORT_BINS = 256;
+constexpr int SORT_BINS = 256;         // survivor counts 0 .. 255 (255 = CNT_SLOW sorts last)
 
 struct __align__(32) TrialRec {        // 224 bytes = seven 32-byte sectors
-    double p[STMPM_NCOLS];
-    uint32_t cnt;
-    uint32_t pad;
-    uint16_t list[REC_CAP];
+    double p[STMPM_NCOLS];             // the trial's parameters (MODEL.md §1)
+    uint32_t cnt;                      // survivors in list[], or CNT_SLOW
+    uint32_t index;                    // the trial's index inside the chunk
+    uint16_t list[REC_CAP];            // catalog indices of the pre-filter survivors, in candidate-list order
 };
 static_assert(sizeof(TrialRec) == 224, "TrialRec layout");
 
 struct SplitCtl {                      // device words of one chunk
-    unsigned int bins[SORT_BINS];      // histogram of survivor counts, then (exclusive scan) the scatter cursors
+    unsigned int n_slow;               // trials the scan could not hand over
+    unsigned int pad0[3];
     int skip_split;                    // 1: too many CNT_SLOW trials — the solve kernel returns, the single kernel runs
     int skip_single;                   // 1: the solve kernel runs, the single kernel returns
     int pad[2];
 };
 
 // ------------------------------------------------------------------------------------------------ scan kernel
-__global__ void __launch_bounds__(TPB_SCAN, 1) split_scan_kernel(const KArgs a, TrialRec* __restrict__ rec, uint8_t* __restrict__ cnt_out,
-                                                                long long n) {
+__global__ void __launch_bounds__(TPB_SCAN, 1) split_scan_kernel(const KArgs a, TrialRec* __restrict__ rec, uint32_t* __restrict__ perm,
+                                                                long long n, SplitCtl* ctl) {
     extern __shared__ __align__(128) unsigned char smem[];
     float4* s_cat = reinterpret_cast<float4*>(smem + OFF_CAT);
     int2* s_lkband = reinterpret_cast<int2*>(smem + OFF_LKBAND);
@@ -59,105 +62,107 @@ __global__ void __launch_bounds__(TPB_SCAN, 1) split_scan_kernel(const KArgs a, 
     while (!mbar_try_wait(s_bar, 0)) {}
     __syncthreads();
 
+    // block-local counting sort of 1 024 survivor counts: bins, then exclusive offsets, in shared memory
+    unsigned int* s_bins = reinterpret_cast<unsigned int*>(smem + OFF_LIST);              // [SORT_BINS] (the list region is unused here)
     const float hu32 = (float)a.half_u, hv32 = (float)a.half_v;
-    for (long long base = (long long)blockIdx.x * TPB_SCAN; base < n; base += (long long)gridDim.x * TPB_SCAN) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int n_slow = 0;
+    const long long n_blocks = (n + TPB_SCAN - 1) / TPB_SCAN;
+    for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        const long long base = blk * TPB_SCAN;
         const long long i = base + threadIdx.x;
-        if (i >= n) continue;
-        TrialParams p;
-        p.ra = __ldcs(a.cols[0] + i);     p.dec = __ldcs(a.cols[1] + i);    p.roll = __ldcs(a.cols[2] + i);
-        p.f = __ldcs(a.cols[3] + i);      p.ex = __ldcs(a.cols[4] + i);     p.ey = __ldcs(a.cols[5] + i);
-        p.ez = __ldcs(a.cols[6] + i);     p.phi = __ldcs(a.cols[7] + i);    p.theta = __ldcs(a.cols[8] + i);
-        p.psi = __ldcs(a.cols[9] + i);    p.devx = __ldcs(a.cols[10] + i);  p.devy = __ldcs(a.cols[11] + i);
-        p.maxmag = __ldcs(a.cols[12] + i);
-        TrialRec* r = rec + i;
-        {   // the parameters travel with the record: the solve kernel reads ONE place per trial
-            double* rp = r->p;
-            __stcg(rp + 0, p.ra);    __stcg(rp + 1, p.dec);   __stcg(rp + 2, p.roll);  __stcg(rp + 3, p.f);
-            __stcg(rp + 4, p.ex);    __stcg(rp + 5, p.ey);    __stcg(rp + 6, p.ez);    __stcg(rp + 7, p.phi);
-            __stcg(rp + 8, p.theta); __stcg(rp + 9, p.psi);   __stcg(rp + 10, p.devx); __stcg(rp + 11, p.devy);
-            __stcg(rp + 12, p.maxmag);
-        }
-        Ctx32 cf;
-        const bool ok = setup32(p, hu32, hv32, cf) && cf.cone <= a.lk_cone;
+        const bool valid = i < n;
+        if (threadIdx.x < SORT_BINS) s_bins[threadIdx.x] = 0u;
+        __syncthreads();
         uint32_t cnt = CNT_SLOW;
-        if (ok) {
-            const uint16_t* __restrict__ lp =
-                a.lk_list + __ldg(a.lk_off + lookup_cell(s_lkband, a.lk_bands, a.lk_inv_band_h, cf.ra0, cf.dec0));
-            uint16_t* __restrict__ rl = r->list;
-            cnt = 0;
-            bool more = true;
-            while (more) {             // eight candidates per 16-byte pack; the +inf terminator star ends every list
-                const uint4 pk = __ldg(reinterpret_cast<const uint4*>(lp));
-                lp += PACK_N;
-                const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
+        if (valid) {
+            TrialParams p;
+            p.ra = __ldcs(a.cols[0] + i);     p.dec = __ldcs(a.cols[1] + i);    p.roll = __ldcs(a.cols[2] + i);
+            p.f = __ldcs(a.cols[3] + i);      p.ex = __ldcs(a.cols[4] + i);     p.ey = __ldcs(a.cols[5] + i);
+            p.ez = __ldcs(a.cols[6] + i);     p.phi = __ldcs(a.cols[7] + i);    p.theta = __ldcs(a.cols[8] + i);
+            p.psi = __ldcs(a.cols[9] + i);    p.devx = __ldcs(a.cols[10] + i);  p.devy = __ldcs(a.cols[11] + i);
+            p.maxmag = __ldcs(a.cols[12] + i);
+            TrialRec* r = rec + i;
+            {   // the parameters travel with the record (the solve kernel reads ONE place per trial): 16-byte stores
+                double2* rp = reinterpret_cast<double2*>(r->p);
+                __stcg(rp + 0, make_double2(p.ra, p.dec));      __stcg(rp + 1, make_double2(p.roll, p.f));
+                __stcg(rp + 2, make_double2(p.ex, p.ey));       __stcg(rp + 3, make_double2(p.ez, p.phi));
+                __stcg(rp + 4, make_double2(p.theta, p.psi));   __stcg(rp + 5, make_double2(p.devx, p.devy));
+            }
+            Ctx32 cf;
+            const bool ok = setup32(p, hu32, hv32, cf) && cf.cone <= a.lk_cone;
+            if (ok) {
+                const uint16_t* __restrict__ lp =
+                    a.lk_list + __ldg(a.lk_off + lookup_cell(s_lkband, a.lk_bands, a.lk_inv_band_h, cf.ra0, cf.dec0));
+                uint4* __restrict__ rl = reinterpret_cast<uint4*>(r->list);
+                cnt = 0;
+                uint32_t buf[4] = {0u, 0u, 0u, 0u};       // eight survivor indices, flushed as one 16-byte store
+                bool more = true;
+                while (more) {             // eight candidates per 16-byte pack; the +inf terminator star ends every list
+                    const uint4 pk = __ldg(reinterpret_cast<const uint4*>(lp));
+                    lp += PACK_N;
+                    const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const uint32_t idx = (w4[e >> 1] >> (16 * (e & 1))) & 0xffffu;
-                    const float4 sc = lds_f4(sb_cat + idx * 16u);
-                    more = sc.w <= cf.magf;
-                    if (more && prefilter_geom(cf, sc)) {
-                        if (cnt < (uint32_t)REC_CAP) rl[cnt] = (uint16_t)idx;
-                        ++cnt;
+                    for (int e = 0; e < 8; ++e) {
+                        const uint32_t idx = (w4[e >> 1] >> (16 * (e & 1))) & 0xffffu;
+                        const float4 sc = lds_f4(sb_cat + idx * 16u);
+                        more = sc.w <= cf.magf;
+                        if (more && prefilter_geom(cf, sc)) {
+                            const uint32_t k = cnt & 7u;
+                            // slot k of the buffer (k is not a compile-time constant: select, do not index)
+                            const uint32_t sh = idx << (16u * (k & 1u));
+                            const uint32_t word = k >> 1;
+                            buf[0] = word == 0 ? ((k & 1u) ? (buf[0] | sh) : sh) : buf[0];
+                            buf[1] = word == 1 ? ((k & 1u) ? (buf[1] | sh) : sh) : buf[1];
+                            buf[2] = word == 2 ? ((k & 1u) ? (buf[2] | sh) : sh) : buf[2];
+                            buf[3] = word == 3 ? ((k & 1u) ? (buf[3] | sh) : sh) : buf[3];
+                            ++cnt;
+                            if ((cnt & 7u) == 0u && cnt <= (uint32_t)REC_CAP) __stcg(rl + (cnt >> 3) - 1, make_uint4(buf[0], buf[1], buf[2], buf[3]));
+                        }
                     }
                 }
+                if ((cnt & 7u) != 0u && cnt < (uint32_t)REC_CAP) __stcg(rl + (cnt >> 3), make_uint4(buf[0], buf[1], buf[2], buf[3]));
+                if (cnt > (uint32_t)REC_CAP) cnt = CNT_SLOW;
             }
-            if (cnt > (uint32_t)REC_CAP) cnt = CNT_SLOW;
+            // last 16 bytes of the parameter block: MAX_MAGNITUDE, the survivor count, the trial's index inside the chunk
+            __stcg(reinterpret_cast<uint4*>(r->p + 12),
+                   make_uint4((uint32_t)__double2loint(p.maxmag), (uint32_t)__double2hiint(p.maxmag), cnt, (uint32_t)i));
+            if (cnt == CNT_SLOW) ++n_slow;
         }
-        r->cnt = cnt;
-        cnt_out[i] = (uint8_t)cnt;
+        // ---- counting sort of the block by cnt: rank = offset[cnt] + arrival order inside the bin
+        unsigned int slot = 0;
+        if (valid) slot = atomicAdd(&s_bins[cnt], 1u);
+        __syncthreads();
+        if (warp == 0) {                   // exclusive scan of 256 bins by one warp: 8 bins per lane
+            unsigned int v[8], tot = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { v[k] = s_bins[lane * 8 + k]; tot += v[k]; }
+            unsigned int incl = tot;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned int o = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += o;
+            }
+            unsigned int run = incl - tot;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { s_bins[lane * 8 + k] = run; run += v[k]; }
+        }
+        __syncthreads();
+        if (valid) perm[base + s_bins[cnt] + slot] = (uint32_t)i;
+        __syncthreads();                   // s_bins is cleared at the top of the next block
     }
+    // trials not handed over, for the fall-back decision
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) n_slow += __shfl_xor_sync(0xffffffffu, n_slow, off);
+    if (lane == 0 && n_slow) atomicAdd(&ctl->n_slow, n_slow);
 }
 
-// ------------------------------------------------------------------------------------------------ counting sort by survivor count
-__global__ void __launch_bounds__(256) split_hist_kernel(const uint8_t* __restrict__ cnt, long long n, SplitCtl* ctl) {
-    __shared__ unsigned int h[SORT_BINS];
-    h[threadIdx.x] = 0u;
-    __syncthreads();
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        atomicAdd(&h[cnt[i]], 1u);
-    __syncthreads();
-    if (h[threadIdx.x]) atomicAdd(&ctl->bins[threadIdx.x], h[threadIdx.x]);
-}
-__global__ void __launch_bounds__(SORT_BINS) split_offsets_kernel(SplitCtl* ctl, long long n, int* fallbacks_seen) {
-    __shared__ unsigned int s[SORT_BINS];
-    const unsigned int v = ctl->bins[threadIdx.x];
-    s[threadIdx.x] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned int run = 0;
-        for (int k = 0; k < SORT_BINS; ++k) { const unsigned int c = s[k]; s[k] = run; run += c; }
-    }
-    __syncthreads();
-    ctl->bins[threadIdx.x] = s[threadIdx.x];           // exclusive offsets = the scatter cursors
-    if (threadIdx.x == CNT_SLOW) {
-        const bool too_many = (long long)v * 64 > n;   // more than 1/64 of the chunk cannot be handed over
-        ctl->skip_split = too_many ? 1 : 0;
-        ctl->skip_single = too_many ? 0 : 1;
-        if (too_many && fallbacks_seen != nullptr) *reinterpret_cast<volatile int*>(fallbacks_seen) = 1;   // host: stop trying the split on this configuration
-    }
-}
-constexpr int SCATTER_ITEMS = 16;                      // trials per thread
-__global__ void __launch_bounds__(256) split_scatter_kernel(const uint8_t* __restrict__ cnt, long long n, SplitCtl* ctl,
-                                                            uint32_t* __restrict__ perm) {
-    __shared__ unsigned int h[SORT_BINS], base[SORT_BINS];
-    const long long b0 = (long long)blockIdx.x * (256 * SCATTER_ITEMS);
-    h[threadIdx.x] = 0u;
-    __syncthreads();
-    uint8_t c[SCATTER_ITEMS];
-    unsigned int slot[SCATTER_ITEMS];
-#pragma unroll
-    for (int k = 0; k < SCATTER_ITEMS; ++k) {
-        const long long i = b0 + (long long)k * 256 + threadIdx.x;
-        if (i < n) { c[k] = cnt[i]; slot[k] = atomicAdd(&h[c[k]], 1u); }
-    }
-    __syncthreads();
-    if (h[threadIdx.x]) base[threadIdx.x] = atomicAdd(&ctl->bins[threadIdx.x], h[threadIdx.x]);   // reserve this block's range
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < SCATTER_ITEMS; ++k) {
-        const long long i = b0 + (long long)k * 256 + threadIdx.x;
-        if (i < n) perm[base[c[k]] + slot[k]] = (uint32_t)i;
-    }
+// decides, after the scan of a chunk, which kernel evaluates it
+__global__ void split_decide_kernel(SplitCtl* ctl, long long n, int* fallbacks_seen) {
+    const bool too_many = (long long)ctl->n_slow * 64 > n;    // more than 1/64 of the chunk cannot be handed over
+    ctl->skip_split = too_many ? 1 : 0;
+    ctl->skip_single = too_many ? 0 : 1;
+    if (too_many && fallbacks_seen != nullptr) *reinterpret_cast<volatile int*>(fallbacks_seen) = 1;   // host: stop trying the split here
 }
 
 // ------------------------------------------------------------------------------------------------ solve kernel
@@ -255,8 +260,9 @@ __global__ void __launch_bounds__(TPB, 1) split_solve_kernel(const KArgs a, cons
                           v5 = __ldcs(rp + 5);
             p.ra = v0.x; p.dec = v0.y; p.roll = v1.x; p.f = v1.y; p.ex = v2.x; p.ey = v2.y; p.ez = v3.x; p.phi = v3.y;
             p.theta = v4.x; p.psi = v4.y; p.devx = v5.x; p.devy = v5.y;
-            p.maxmag = __ldcs(r->p + 12);
-            cnt = __ldcs(&r->cnt);
+            const uint4 tail = __ldcs(reinterpret_cast<const uint4*>(r->p + 12));
+            p.maxmag = __hiloint2double((int)tail.y, (int)tail.x);
+            cnt = tail.z;
         } else {
             p.ra = p.dec = p.roll = 0.0; p.f = 1000.0; p.ex = p.ey = p.ez = p.phi = p.theta = p.psi = 0.0;
             p.devx = p.devy = 0.0; p.maxmag = -100.0;
