@@ -665,6 +665,12 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                         s.x = rr.x; s.y = rr.y; s.z = rr.z;
                         s.star_id = (uint32_t)(__double_as_longlong(rr.w) & 0xffffffffll);
                         if (INSTR == 2) s.mag = __int_as_float((int)(__double_as_longlong(rr.w) >> 32));
+                        // The record's last word (the magnitude) takes part in the detection decision below.  Besides being the
+                        // exact magnitude test once more, this keeps that word ALIVE: when it was unused, ptxas treated the
+                        // corresponding destination register of the NEXT record's 256-bit load as dead and reused it as a Philox
+                        // temporary right behind the load — a write-after-write hazard that exposed the full L2 latency in every
+                        // iteration (round 2, fp32 instantiation: 19 % of all stall samples on one IADD3).
+                        const bool mag_ok = __int_as_float(__double2hiint(rr.w)) <= cf.magf;
                         if (j + 1 < cnt) rr = ld_rec(a.cat64 + lds_u16(sb_row + (uint32_t)(j + 1) * (TPB * 2u)));
                         // (hand-pipelining Philox one star ahead, or two stars per iteration, both measured slower:
                         // ptxas already overlaps the integer chain with the fp64 one, and extra live state spills)
@@ -673,7 +679,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                         bool det;
                         if (PREC == 64) det = star_exact(c, tabs, s, x0, x1, a.f_ideal, a.f_ideal2, a.half_u, a.half_v, B);
                         else det = star_f32(c, cf, tabs, s, x0, x1, a.f_ideal, a.f_ideal2, a.half_u, a.half_v, B);
-                        n_det += det ? 1 : 0;
+                        n_det += (det && mag_ok) ? 1 : 0;
                         if (INSTR == 2 && det) mag_faintest = fmaxf(mag_faintest, s.mag);
                     }
                     cnt = 0;

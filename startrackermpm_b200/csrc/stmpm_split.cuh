@@ -292,6 +292,7 @@ __global__ void __launch_bounds__(TPB, 1) split_solve_kernel(const KArgs a, cons
                 StarRec s;
                 s.x = rr.x; s.y = rr.y; s.z = rr.z;
                 s.star_id = (uint32_t)(__double_as_longlong(rr.w) & 0xffffffffll);
+                const bool mag_ok = __int_as_float(__double2hiint(rr.w)) <= cf.magf;   // see trials_kernel: also keeps the word alive
                 if (j + 1 < m) rr = ld_rec(a.cat64 + i_next);
                 if (j + 2 < m) i_next = ldg_u16(rl + j + 2);
                 uint32_t x0, x1;
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(TPB, 1) split_solve_kernel(const KArgs a, cons
                 bool det;
                 if (PREC == 64) det = star_exact(c, tabs, s, x0, x1, a.f_ideal, a.f_ideal2, a.half_u, a.half_v, B);
                 else det = star_f32(c, cf, tabs, s, x0, x1, a.f_ideal, a.f_ideal2, a.half_u, a.half_v, B);
-                n_det += det ? 1 : 0;
+                n_det += (det && mag_ok) ? 1 : 0;
             }
         }
 #if !defined(STMPM_NO_PARK)
