@@ -126,8 +126,10 @@ int stmpm_set_tuning(stmpm_t* h, int32_t window, double key_radius_deg, int32_t 
 
 /* Pre-sampled launches of one segment run either as ONE persistent kernel or as the two-kernel split pipeline (candidate scan
  * -> counting sort of the trials by survivor count -> exact star loop + solve over warps of identical star counts; DESIGN.md
- * §3).  -1 (default) = the split pipeline for launches of >= 2^21 trials, until a chunk falls back (star-rich / wide-cone
- * workloads, decided on the device), 0 = always the single kernel, 1 = always try the split.  Records are identical. */
+ * §4).  The split measured SLOWER than the single kernel (the duplicated set-up and the record traffic outweigh the idle
+ * lanes it removes), so -1 (default) and 0 = the single kernel; 1 = the split, kept as a tested experiment (chunks it cannot
+ * hand over — star-rich / wide-cone workloads — fall back to the single kernel, decided on the device).  Records agree to
+ * the last bits (1e-13 rad). */
 int stmpm_set_pipeline(stmpm_t* h, int32_t pipeline);
 
 /* Packed statistics buffer (MODEL.md §9): STMPM_STATS_HEAD doubles then 34 * 2^hist_log2_sub histogram bins; every entry

@@ -1590,9 +1590,8 @@ static int launch_split(stmpm_handle* h, const KArgs& a0, cudaStream_t st) {
 }
 
 static bool want_split(const stmpm_handle* h, const KArgs& a) {
-    if (h->tune_pipeline == 0 || a.n_segments != 1 || a.maxmag != nullptr) return false;
-    if (h->tune_pipeline == 1) return true;
-    return a.trials_per_segment >= (1LL << 21) && h->status_host[1] == 0;
+    // measured slower than the single kernel: opt-in only
+    return h->tune_pipeline == 1 && a.n_segments == 1 && a.maxmag == nullptr;
 }
 
 static int fill_common(stmpm_handle* h, KArgs& a, int precision) {

@@ -35,7 +35,8 @@ static_assert(sizeof(TrialRec) == 224, "TrialRec layout");
 
 struct SplitCtl {                      // device words of one chunk
     unsigned int n_slow;               // trials the scan could not hand over
-    unsigned int pad0[3];
+    unsigned int next_group;           // solve kernel: next group of 32 sorted trials to hand out
+    unsigned int pad0[2];
     int skip_split;                    // 1: too many CNT_SLOW trials — the solve kernel returns, the single kernel runs
     int skip_single;                   // 1: the solve kernel runs, the single kernel returns
     int pad[2];
@@ -229,7 +230,7 @@ __device__ __forceinline__ uint32_t ldg_u16(const uint16_t* p) {
 
 template <int PREC>
 __global__ void __launch_bounds__(TPB, 1) split_solve_kernel(const KArgs a, const TrialRec* __restrict__ rec,
-                                                             const uint32_t* __restrict__ perm, long long n, const SplitCtl* ctl) {
+                                                             const uint32_t* __restrict__ perm, long long n, SplitCtl* ctl) {
     __shared__ __align__(16) unsigned char s_tab_raw[sizeof(MathTables)];
     if (*reinterpret_cast<const volatile int*>(&ctl->skip_split) != 0) return;
     {
@@ -246,8 +247,14 @@ __global__ void __launch_bounds__(TPB, 1) split_solve_kernel(const KArgs a, cons
     unsigned long long acc_ndet = 0;
     double acc_x = 0.0, acc_xx = 0.0, acc_max = 0.0;
 
+    // groups are handed out dynamically: inside every 1 024-trial block they run from few to many stars, so any static
+    // stride that is a multiple of 32 would give a warp the same position — the same cost — in every block
     const long long n_groups = (n + 31) >> 5;
-    for (long long g = (long long)blockIdx.x * (TPB / 32) + warp; g < n_groups; g += (long long)gridDim.x * (TPB / 32)) {
+    for (;;) {
+        unsigned int g32 = 0;
+        if (lane == 0) g32 = atomicAdd(&ctl->next_group, 1u);
+        const long long g = (long long)__shfl_sync(0xffffffffu, g32, 0);
+        if (g >= n_groups) break;
         const long long q = (g << 5) + lane;
         const bool valid = q < n;
         const long long i = valid ? (long long)__ldg(perm + q) : 0;
