@@ -314,9 +314,14 @@ def run_ours(args):
     try:
         h_cols = torch.empty((13, n_e2e), dtype=torch.float64, pin_memory=True)
         h_cols.copy_(cols[:, :n_e2e])
-        h_err = torch.empty(n_e2e, dtype=torch.float64, pin_memory=True)
-        h_ndet = torch.empty(n_e2e, dtype=torch.int32, pin_memory=True)
-        hc, he, hn = h_cols.numpy(), h_err.numpy(), h_ndet.numpy()
+        # ONE pinned result buffer of 13 bytes per trial, carved into the views the calls below need (no rank pins more than
+        # 117 bytes per trial: eight ranks share one host)
+        h_out = torch.empty(13 * n_e2e, dtype=torch.uint8, pin_memory=True).numpy()
+        he = h_out[:8 * n_e2e].view(np.float64)
+        hn = h_out[8 * n_e2e:12 * n_e2e].view(np.int32)
+        h_nd8 = h_out[12 * n_e2e:13 * n_e2e]
+        h_dst = h_out[:12 * n_e2e]
+        hc = h_cols.numpy()
         eng.run_presampled(hc, SEED, trial0, 64, out_err=he, out_ndet=hn)       # warm: staging buffers allocate here
         barrier()
         e2e_steps = max(1, min(args.steps, 3))
@@ -348,7 +353,6 @@ def run_ours(args):
                 best = sec if best is None else min(best, sec)
             return world * n_e2e / best
 
-        h_dst = torch.empty(12 * n_e2e, dtype=torch.uint8, pin_memory=True).numpy()
         roof = host_roofline(BYTES_IN_PER_TRIAL, BYTES_OUT_PER_TRIAL, hc, h_dst)
         e2e["host_roofline"] = {"value": roof, "unit": UNIT, "frac": e2e["value"] / roof,
                                 "gb_per_s": roof * (BYTES_IN_PER_TRIAL + BYTES_OUT_PER_TRIAL) / 1e9,
@@ -357,7 +361,8 @@ def run_ours(args):
         # the same workload through the native-RNG host entry (MonteCarlo.create_data + run_sim fused on the device):
         # nothing but the distribution goes up, the per-trial records come down (12 B, or 9 B with n_det as uint8)
         native = {}
-        h_nd8 = torch.empty(n_e2e, dtype=torch.uint8, pin_memory=True).numpy()
+        n_chk = min(n_e2e, 1 << 20)
+        nd_sample = None
         for label, compact, nd, nbytes in (("records_12B", False, hn, 12), ("records_9B", True, h_nd8, 9)):
             eng.run_rng(d, n_e2e, SEED, trial0, 64, out_err=he, out_ndet=nd, compact=compact)
             barrier()
@@ -366,10 +371,13 @@ def run_ours(args):
                 eng.run_rng(d, n_e2e, SEED, trial0, 64, out_err=he, out_ndet=nd, compact=compact)
             torch.cuda.synchronize()
             v = world * n_e2e * e2e_steps / max_over_ranks(time.perf_counter() - tw)
+            if not compact:
+                nd_sample = np.minimum(hn[:n_chk], 255).astype(np.uint8)      # (the copy-only pass below reuses this buffer)
+            else:
+                assert np.array_equal(nd_sample, h_nd8[:n_chk]), "compact records differ from the int32 records"
             roof = host_roofline(0, nbytes, None, h_dst)
             native[label] = {"value": v, "unit": UNIT, "d2h_bytes_per_step": nbytes * n_e2e,
                              "host_roofline": {"value": roof, "unit": UNIT, "frac": v / roof, "gb_per_s": roof * nbytes / 1e9}}
-        assert np.array_equal(np.minimum(hn, 255).astype(np.uint8), h_nd8)
         e2e["native_rng"] = {"value": native["records_12B"]["value"], "unit": UNIT,
                              "h2d_bytes_per_step": ctypes.sizeof(_abi.Dist), "d2h_bytes_per_step": BYTES_OUT_PER_TRIAL * n_e2e,
                              "api": "stmpm_run_rng_host (parameters sampled on the device, host records + statistics out)",
