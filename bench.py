@@ -216,6 +216,36 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local: int):
+    """Best effort: pin this rank's host threads — and, through first-touch, the pinned buffers it allocates afterwards — to
+    the CPUs of the NUMA node its GPU hangs off (sysfs `local_cpulist` of the GPU's PCI function).  Returns what was found
+    and done, for the JSON line.  On this pool the 8-GPU box exposes ONE node (numa_node 0 / -1 and the same CPU list for
+    every GPU), so this is a recorded no-op there."""
+    info = {"numa_node": None, "cpus": None, "bound": False}
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        dev = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        info["numa_node"] = int(open(dev + "/numa_node").read().strip())
+        cpulist = open(dev + "/local_cpulist").read().strip()
+        info["cpus"] = cpulist
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        target = cpus & allowed
+        if target and target != allowed:
+            os.sched_setaffinity(0, target)
+            info["bound"] = True
+    except Exception as ex:                                                # noqa: BLE001 — sysfs layout / permissions vary
+        info["error"] = f"{type(ex).__name__}: {str(ex)[:80]}"
+    return info
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
     import torch
@@ -232,6 +262,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the trial loop has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if rank == 0:
@@ -336,7 +367,8 @@ def run_ours(args):
                "h2d_bytes_per_step": BYTES_IN_PER_TRIAL * n_e2e, "d2h_bytes_per_step": BYTES_OUT_PER_TRIAL * n_e2e,
                "trials_per_gpu_per_step": n_e2e, "steps": e2e_steps,
                "api": "stmpm_run_presampled_host (pinned host columns in, host records out, chunked H2D/kernel/D2H pipeline)",
-               "records_match_device_run": bool(np.array_equal(he, err[:n_e2e].cpu().numpy()))}
+               "records_match_device_run": bool(np.array_equal(he, err[:n_e2e].cpu().numpy())),
+               "host_numa": numa}
 
         def max_over_ranks(seconds):
             t_ = torch.tensor([seconds], dtype=torch.float64, device="cuda")
