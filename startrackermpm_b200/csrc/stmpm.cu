@@ -2023,14 +2023,15 @@ extern "C" int stmpm_mc_converge(stmpm_t* h, int precision, const stmpm_dist* di
     a.err = h->stage_err[0]; a.ndet = h->stage_ndet[0]; a.stats = nullptr;
     a.cancel = &d_state->done;
     McState res{};
-    // first round: twice the batches min_rows needs (the rule cannot fire earlier, and typically fires within that span)
+    // first round: twice the batches min_rows needs, at least 32 (the rule cannot fire before min_rows, and typically fires
+    // within that span); every later round covers four times as many batches
     long long done_batches = 0, rounds = 0;
-    long long chunks_per_round = std::max<long long>(1, (2 * std::max<long long>(min_rows, 0) / batch + chunk_batches - 1) / chunk_batches);
-    chunks_per_round = std::min<long long>(chunks_per_round, 4096);
+    long long round_batches = std::max<long long>(32, (2 * std::max<long long>(min_rows, 0) + batch - 1) / batch);
     const long long limit = max_batches > 0 ? max_batches : (1LL << 40);
     for (;;) {
-        for (long long c = 0; c < chunks_per_round && done_batches < limit; ++c) {
-            const int nb = (int)std::min<long long>(chunk_batches, limit - done_batches);
+        const long long round_end = std::min<long long>(limit, done_batches + round_batches);
+        while (done_batches < round_end) {
+            const int nb = (int)std::min<long long>(chunk_batches, round_end - done_batches);
             KArgs k = a;
             k.trials_per_segment = (long long)nb * batch;
             k.trial0 = trial0 + done_batches * batch;
@@ -2046,7 +2047,7 @@ extern "C" int stmpm_mc_converge(stmpm_t* h, int precision, const stmpm_dist* di
         CK(cudaMemcpyAsync(&res, d_state, sizeof(res), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         if (res.done || done_batches >= limit) break;
-        chunks_per_round = std::min<long long>(chunks_per_round * 4, 4096);
+        round_batches = std::min<long long>(round_batches * 4, 4096LL * chunk_batches);
     }
     if (stats_host) CK(cudaMemcpy(stats_host, d_stats, sizeof(double) * slen, cudaMemcpyDeviceToHost));
     std::memset(out, 0, sizeof(*out));
