@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(TPB, 1) split_solve_kernel(const KArgs a, cons
     }
     __syncthreads();
     const TabSmem tabs{smem_u32(s_tab_raw)};
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     const float hu32 = (float)a.half_u, hv32 = (float)a.half_v;
     const bool want_stats = a.stats != nullptr;
     unsigned int acc_ok = 0, acc_fail = 0;
