@@ -221,7 +221,12 @@ def bind_to_gpu_numa_node(local: int):
     the CPUs of the NUMA node its GPU hangs off (sysfs `local_cpulist` of the GPU's PCI function).  Returns what was found
     and done, for the JSON line.  On this pool the 8-GPU box exposes ONE node (numa_node 0 / -1 and the same CPU list for
     every GPU), so this is a recorded no-op there."""
-    info = {"numa_node": None, "cpus": None, "bound": False}
+    info = {"numa_node": None, "cpus": None, "bound": False, "nodes_visible": None}
+    try:
+        import glob
+        info["nodes_visible"] = len(glob.glob("/sys/devices/system/node/node[0-9]*"))
+    except Exception:                                                      # noqa: BLE001
+        pass
     try:
         import torch
         pr = torch.cuda.get_device_properties(local)
