@@ -660,10 +660,10 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                     // Software-pipelined: the 32-byte record of star j+1 is in flight while star j is evaluated.
                     double4 rr = make_double4(0.0, 0.0, 0.0, 0.0);
                     if (cnt > 0) rr = ld_rec(a.cat64 + lds_u16(sb_row));
-#if !defined(STMPM_NO_IDX_AHEAD)
-                    // ... and the survivor INDEX of star j+2 is read a whole iteration before the record load that needs it: the
-                    // shared-memory latency otherwise sits between every iteration's list read and its record load (round 2:
-                    // 3 - 4.5 % of all stall samples on that load's address computation)
+#if defined(STMPM_IDX_AHEAD)
+                    // experiment (round 2, exp G): the survivor INDEX of star j+2 read a whole iteration before the record load
+                    // that needs it, to take the shared-memory latency out of the load's address chain (3 - 4.5 % of the stall
+                    // samples).  Measured -6 % (2.70 vs 2.86e9): the extra live register costs more than the wait.  Off.
                     uint32_t i_nx = 0u;
                     if (cnt > 1) i_nx = lds_u16(sb_row + (uint32_t)(TPB * 2u));
 #endif
@@ -678,7 +678,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                         // temporary right behind the load — a write-after-write hazard that exposed the full L2 latency in every
                         // iteration (round 2, fp32 instantiation: 19 % of all stall samples on one IADD3).
                         const bool mag_ok = __int_as_float(__double2hiint(rr.w)) <= cf.magf;
-#if !defined(STMPM_NO_IDX_AHEAD)
+#if defined(STMPM_IDX_AHEAD)
                         if (j + 1 < cnt) rr = ld_rec(a.cat64 + i_nx);
                         if (j + 2 < cnt) i_nx = lds_u16(sb_row + (uint32_t)(j + 2) * (TPB * 2u));
 #else
