@@ -391,8 +391,18 @@ def run_ours(args):
             return world * n_e2e / best
 
         roof = host_roofline(BYTES_IN_PER_TRIAL, BYTES_OUT_PER_TRIAL, hc, h_dst)
+        solo = None
+        if world > 1:     # one rank alone on the host fabric (the others idle at the barrier): what a single PCIe link gives here
+            barrier()
+            sec = eng.host_copy_roofline(n_e2e, BYTES_IN_PER_TRIAL, BYTES_OUT_PER_TRIAL, hc, h_dst) if rank == 0 else 0.0
+            barrier()
+            solo = n_e2e / max_over_ranks(sec)
         e2e["host_roofline"] = {"value": roof, "unit": UNIT, "frac": e2e["value"] / roof,
                                 "gb_per_s": roof * (BYTES_IN_PER_TRIAL + BYTES_OUT_PER_TRIAL) / 1e9,
+                                "one_rank_alone": None if solo is None else {
+                                    "value": solo, "unit": UNIT, "gb_per_s": solo * (BYTES_IN_PER_TRIAL + BYTES_OUT_PER_TRIAL) / 1e9,
+                                    "ranks_x_alone": world * solo,
+                                    "what": "rank 0's copies with the other ranks idle; ranks x this = the fabric-unlimited aggregate"},
                                 "what": "the same host pipeline with the kernel removed: 104 B/trial H2D + 12 B/trial D2H through "
                                         "the same chunks, streams and staging buffers, all ranks concurrently, max over ranks"}
         # the same workload through the native-RNG host entry (MonteCarlo.create_data + run_sim fused on the device):
