@@ -3,7 +3,9 @@
 PARITY UNPINNED.  The reference's own trial code (`simObjects/Simulation.py`, `AttitudeEstimation.py`, ...) is absent
 from /root/reference and the reference holds no tests, golden vectors or fixtures, so
 this file cannot be checked against reference outputs.  It restates docs/MODEL.md, which is constrained by the facts
-the present reference files DO pin; each function cites them:
+the present reference files DO pin; each function cites them.  What it IS checked against: an independent scalar
+restatement of MODEL.md that shares no function with it (tests/golden/independent_trial.py -> trial_golden_v2.npz:
+identical detection counts, errors within 5e-14 rad), Random123 known answers, scipy's Wahba solver, analytic cases.
 
   * rotation primitives Rx/Ry/Rz ............ /root/reference/constants.py:81-94
   * sensor 1024 x 1024 px ................... /root/reference/constants.py:97-98
