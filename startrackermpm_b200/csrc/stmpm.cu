@@ -677,11 +677,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                         // corresponding destination register of the NEXT record's 256-bit load as dead and reused it as a Philox
                         // temporary right behind the load — a write-after-write hazard that exposed the full L2 latency in every
                         // iteration (round 2, fp32 instantiation: 19 % of all stall samples on one IADD3).
-#if defined(STMPM_MAG_NAN_TEST)
-                        const bool mag_ok = __double2hiint(rr.w) != 0x7fc00000;      // experiment: immediate compare, no live register
-#else
-                        const bool mag_ok = __int_as_float(__double2hiint(rr.w)) <= cf.magf;
-#endif
+                        const bool mag_ok = __int_as_float(__double2hiint(rr.w)) <= cf.magf;   // (an immediate compare instead: +-0, exp H)
 #if defined(STMPM_IDX_AHEAD)
                         if (j + 1 < cnt) rr = ld_rec(a.cat64 + i_nx);
                         if (j + 2 < cnt) i_nx = lds_u16(sb_row + (uint32_t)(j + 2) * (TPB * 2u));

@@ -209,8 +209,9 @@ STMPM_HD void box_muller_t(const Tab T, uint32_t wa, uint32_t wb, double& z1, do
     // log1p(r) = r - r^2/2 + r^3/3 - r^4/4 + r^5/5, |r| <= 2^-9 (truncation r^6/6 < 1e-17), Estrin form: depth 3
     const double r2 = r * r;
     const double p = fma(r2, fma(r2, fma(r, 0.2, -0.25), fma(r, 1.0 / 3.0, -0.5)), r);
-#if defined(STMPM_K2_ARITH)
-    // experiment: 2 k ln 2 by arithmetic (k exact through the 2^52 magic number) instead of the table read
+#if !defined(STMPM_K2_TABLE)
+    // -2 ln m + 2 k ln 2, the second term by arithmetic (k exact through the 2^52 magic number): the table read it replaces
+    // was the loop's largest single short-scoreboard wait (4 % of the stall samples; round 2 exp H: +0.3 %)
     const double kd = bits_to_double(0x4330000000000000ull | (unsigned long long)(unsigned)k) - 4503599627370496.0;
     const double L = fma(kd, 1.3862943611198906, fma(-2.0, p, m2ln_c));
 #else
