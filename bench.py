@@ -410,18 +410,24 @@ def run_ours(args):
         native = {}
         n_chk = min(n_e2e, 1 << 20)
         nd_sample = None
-        for label, compact, nd, nbytes in (("records_12B", False, hn, 12), ("records_9B", True, h_nd8, 9)):
-            eng.run_rng(d, n_e2e, SEED, trial0, 64, out_err=he, out_ndet=nd, compact=compact)
+        he32 = h_out[:4 * n_e2e].view(np.float32)              # the 5-byte format's float32 errors (aliases he: used last)
+        err_sample = None
+        for label, compact, eb, nd, nbytes in (("records_12B", False, he, hn, 12), ("records_9B", True, he, h_nd8, 9),
+                                               ("records_5B", 5, he32, h_nd8, 5)):
+            eng.run_rng(d, n_e2e, SEED, trial0, 64, out_err=eb, out_ndet=nd, compact=compact)
             barrier()
             tw = time.perf_counter()
             for _ in range(e2e_steps):
-                eng.run_rng(d, n_e2e, SEED, trial0, 64, out_err=he, out_ndet=nd, compact=compact)
+                eng.run_rng(d, n_e2e, SEED, trial0, 64, out_err=eb, out_ndet=nd, compact=compact)
             torch.cuda.synchronize()
             v = world * n_e2e * e2e_steps / max_over_ranks(time.perf_counter() - tw)
-            if not compact:
-                nd_sample = np.minimum(hn[:n_chk], 255).astype(np.uint8)      # (the copy-only pass below reuses this buffer)
+            if nbytes == 12:                                  # (the copy-only pass below reuses these buffers)
+                nd_sample = np.minimum(hn[:n_chk], 255).astype(np.uint8)
+                err_sample = he[:n_chk].astype(np.float32)
             else:
                 assert np.array_equal(nd_sample, h_nd8[:n_chk]), "compact records differ from the int32 records"
+                if nbytes == 5:
+                    assert np.array_equal(err_sample, he32[:n_chk]), "float32 records differ from the rounded float64 records"
             roof = host_roofline(0, nbytes, None, h_dst)
             native[label] = {"value": v, "unit": UNIT, "d2h_bytes_per_step": nbytes * n_e2e,
                              "host_roofline": {"value": roof, "unit": UNIT, "frac": v / roof, "gb_per_s": roof * nbytes / 1e9}}

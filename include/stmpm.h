@@ -185,6 +185,13 @@ int stmpm_run_rng_host(stmpm_t* h, int precision, int64_t n_segments, int64_t tr
 int stmpm_run_rng_host_compact(stmpm_t* h, int precision, int64_t n_segments, int64_t trials_per_segment, uint64_t seed,
                                int64_t trial0, const stmpm_dist* dists_host, double* err_arcsec_host, uint8_t* n_det_u8_host,
                                double* stats_host);
+/* ... and with 5-byte records: the error rounded to float32 as well.  The statistics are still accumulated from the float64
+ * error on the device; only the per-trial record loses precision (half an ulp of a float32 number of arcseconds: 3e-5" =
+ * 1.5e-10 rad at 1000", inside the 1e-9 rad parity bar up to 0.9 degrees of error).  For hosts whose device-to-host fabric is
+ * the limit (94 GB/s for eight B200s on this pool): records per second scale with 1 / bytes. */
+int stmpm_run_rng_host_compact32(stmpm_t* h, int precision, int64_t n_segments, int64_t trials_per_segment, uint64_t seed,
+                                 int64_t trial0, const stmpm_dist* dists_host, float* err_arcsec_f32_host, uint8_t* n_det_u8_host,
+                                 double* stats_host);
 /* Trials per stage of the host pipelines (0 = default 2^22; staging buffers are re-allocated on the next host call). */
 int stmpm_set_host_pipeline(stmpm_t* h, int64_t chunk_trials);
 /* Host-side roofline of the host-buffer entry points: n trials' worth of bytes through the SAME chunking, streams and

@@ -4,7 +4,7 @@
 # The by-line join needs the .so that was profiled: run right after the capture, before rebuilding.
 cd "$(dirname "$0")/.."
 set -e
-rm -rf /tmp/stmpm_cub && mkdir /tmp/stmpm_cub && (cd /tmp/stmpm_cub && cuobjdump -xelf all "$OLDPWD/startrackermpm_b200/libstmpm.so" > /dev/null)
+rm -rf /tmp/stmpm_cub && mkdir /tmp/stmpm_cub && (cd /tmp/stmpm_cub && cuobjdump -xelf all "${STMPM_SO:-$OLDPWD/startrackermpm_b200/libstmpm.so}" > /dev/null)
 declare -A FN=( [fp64]=_Z13trials_kernelILi0ELi64ELi0EEv5KArgs [fp32]=_Z13trials_kernelILi0ELi32ELi0EEv5KArgs [allvis]=_Z13trials_kernelILi0ELi64ELi0EEv5KArgs [rng]=_Z13trials_kernelILi1ELi64ELi0EEv5KArgs )
 for k in fp64 fp32 allvis rng; do
   rep=gpurun_out/r2_$k.ncu-rep

@@ -58,6 +58,7 @@ struct KArgs {
     unsigned long long* counters;   // INSTR only: [visits, mag_pass, survivors, detected]
     double* stage;                  // MODE 0: per-CTA scratch [gridDim][2][STMPM_NCOLS][WIN_MAX] — the window's columns in key order
     uint8_t* ndet8;                 // optional compact record: detected stars saturated at 255 (9-byte records with err)
+    float* err32;                   // optional compact record: the error rounded to float32 (5-byte records with ndet8)
     int* status;                    // host-mapped word: a scheduler wait that exceeds WATCHDOG_NS writes STMPM_E_WATCHDOG here
     const int* cancel;              // optional: a non-zero word makes the launch a no-op (on-device MonteCarlo stop rule)
 };
@@ -731,6 +732,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                     if (a.err) a.err[rec] = err;
                     if (a.ndet) a.ndet[rec] = n_det;
                     if (a.ndet8) a.ndet8[rec] = (uint8_t)min(n_det, 255);
+                    if (a.err32) a.err32[rec] = (float)err;
                     if (INSTR == 2 && a.maxmag) a.maxmag[rec] = mag_faintest;
                     if (want_stats) {
                         acc_ndet += (unsigned long long)n_det;
@@ -1793,8 +1795,9 @@ extern "C" int stmpm_run_presampled_host_ex(stmpm_t* h, int precision, int64_t n
     return check_status(h);
 }
 
+// record format: 12 = (f64 err, i32 n_det), 9 = (f64 err, u8 n_det), 5 = (f32 err, u8 n_det)
 static int run_rng_host_impl(stmpm_t* h, int precision, int64_t n_segments, int64_t tps, uint64_t seed, int64_t trial0,
-                             const stmpm_dist* dists, double* err, void* ndet, bool compact, double* stats) {
+                             const stmpm_dist* dists, void* err, void* ndet, int format, double* stats) {
     KArgs probe;
     if (int rc = fill_common(h, probe, precision)) return rc;
     if (n_segments < 0 || tps < 0 || !dists) return fail(STMPM_E_ARG, "stmpm_run_rng_host: bad arguments");
@@ -1814,7 +1817,7 @@ static int run_rng_host_impl(stmpm_t* h, int precision, int64_t n_segments, int6
         const long long chunk = std::min<long long>(h->host_chunk, tps);
         if (int rc = ensure_stage(h, chunk, false)) return rc;
         CK(cudaStreamSynchronize(s0));
-        const size_t nd_bytes = compact ? 1 : sizeof(int);
+        const size_t nd_bytes = format == 12 ? sizeof(int) : 1, err_bytes = format == 5 ? sizeof(float) : sizeof(double);
         int k = 0;
         for (long long s = 0; s < n_segments; ++s) {
             for (long long off = 0; off < tps; off += chunk, ++k) {
@@ -1826,12 +1829,13 @@ static int run_rng_host_impl(stmpm_t* h, int precision, int64_t n_segments, int6
                 to_dev_dist(dists[s], a.dist0);
                 a.n_segments = 1; a.trials_per_segment = m; a.trial0 = trial0 + s * tps + off;
                 a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
-                a.err = h->stage_err[b];
-                if (compact) a.ndet8 = reinterpret_cast<uint8_t*>(h->stage_ndet[b]); else a.ndet = h->stage_ndet[b];
+                if (format == 5) a.err32 = reinterpret_cast<float*>(h->stage_err[b]); else a.err = h->stage_err[b];
+                if (format != 12) a.ndet8 = reinterpret_cast<uint8_t*>(h->stage_ndet[b]); else a.ndet = h->stage_ndet[b];
                 a.stats = stats ? h->stage_stats + s * slen : nullptr;
                 const int rc = precision == 64 ? launch_trials<1, 64>(h, a, st) : launch_trials<1, 32>(h, a, st);
                 if (rc) return rc;
-                CK(cudaMemcpyAsync(err + s * tps + off, h->stage_err[b], sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(static_cast<char*>(err) + (size_t)(s * tps + off) * err_bytes, h->stage_err[b], err_bytes * m,
+                                   cudaMemcpyDeviceToHost, st));
                 CK(cudaMemcpyAsync(static_cast<char*>(ndet) + (size_t)(s * tps + off) * nd_bytes, h->stage_ndet[b], nd_bytes * m,
                                    cudaMemcpyDeviceToHost, st));
             }
@@ -1844,12 +1848,17 @@ static int run_rng_host_impl(stmpm_t* h, int precision, int64_t n_segments, int6
 
 extern "C" int stmpm_run_rng_host(stmpm_t* h, int precision, int64_t n_segments, int64_t tps, uint64_t seed,
                                   int64_t trial0, const stmpm_dist* dists, double* err, int32_t* ndet, double* stats) {
-    return run_rng_host_impl(h, precision, n_segments, tps, seed, trial0, dists, err, ndet, false, stats);
+    return run_rng_host_impl(h, precision, n_segments, tps, seed, trial0, dists, err, ndet, 12, stats);
 }
 
 extern "C" int stmpm_run_rng_host_compact(stmpm_t* h, int precision, int64_t n_segments, int64_t tps, uint64_t seed,
                                           int64_t trial0, const stmpm_dist* dists, double* err, uint8_t* ndet_u8, double* stats) {
-    return run_rng_host_impl(h, precision, n_segments, tps, seed, trial0, dists, err, ndet_u8, true, stats);
+    return run_rng_host_impl(h, precision, n_segments, tps, seed, trial0, dists, err, ndet_u8, 9, stats);
+}
+
+extern "C" int stmpm_run_rng_host_compact32(stmpm_t* h, int precision, int64_t n_segments, int64_t tps, uint64_t seed,
+                                            int64_t trial0, const stmpm_dist* dists, float* err_f32, uint8_t* ndet_u8, double* stats) {
+    return run_rng_host_impl(h, precision, n_segments, tps, seed, trial0, dists, err_f32, ndet_u8, 5, stats);
 }
 
 // Host-side roofline of the host-buffer entry points: the SAME chunking, streams and staging buffers, copies only — no

@@ -332,6 +332,7 @@ __global__ void __launch_bounds__(TPB, 1) split_solve_kernel(const KArgs a, cons
             if (a.err) a.err[i] = err;
             if (a.ndet) a.ndet[i] = n_det;
             if (a.ndet8) a.ndet8[i] = (uint8_t)min(n_det, 255);
+            if (a.err32) a.err32[i] = (float)err;
             if (want_stats) {
                 acc_ndet += (unsigned long long)n_det;
                 if (err >= 0.0) {

@@ -216,23 +216,28 @@ class TrialEngine:
         return arr, len(dists)
 
     def run_rng(self, dists, trials_per_segment: int, seed: int, trial0: int = 0, precision: int = 64,
-                records: bool = False, out_err=None, out_ndet=None, compact: bool = False):
+                records: bool = False, out_err=None, out_ndet=None, compact=False):
         """HOST results.  Returns stats [n_segments, stats_len] (and err, n_det [n_segments*trials_per_segment] if records).
         out_err / out_ndet: caller-owned (e.g. pinned) record buffers; giving them implies records.
-        compact=True: n_det comes back as uint8 saturated at 255 — 9 bytes per trial over PCIe instead of 12."""
+        compact: False = (float64 err, int32 n_det), 12 bytes per trial over PCIe; True or 9 = n_det as uint8 saturated at
+        255 (9 bytes); 5 = the error as float32 too (5 bytes; the statistics still come from the float64 error)."""
         arr, ns = self._dist_array(dists)
         n = ns * int(trials_per_segment)
         if (out_err is None) != (out_ndet is None):
             raise ValueError("out_err and out_ndet go together")
-        nd_type = np.uint8 if compact else np.int32
+        fmt = {False: 12, True: 9, 12: 12, 9: 9, 5: 5}.get(compact)
+        if fmt is None:
+            raise ValueError("compact must be False, True / 9, or 5")
+        nd_type = np.int32 if fmt == 12 else np.uint8
+        err_type = np.float32 if fmt == 5 else np.float64
         if out_err is not None:
-            _check_host_out(out_err, np.float64, n, "out_err")
+            _check_host_out(out_err, err_type, n, "out_err")
             _check_host_out(out_ndet, nd_type, n, "out_ndet")
             records = True
-        err = out_err if out_err is not None else (np.empty(n, dtype=np.float64) if records else None)
+        err = out_err if out_err is not None else (np.empty(n, dtype=err_type) if records else None)
         ndet = out_ndet if out_ndet is not None else (np.empty(n, dtype=nd_type) if records else None)
         stats = np.zeros((ns, self.stats_len), dtype=np.float64)
-        fn = self._lib.stmpm_run_rng_host_compact if compact else self._lib.stmpm_run_rng_host
+        fn = {12: self._lib.stmpm_run_rng_host, 9: self._lib.stmpm_run_rng_host_compact, 5: self._lib.stmpm_run_rng_host_compact32}[fmt]
         _abi.check(fn(self._h, int(precision), ns, int(trials_per_segment), int(seed) & (2**64 - 1), int(trial0), arr,
                       _ptr(err), _ptr(ndet), _ptr(stats)))
         return (stats, err, ndet) if records else stats

@@ -359,6 +359,9 @@ def test_compact_records_and_host_pipeline_knob(engine):
         st8, e8, d8 = engine.run_rng(dist, n, 3, 11, records=True, compact=True)
         assert d8.dtype == np.uint8 and np.array_equal(e8, e) and np.array_equal(d8, np.minimum(d, 255).astype(np.uint8))
         assert np.array_equal(st8[0, :2], st[0, :2]) and np.array_equal(st8[0, 4:], st[0, 4:])
+    st5, e5, d5 = engine.run_rng(dist, n, 3, 11, records=True, compact=5)                          # 5-byte records: float32 error
+    assert e5.dtype == np.float32 and np.array_equal(e5, e.astype(np.float32)) and np.array_equal(d5, d8)
+    assert np.array_equal(st5[0, :2], st[0, :2]) and np.array_equal(st5[0, 4:], st[0, 4:])         # statistics from the float64 error
     wide = make_dist(dict(BASIC_MEAN, MAX_MAGNITUDE=20.0, FOCAL_LENGTH=700.0), ZERO_SIGMA, 0.0)   # > 255 stars in the field
     _, _, dw = engine.run_rng(wide, 2000, 3, 0, records=True)
     _, _, dw8 = engine.run_rng(wide, 2000, 3, 0, records=True, compact=True)
