@@ -1,0 +1,15 @@
+#!/bin/bash
+# round-2 experiment I: libm sincos / atan2 and fp32 mode's exact fall-back out of line (smaller instruction footprint) vs inlined
+cd "$(dirname "$0")/.."
+run() { label=$1; shift; timeout 300 python bench.py --steps 4 --warmup 3 --no-cpu-baseline --e2e-trials 1e6 "$@" 2>&1 | tail -1 | python scripts/bench_value.py "$label"; }
+cp startrackermpm_b200/libstmpm.so /tmp/libstmpm_keep.so
+for v in smallcode inlinelibm smallcode inlinelibm; do
+  cp variants/libstmpm_$v.so startrackermpm_b200/libstmpm.so; touch startrackermpm_b200/libstmpm.so
+  run "$v default"
+done
+for v in smallcode inlinelibm; do
+  cp variants/libstmpm_$v.so startrackermpm_b200/libstmpm.so; touch startrackermpm_b200/libstmpm.so
+  run "$v all_visible" --workload all_visible
+  echo "$v mode matrix:"; python scripts/mode_matrix.py
+done
+cp /tmp/libstmpm_keep.so startrackermpm_b200/libstmpm.so; touch startrackermpm_b200/libstmpm.so

@@ -339,11 +339,22 @@ __device__ __forceinline__ void sincos_small(double x, double* s, double* c) {
     *c = fma(x2, fma(x2, fma(x2, fma(x2, fma(x2, -1.0 / 3628800.0, 1.0 / 40320.0), -1.0 / 720.0), 1.0 / 24.0), -0.5), 1.0);
 }
 
+// libm's sincos / atan2 inline several hundred instructions each (range reduction with a Payne-Hanek slow path).  The trial
+// kernel's 16 warps sit in different phases of a ~100 KB instruction stream, and ncu shows them waiting for instruction fetch
+// (`no_instruction` 0.23 per issue in fp64 mode, 0.51 in fp32 mode): ONE out-of-line copy of each instead of six / one inlined.
+#if defined(STMPM_INLINE_LIBM)
+#define STMPM_LIBM_INLINE __forceinline__
+#else
+#define STMPM_LIBM_INLINE __noinline__
+#endif
+__device__ STMPM_LIBM_INLINE void sincos_libm(double x, double* s, double* c) { sincos(x, s, c); }
+__device__ STMPM_LIBM_INLINE double atan2_libm(double y, double x) { return atan2(y, x); }
+
 __device__ __forceinline__ void setup64(const TrialParams& p, Ctx64& c) {
     double sa, ca, sd, cd, sr, cr;
-    sincos(p.ra, &sa, &ca);
-    sincos(p.dec, &sd, &cd);
-    sincos(p.roll, &sr, &cr);
+    sincos_libm(p.ra, &sa, &ca);
+    sincos_libm(p.dec, &sd, &cd);
+    sincos_libm(p.roll, &sr, &cr);
     // C = Rz(ra) Ry(pi/2 - dec) Rz(roll)   (MODEL.md §2; primitives: constants.py:81-94)
     c.C[0] = ca * sd * cr - sa * sr;  c.C[1] = -ca * sd * sr - sa * cr;  c.C[2] = ca * cd;
     c.C[3] = sa * sd * cr + ca * sr;  c.C[4] = -sa * sd * sr + ca * cr;  c.C[5] = sa * cd;
@@ -355,9 +366,9 @@ __device__ __forceinline__ void setup64(const TrialParams& p, Ctx64& c) {
         sincos_small(theta, &st, &ct);
         sincos_small(psi, &ss, &cs);
     } else {
-        sincos(phi, &sp, &cp);
-        sincos(theta, &st, &ct);
-        sincos(psi, &ss, &cs);
+        sincos_libm(phi, &sp, &cp);
+        sincos_libm(theta, &st, &ct);
+        sincos_libm(psi, &ss, &cs);
     }
     // R_p = Rx(phi) Ry(theta) Rz(psi): columns e_u, e_v, n
     const double eu[3] = {ct * cs, cp * ss + sp * st * cs, sp * ss - cp * st * cs};
@@ -520,6 +531,19 @@ __device__ __forceinline__ bool star_exact(const Ctx64& c, const Tab T, const St
     return det;
 }
 
+// the exact evaluation as an out-of-line call, for fp32 mode's rare guard-band fall-back (keeps that loop's code small)
+template <class Tab>
+__device__ STMPM_LIBM_INLINE bool star_exact_rare(const Ctx64* c, const Tab T, const StarRec* s, uint32_t x0, uint32_t x1, double f_ideal,
+                                                  double f_ideal2, double half_u, double half_v, double* B) {
+    double Bl[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Bl[k] = B[k];
+    const bool det = star_exact(*c, T, *s, x0, x1, f_ideal, f_ideal2, half_u, half_v, Bl);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) B[k] = Bl[k];
+    return det;
+}
+
 // fp32 star evaluation (precision = 32, bar 1e-6 rad).  What stays fp64 and why: the three
 // plane-triad dot products and the projection scale (an fp32 dot product's 6e-8 absolute error times f = 3500 px is 2e-4 px,
 // which 3-4-star geometries amplify past the bar through the roll lever arm) and B (roll observability).  What drops to fp32:
@@ -549,7 +573,7 @@ __device__ __forceinline__ bool star_f32(const Ctx64& c, const Ctx32& cf, const 
     // over-covers by less than one unit of g's leading word — the guard only has to be wide enough
     const int hu = __double2hiint(eu), hv = __double2hiint(ev);
     if ((hu & 0x7fffffff) <= cf.guard_hi || (hv & 0x7fffffff) <= cf.guard_hi)
-        return star_exact(c, T, s, x0, x1, f_ideal, f_ideal2, half_u, half_v, B);   // rare (~1e-7 of the stars): exact decision + exact b
+        return star_exact_rare(&c, T, &s, x0, x1, f_ideal, f_ideal2, half_u, half_v, B);   // rare (~1e-7 of the stars): exact decision + exact b
     const bool det = (__double2hiint(dn) > 0) && ((hu & hv) < 0);      // n.r > 0 and both distances negative (zero is in the guard)
     if (det) {
         const double y = seed_rsqrt(fma(vm, vm, fma(um, um, f_ideal2)));
@@ -611,7 +635,7 @@ __device__ __forceinline__ double quest_error_arcsec(const double* __restrict__ 
         const double p = fma(t2, fma(t2, fma(t2, fma(t2, 1.0 / 9.0, -1.0 / 7.0), 0.2), -1.0 / 3.0), 1.0);
         return (2.0 * RAD2ARCSEC) * (t * p);
     }
-    return 2.0 * atan2(vn, ag) * RAD2ARCSEC;
+    return 2.0 * atan2_libm(vn, ag) * RAD2ARCSEC;
 }
 
 // MODEL.md §6: native-RNG parameter draw for one trial.
