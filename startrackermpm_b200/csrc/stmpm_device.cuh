@@ -339,13 +339,15 @@ __device__ __forceinline__ void sincos_small(double x, double* s, double* c) {
     *c = fma(x2, fma(x2, fma(x2, fma(x2, fma(x2, -1.0 / 3628800.0, 1.0 / 40320.0), -1.0 / 720.0), 1.0 / 24.0), -0.5), 1.0);
 }
 
-// libm's sincos / atan2 inline several hundred instructions each (range reduction with a Payne-Hanek slow path).  The trial
-// kernel's 16 warps sit in different phases of a ~100 KB instruction stream, and ncu shows them waiting for instruction fetch
-// (`no_instruction` 0.23 per issue in fp64 mode, 0.51 in fp32 mode): ONE out-of-line copy of each instead of six / one inlined.
-#if defined(STMPM_INLINE_LIBM)
-#define STMPM_LIBM_INLINE __forceinline__
-#else
+// Experiment (round 2, exp I; STMPM_SMALL_CODE): the trial kernel's 16 warps sit in different phases of a ~100 KB instruction
+// stream and ncu shows them waiting for instruction fetch (`no_instruction` 0.23 per issue in fp64 mode, 0.51 in fp32 mode), so
+// libm's sincos / atan2 and fp32 mode's exact fall-back were tried as ONE out-of-line copy each.  Measured WORSE: fp64 -2.5 %,
+// fp32 -50 % (an out-of-line callee takes the plane context and B by address, which moves them to local memory inside the star
+// loop).  Inlined by default.
+#if defined(STMPM_SMALL_CODE)
 #define STMPM_LIBM_INLINE __noinline__
+#else
+#define STMPM_LIBM_INLINE __forceinline__
 #endif
 __device__ STMPM_LIBM_INLINE void sincos_libm(double x, double* s, double* c) { sincos(x, s, c); }
 __device__ STMPM_LIBM_INLINE double atan2_libm(double y, double x) { return atan2(y, x); }
@@ -572,8 +574,13 @@ __device__ __forceinline__ bool star_f32(const Ctx64& c, const Ctx32& cf, const 
     // comparisons run on the high words (integer pipe, not the 16-lane FP64 pipe): |x| <= g  <=  hi(|x|) <= hi(g), which
     // over-covers by less than one unit of g's leading word — the guard only has to be wide enough
     const int hu = __double2hiint(eu), hv = __double2hiint(ev);
-    if ((hu & 0x7fffffff) <= cf.guard_hi || (hv & 0x7fffffff) <= cf.guard_hi)
-        return star_exact_rare(&c, T, &s, x0, x1, f_ideal, f_ideal2, half_u, half_v, B);   // rare (~1e-7 of the stars): exact decision + exact b
+    if ((hu & 0x7fffffff) <= cf.guard_hi || (hv & 0x7fffffff) <= cf.guard_hi) {      // rare (~1e-7 of the stars): exact decision + exact b
+#if defined(STMPM_SMALL_CODE)
+        return star_exact_rare(&c, T, &s, x0, x1, f_ideal, f_ideal2, half_u, half_v, B);
+#else
+        return star_exact(c, T, s, x0, x1, f_ideal, f_ideal2, half_u, half_v, B);
+#endif
+    }
     const bool det = (__double2hiint(dn) > 0) && ((hu & hv) < 0);      // n.r > 0 and both distances negative (zero is in the guard)
     if (det) {
         const double y = seed_rsqrt(fma(vm, vm, fma(um, um, f_ideal2)));
