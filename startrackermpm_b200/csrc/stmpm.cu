@@ -659,6 +659,34 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                     __syncwarp();
                     // ---- phase B: exact evaluation of the listed stars (lanes in lock-step).
                     // Software-pipelined: the 32-byte record of star j+1 is in flight while star j is evaluated.
+#if defined(STMPM_PINGPONG)
+                    // experiment (round 2, exp J): two record buffers used alternately by a two-way unrolled loop, instead of one
+                    // landing buffer copied into the working one at the end of every iteration (8 MOVs of ~165 instructions)
+                    auto star_step = [&](const double4& cur) {
+                        StarRec s;
+                        s.x = cur.x; s.y = cur.y; s.z = cur.z;
+                        s.star_id = (uint32_t)(__double_as_longlong(cur.w) & 0xffffffffll);
+                        if (INSTR == 2) s.mag = __int_as_float((int)(__double_as_longlong(cur.w) >> 32));
+                        const bool mag_ok = __int_as_float(__double2hiint(cur.w)) <= cf.magf;
+                        uint32_t x0, x1;
+                        philox2x32_10(s.star_id, kb, ka, x0, x1);
+                        bool det;
+                        if (PREC == 64) det = star_exact(c, tabs, s, x0, x1, a.f_ideal, a.f_ideal2, a.half_u, a.half_v, B);
+                        else det = star_f32(c, cf, tabs, s, x0, x1, a.f_ideal, a.f_ideal2, a.half_u, a.half_v, B);
+                        n_det += (det && mag_ok) ? 1 : 0;
+                        if (INSTR == 2 && det) mag_faintest = fmaxf(mag_faintest, s.mag);
+                    };
+                    double4 ra = make_double4(0.0, 0.0, 0.0, 0.0), rb = ra;
+                    if (cnt > 0) ra = ld_rec(a.cat64 + lds_u16(sb_row));
+                    for (int j = 0; j < cnt;) {
+                        if (j + 1 < cnt) rb = ld_rec(a.cat64 + lds_u16(sb_row + (uint32_t)(j + 1) * (TPB * 2u)));
+                        star_step(ra);
+                        if (++j >= cnt) break;
+                        if (j + 1 < cnt) ra = ld_rec(a.cat64 + lds_u16(sb_row + (uint32_t)(j + 1) * (TPB * 2u)));
+                        star_step(rb);
+                        ++j;
+                    }
+#else
                     double4 rr = make_double4(0.0, 0.0, 0.0, 0.0);
                     if (cnt > 0) rr = ld_rec(a.cat64 + lds_u16(sb_row));
 #if defined(STMPM_IDX_AHEAD)
@@ -695,6 +723,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                         n_det += (det && mag_ok) ? 1 : 0;
                         if (INSTR == 2 && det) mag_faintest = fmaxf(mag_faintest, s.mag);
                     }
+#endif
                     cnt = 0;
                     if (!__any_sync(0xffffffffu, scanning)) break;
                     if (scanning) {                             // survivor row was full: re-derive the fp32 geometry, go on

@@ -208,7 +208,13 @@ STMPM_HD void box_muller_t(const Tab T, uint32_t wa, uint32_t wb, double& z1, do
     const double r = fma(m, inv_c, -1.0);
     // log1p(r) = r - r^2/2 + r^3/3 - r^4/4 + r^5/5, |r| <= 2^-9 (truncation r^6/6 < 1e-17), Estrin form: depth 3
     const double r2 = r * r;
+#if defined(STMPM_HI_COEF)
+    // experiment (round 2, exp J): 1/3 and 1/5 truncated to their high words (relative 2.4e-7 on terms below 2.5e-9), so that
+    // they encode as DFMA immediates instead of two register moves each
+    const double p = fma(r2, fma(r2, fma(r, 0.19999992847442627, -0.25), fma(r, 0.33333325386047363, -0.5)), r);
+#else
     const double p = fma(r2, fma(r2, fma(r, 0.2, -0.25), fma(r, 1.0 / 3.0, -0.5)), r);
+#endif
 #if !defined(STMPM_K2_TABLE)
     // -2 ln m + 2 k ln 2, the second term by arithmetic (k exact through the 2^52 magic number): the table read it replaces
     // was the loop's largest single short-scoreboard wait (4 % of the stall samples; round 2 exp H: +0.3 %)
@@ -228,8 +234,13 @@ STMPM_HD void box_muller_t(const Tab T, uint32_t wa, uint32_t wb, double& z1, do
     const double t = bits_to_double(0x4330000000000000ull | (unsigned long long)(2u * rem + 1u));
     const double d = (t - 4503599631564800.0) * 7.314590396335798e-10;   // (2^52 + 2^22);  pi / 512 / 2^23
     const double d2 = d * d;
+#if defined(STMPM_HI_COEF)
+    const double sd = fma(d * d2, -0.16666662693023682, d);              // high-word-only 1/6: 1.2e-15 on top of the truncation
+    const double cd = fma(d2, fma(d2, 0.041666656732559204, -0.5), 1.0);
+#else
     const double sd = fma(d * d2, -1.0 / 6.0, d);                        // truncation d^5/120 < 2.3e-15
     const double cd = fma(d2, fma(d2, 1.0 / 24.0, -0.5), 1.0);           // truncation d^6/720 < 1.2e-18
+#endif
     double S, C;
     T.sc(j2, S, C);
     const double sq = fma(S, cd, C * sd);
