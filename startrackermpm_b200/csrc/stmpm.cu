@@ -78,8 +78,8 @@ constexpr size_t OFF_MBAR = OFF_TAB + (sizeof(MathTables) + 15) / 16 * 16;
 constexpr size_t OFF_LKBAND = OFF_MBAR + 16;
 constexpr size_t OFF_BAND = OFF_LKBAND + (size_t)LK_BANDS * 8;
 constexpr size_t OFF_CAT = (OFF_BAND + (size_t)MAX_BANDS * 8 + 127) / 128 * 128;
-constexpr size_t CAT_ENTRY_BYTES = CAT_ENTRY;
-static size_t smem_total(int n_stars) { return OFF_CAT + ((size_t)(n_stars + 1) * CAT_ENTRY_BYTES + 15) / 16 * 16; }   // + the +inf terminator star
+constexpr size_t CAT_ENTRY_BYTES = 16;
+static size_t smem_total(int n_stars) { return OFF_CAT + (size_t)(n_stars + 1) * CAT_ENTRY_BYTES; }   // + the +inf terminator star
 // the real catalog (BSC5: 9 110 stars, 9 096 after load_bsc5 drops the non-stellar entries) must fit the 227 KB a CTA can opt in to
 static_assert(OFF_CAT + (9110 + 1) * CAT_ENTRY_BYTES <= 227 * 1024, "a 9110-star catalog no longer fits in shared memory");
 
@@ -131,9 +131,9 @@ __device__ __forceinline__ bool eval_pack(const Ctx32& c, uint32_t sb_cat, const
 #pragma unroll                               // would pin every later catalog read behind it — ptxas must assume aliasing)
     for (int e = 0; e < 8; ++e) {
         const uint32_t idx = (w4[e >> 1] >> (16 * (e & 1))) & 0xffffu;
-        const CatEnt sc = lds_cat(sb_cat, idx);
+        const float4 sc = lds_f4(sb_cat + idx * 16u);
         if (INSTR == 1) ins[0] += m ? 1 : 0;
-        m = cat_mag_ok(c, sc);
+        m = sc.w <= c.magf;
         if (INSTR == 1) ins[1] += m ? 1 : 0;
         const bool g = prefilter_geom(c, sc);        // evaluated regardless of m: no branch
         pass |= (m & g) ? (1u << e) : 0u;
@@ -224,6 +224,7 @@ __device__ __noinline__ void band_walk_trial(const Ctx64* cp, const Ctx32* cfp, 
     const Ctx64 c = *cp;
     const Ctx32 cf = *cfp;
     unsigned char* smem = reinterpret_cast<unsigned char*>(__cvta_shared_to_generic((size_t)sb));
+    const float4* s_cat = reinterpret_cast<const float4*>(smem + OFF_CAT);
     const int2* s_band = reinterpret_cast<const int2*>(smem + OFF_BAND);
     uint16_t* s_list = reinterpret_cast<uint16_t*>(smem + OFF_LIST) + threadIdx.x;   // entry j at s_list[j * TPB]
     const TabSmem tabs{sb + (uint32_t)OFF_TAB};
@@ -261,9 +262,9 @@ __device__ __noinline__ void band_walk_trial(const Ctx64* cp, const Ctx32* cfp, 
                 }
                 continue;
             }
-            const CatEnt sc = lds_cat(sb + (uint32_t)OFF_CAT, (uint32_t)i);
-            if (INSTR == 1) { ++ins[0]; if (cat_mag_ok(cf, sc)) ++ins[1]; }
-            if (cat_mag_ok(cf, sc) && prefilter_geom(cf, sc)) {
+            const float4 sc = s_cat[i];
+            if (INSTR == 1) { ++ins[0]; if (sc.w <= cf.magf) ++ins[1]; }
+            if (sc.w <= cf.magf && prefilter_geom(cf, sc)) {
                 s_list[cnt * TPB] = (uint16_t)i; ++cnt; if (INSTR == 1) ++ins[2];
             }
             ++i;
@@ -314,7 +315,7 @@ template <int MODE, int PREC, int INSTR>
 __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     if (a.cancel != nullptr && *reinterpret_cast<const volatile int*>(a.cancel) != 0) return;   // converged in an earlier chunk
-    unsigned char* s_cat = smem + OFF_CAT;
+    float4* s_cat = reinterpret_cast<float4*>(smem + OFF_CAT);
     int2* s_band = reinterpret_cast<int2*>(smem + OFF_BAND);
     int2* s_lkband = reinterpret_cast<int2*>(smem + OFF_LKBAND);
     const MathTables* s_tab = reinterpret_cast<const MathTables*>(smem + OFF_TAB);
@@ -340,10 +341,10 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
     if (threadIdx.x < 8) s_sched[threadIdx.x] = 0;
     __syncthreads();
     if (threadIdx.x == 0) {
-        const uint32_t total = ((uint32_t)(a.n_stars + 1) * CAT_ENTRY + 15u) & ~15u;   // bulk copies move multiples of 16 B
+        const uint32_t total = (uint32_t)(a.n_stars + 1) * 16u;
         mbar_expect_tx(s_bar, total);
         const unsigned char* src = reinterpret_cast<const unsigned char*>(a.cat32);
-        unsigned char* dst = s_cat;
+        unsigned char* dst = reinterpret_cast<unsigned char*>(s_cat);
         for (uint32_t off = 0; off < total; off += 32768u) bulk_g2s(dst + off, src + off, min(32768u, total - off), s_bar);
     }
     {
@@ -1386,30 +1387,8 @@ extern "C" int stmpm_set_catalog(stmpm_t* h, const double* xyz, const float* mag
     std::vector<float4> c32(n_stars + 1);
     c32[n_stars] = make_float4(0.0f, 0.0f, 1.0f, INFINITY);                // dummy list terminator: never passes a magnitude test
     std::vector<StarRec> c64(n_stars);
-#if defined(STMPM_CAT8)
-    {   // 8-byte scan entries (stmpm_device.cuh: CatEnt), written over the front of the same buffer
-        uint32_t* w = reinterpret_cast<uint32_t*>(c32.data());
-        auto q15 = [](double x) -> uint32_t {
-            const long q = std::lrint((x + 1.0) * 16383.5);
-            return 0x8000u | (uint32_t)std::min(32767L, std::max(0L, q));
-        };
-        for (int i = 0; i <= n_stars; ++i) {
-            uint32_t code = 0xffffu;                                       // the terminator's: no threshold exceeds it
-            const double* d = xyz + 3 * (size_t)std::min(i, n_stars - 1);
-            if (i < n_stars) {
-                const double t = ((double)mag[i] - CAT8_M0) * CAT8_MS;     // window_and_cone evaluates the same expression
-                code = !(t < 65535.0) ? 65534u : (t < 0.0 ? 0u : (uint32_t)std::floor(t));
-                if (!(t >= 0.0)) code = 0u;
-            }
-            w[2 * i] = q15(d[0]) | (q15(d[1]) << 16);
-            w[2 * i + 1] = q15(d[2]) | (code << 16);
-        }
-    }
-#endif
     for (int i = 0; i < n_stars; ++i) {
-#if !defined(STMPM_CAT8)
         c32[i] = make_float4((float)xyz[3 * i], (float)xyz[3 * i + 1], (float)xyz[3 * i + 2], mag[i]);
-#endif
         c64[i].x = xyz[3 * i]; c64[i].y = xyz[3 * i + 1]; c64[i].z = xyz[3 * i + 2];
         c64[i].star_id = (uint32_t)star_id[i]; c64[i].mag = mag[i];
     }

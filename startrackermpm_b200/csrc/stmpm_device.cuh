@@ -26,7 +26,7 @@ namespace stmpm {
 
 constexpr int TPB = 512;          // threads per CTA (1 CTA / SM: the fp32 catalog lives in shared memory)
 #if !defined(STMPM_LIST_CAP)
-#define STMPM_LIST_CAP 48
+#define STMPM_LIST_CAP 48         // 32 measured -4.4 % (round 2, exp K: more drain rounds); larger does not fit beside the catalog
 #endif
 constexpr int LIST_CAP = STMPM_LIST_CAP;   // per-thread survivor list in shared memory (phase A -> phase B hand-off), drained in rounds
 constexpr int WIN_MAX = 2048;     // largest CTA sort window (trials)
@@ -36,7 +36,6 @@ constexpr int WIN_STAGED = 2048;      // default window, pre-sampled columns sta
 constexpr int WIN_RNG = 2048;         // default window, native RNG: no gathers, so the widest sort wins
 constexpr int KEY_LEVELS = 128;   // work-key table: candidate visits per lookup cell at magnitude levels KEY_M0 + (k+1)/16
 constexpr float KEY_M0 = 1.0f;
-constexpr double CAT8_M0 = -32.0, CAT8_MS = 1024.0;   // STMPM_CAT8 magnitude code = floor((mag - M0) * MS), clamped to [0, 65534]
 constexpr int KEY_ROLLS = 8;      // work-key table: orientation bins of the array footprint (roll modulo its symmetry period)
 constexpr int KEY_BINS = 256;     // sort bins (= candidate visits, saturated)
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u, PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
@@ -339,10 +338,6 @@ struct Ctx32 {
     float sxf, syf;               // fp32 mode: |BASE_DEV_X|, |BASE_DEV_Y|
     int guard_hi;                 // fp32 mode: high word of the guard distance around the array edges (see star_f32)
     float ra0, dec0, cone;        // boresight (lookup-cell key) and scan-cone half angle
-#if defined(STMPM_CAT8)
-    float kN, kU, kV;             // constant terms of the three dot products over the biased 15-bit components (CatEnt)
-    uint32_t magthr;              // (magnitude code of MAX_MAGNITUDE + 1) << 16: entry word 1 < magthr  <=>  bright enough
-#endif
 };
 
 __device__ __forceinline__ float opaque(float x) {   // stop ptxas re-deriving an fp32 copy from its fp64 source at every
@@ -414,20 +409,7 @@ __device__ __forceinline__ void setup64(const TrialParams& p, Ctx64& c) {
 // Cone: every point of the (tilted, shifted, noise-padded) array lies within atan(reach / depth) of the boresight.
 __device__ __forceinline__ void window_and_cone(const TrialParams& p, float half_u, float half_v, Ctx32& c) {
     const float ff = fabsf((float)p.f);
-#if defined(STMPM_CAT8)
-    // + the 15-bit quantisation of the shared-memory catalog's directions: each component is off by <= 3.05e-5, a dot
-    // product by <= 5.3e-5, the projection by <= 5.3e-5 f (1 + t)^2 with t = tan(angle of the window's corner)
-    const float tq = 1.0f + (1.41421357f * fmaxf(half_u, half_v) + 6.8f * fmaxf(fabsf((float)p.devx), fabsf((float)p.devy))) / fmaxf(ff, 1.0f);
-    const float noise = 6.8f * fmaxf(fabsf((float)p.devx), fabsf((float)p.devy)) + 0.05f + 1e-5f * ff
-                        + 6e-5f * (ff + fabsf((float)p.ez)) * tq * tq;
-    {
-        const double t = __dmul_rn(__dadd_rn(p.maxmag, -CAT8_M0), CAT8_MS);       // same expression as the host encoder
-        c.magthr = !(t < 65535.0) ? 0xffff0000u : (t < 0.0 ? 0u : (((uint32_t)(int)floor(t)) + 1u) << 16);
-        asm volatile("" : "+r"(c.magthr));
-    }
-#else
     const float noise = 6.8f * fmaxf(fabsf((float)p.devx), fabsf((float)p.devy)) + 0.05f + 1e-5f * ff;
-#endif
     c.limu = opaque(half_u + noise);
     c.limv = opaque(half_v + noise);
     c.sxf = opaque(fabsf((float)p.devx));
@@ -443,23 +425,6 @@ __device__ __forceinline__ void window_and_cone(const TrialParams& p, float half
     c.cone = (depth > 1.0f) ? atanf(reach / depth) + 0.002f : 3.2f;
 }
 
-// STMPM_CAT8: the scan reads each direction component as f = 1 + q / 32768 (q = 15-bit code, see CatEnt), i.e.
-// x = A f - (A + 1) with A = 32768 / 16383.5, so  N . s = sum (A N_i) f_i - (A + 1) sum N_i: the vectors are pre-scaled and
-// the constant term becomes the first addend of the FFMA chain — no per-candidate decode beyond one PRMT per component.
-__device__ __forceinline__ void finish32(Ctx32& c) {
-#if defined(STMPM_CAT8)
-    constexpr float A = 32768.0f / 16383.5f;
-    c.kN = opaque((A + 1.0f) * (c.NI[0] + c.NI[1] + c.NI[2]));
-    c.kU = opaque((A + 1.0f) * (c.EU[0] + c.EU[1] + c.EU[2]));
-    c.kV = opaque((A + 1.0f) * (c.EV[0] + c.EV[1] + c.EV[2]));
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        c.NI[i] = opaque(A * c.NI[i]);
-        c.EU[i] = opaque(A * c.EU[i]);
-        c.EV[i] = opaque(A * c.EV[i]);
-    }
-#endif
-}
 // fp32 copies of the plane geometry (what prefilter_geom reads).  Cheap enough to redo for the rare re-scan, so the twelve
 // floats need not stay live across the fp64 star loop.
 __device__ __forceinline__ void geom32(const Ctx64& d, Ctx32& c) {
@@ -472,7 +437,6 @@ __device__ __forceinline__ void geom32(const Ctx64& d, Ctx32& c) {
     c.np0 = opaque((float)d.np0);
     c.cu = opaque((float)d.cu);
     c.cv = opaque((float)d.cv);
-    finish32(c);
 }
 // boresight = third column of C; its (ra, dec) key the lookup grid
 __device__ __forceinline__ void boresight32(const Ctx64& d, Ctx32& c) {
@@ -516,7 +480,6 @@ __device__ __forceinline__ bool setup32(const TrialParams& p, float half_u, floa
         c.EU[i] = C[3 * i] * eu[0] + C[3 * i + 1] * eu[1] + C[3 * i + 2] * eu[2];
         c.EV[i] = C[3 * i] * ev[0] + C[3 * i + 1] * ev[1] + C[3 * i + 2] * ev[2];
     }
-    finish32(c);
     window_and_cone(p, half_u, half_v, c);
     // boresight = third column of C; its (ra, dec) key the lookup grid
     c.dec0 = asinf(fminf(fmaxf(C[8], -1.0f), 1.0f));
@@ -539,39 +502,6 @@ __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-// ---- the shared-memory catalog entry of the candidate scan (phase A).
-// Default: float4 (x, y, z, mag), 16 B.  STMPM_CAT8: 8 B — three direction components as 15-bit codes q = round((x + 1) 16383.5)
-// stored with bit 15 set, and a 16-bit magnitude code floor((mag + 32) 1024) in the top half of word 1 (0xffff = the lists'
-// terminator).  One PRMT drops a component's two bytes into the mantissa of 1.0f (bit 15 lands on the exponent's lowest bit):
-// f = 1 + q / 32768, no conversion instruction; the magnitude test is one unsigned compare of word 1.  The codes are
-// monotone in mag and the window grows by the quantisation bound (window_and_cone), so the scan stays conservative; the exact
-// decisions are phase B's.  73 KB instead of 146 KB of shared memory: the carve-out drops from 228 to 164 KB, L1 grows to 92 KB.
-#if defined(STMPM_CAT8)
-constexpr uint32_t CAT_ENTRY = 8;
-struct CatEnt { uint32_t w0, w1; };
-__device__ __forceinline__ CatEnt lds_cat(uint32_t sb_cat, uint32_t idx) {
-    CatEnt e;
-    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.w0), "=r"(e.w1) : "r"(sb_cat + idx * 8u));
-    return e;
-}
-__device__ __forceinline__ bool cat_mag_ok(const Ctx32& c, const CatEnt e) { return e.w1 < c.magthr; }
-__device__ __forceinline__ bool prefilter_geom(const Ctx32& c, const CatEnt e) {
-    const float fx = __uint_as_float(__byte_perm(e.w0, 0x3f000000u, 0x7104));
-    const float fy = __uint_as_float(__byte_perm(e.w0, 0x3f000000u, 0x7324));
-    const float fz = __uint_as_float(__byte_perm(e.w1, 0x3f000000u, 0x7104));
-    const float dn = fmaf(c.NI[0], fx, fmaf(c.NI[1], fy, fmaf(c.NI[2], fz, -c.kN)));
-    float rcp_dn;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp_dn) : "f"(dn));
-    const float rl = c.np0 * rcp_dn;
-    const float u = fmaf(rl, fmaf(c.EU[0], fx, fmaf(c.EU[1], fy, fmaf(c.EU[2], fz, -c.kU))), -c.cu);
-    const float v = fmaf(rl, fmaf(c.EV[0], fx, fmaf(c.EV[1], fy, fmaf(c.EV[2], fz, -c.kV))), -c.cv);
-    return dn > 0.02f && fabsf(u) <= c.limu && fabsf(v) <= c.limv;
-}
-#else
-constexpr uint32_t CAT_ENTRY = 16;
-typedef float4 CatEnt;
-__device__ __forceinline__ CatEnt lds_cat(uint32_t sb_cat, uint32_t idx) { return lds_f4(sb_cat + idx * 16u); }
-__device__ __forceinline__ bool cat_mag_ok(const Ctx32& c, const CatEnt s) { return s.w <= c.magf; }
 // fp32 conservative geometric pre-filter on one shared-memory catalog entry (x, y, z, mag); magnitude tested by caller
 __device__ __forceinline__ bool prefilter_geom(const Ctx32& c, const float4 s) {
     const float dn = c.NI[0] * s.x + c.NI[1] * s.y + c.NI[2] * s.z;
@@ -582,7 +512,6 @@ __device__ __forceinline__ bool prefilter_geom(const Ctx32& c, const float4 s) {
     const float v = fmaf(rl, c.EV[0] * s.x + c.EV[1] * s.y + c.EV[2] * s.z, -c.cv);
     return dn > 0.02f && fabsf(u) <= c.limu && fabsf(v) <= c.limv;
 }
-#endif
 
 // Exact (fp64) star evaluation: MODEL.md §2-§4. Returns detected?; on detection adds b s^T into B.
 // (x0, x1) = the star's Philox2x32-10 words (MODEL.md §5), computed by the caller.

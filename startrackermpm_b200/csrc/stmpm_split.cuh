@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(TPB_SCAN, 1) split_scan_kernel(const KArgs a, 
     if (threadIdx.x == 0) mbar_init(s_bar, 1);
     __syncthreads();
     if (threadIdx.x == 0) {            // the fp32 catalog through the TMA unit, as in trials_kernel
-        const uint32_t total = ((uint32_t)(a.n_stars + 1) * CAT_ENTRY + 15u) & ~15u;
+        const uint32_t total = (uint32_t)(a.n_stars + 1) * 16u;
         mbar_expect_tx(s_bar, total);
         const unsigned char* src = reinterpret_cast<const unsigned char*>(a.cat32);
         unsigned char* dst = reinterpret_cast<unsigned char*>(s_cat);
@@ -106,8 +106,8 @@ __global__ void __launch_bounds__(TPB_SCAN, 1) split_scan_kernel(const KArgs a, 
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         const uint32_t idx = (w4[e >> 1] >> (16 * (e & 1))) & 0xffffu;
-                        const CatEnt sc = lds_cat(sb_cat, idx);
-                        more = cat_mag_ok(cf, sc);
+                        const float4 sc = lds_f4(sb_cat + idx * 16u);
+                        more = sc.w <= cf.magf;
                         if (more && prefilter_geom(cf, sc)) {
                             const uint32_t k = cnt & 7u;
                             // slot k of the buffer (k is not a compile-time constant: select, do not index)
@@ -202,13 +202,8 @@ __device__ __noinline__ void slow_trial_global(const KArgs* ap, const Ctx64* cp,
         }
         for (int sgm = 0; sgm < 2; ++sgm)
             for (int i = seg_lo[sgm]; i < seg_hi[sgm]; ++i) {
-#if defined(STMPM_CAT8)
-                const uint2 raw = __ldg(reinterpret_cast<const uint2*>(a.cat32) + i);
-                const CatEnt sc{raw.x, raw.y};
-#else
-                const CatEnt sc = __ldg(a.cat32 + i);
-#endif
-                if (cat_mag_ok(cf, sc) && prefilter_geom(cf, sc)) {
+                const float4 sc = __ldg(a.cat32 + i);
+                if (sc.w <= cf.magf && prefilter_geom(cf, sc)) {
                     const double4 rr = ld_rec(a.cat64 + i);
                     StarRec s;
                     s.x = rr.x; s.y = rr.y; s.z = rr.z;
