@@ -5,6 +5,7 @@ import torch
 from startrackermpm_b200.engine import TrialEngine, make_dist
 from bench import BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF, F_IDEAL, SEED
 eng = TrialEngine(0, f_ideal=F_IDEAL)
+if os.environ.get("MM_KEY_TABLE"): eng.set_tuning(key_table=int(os.environ["MM_KEY_TABLE"]))   # experiment knob
 d = make_dist(BASIC_MEAN, BASIC_SIGMA, THERMAL_COEF)
 N = 1 << 26
 cols = torch.empty((13, N), dtype=torch.float64, device="cuda")

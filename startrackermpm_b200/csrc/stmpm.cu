@@ -37,7 +37,9 @@ struct KArgs {
     int lk_bands;
     float lk_inv_band_h, lk_cone; // a trial whose scan cone exceeds lk_cone takes the sky-grid scan instead
     const MathTables* tables;
-    const uint8_t* lk_key;        // [n_lk_cells][KEY_ROLLS][KEY_LEVELS]: stars with mag <= KEY_M0 + (k+1)/16 on the array footprint, saturated at 255
+    const uint8_t* lk_key;        // [KEY_LEVELS][n_lk_cells][key_rolls]: stars with mag <= KEY_M0 + (k+1)/16 on the array footprint, saturated at 255
+                                  // (level-major: a run's MAX_MAGNITUDE sits in a few levels, whose slices — 41 KB disc, 330 KB footprint — stay cached)
+    int lk_cells;                 // n_lk_cells
     int key_rolls;                // orientation bins of the table handed to this launch (1 = the disc table, KEY_ROLLS = the footprint table)
     float key_roll_inv;           // 1 / symmetry period of the footprint's orientation (2/pi for a square array, 1/pi otherwise)
     int win;                      // trials per CTA sort window (multiple of 32, <= WIN_MAX)
@@ -208,7 +210,7 @@ __device__ __forceinline__ int work_key(const KArgs& a, const int2* __restrict__
     t -= floorf(t);
     const int rb = min(a.key_rolls - 1, max(0, (int)(t * (float)a.key_rolls)));
     const int lev = min(KEY_LEVELS - 1, (int)floorf((mm - KEY_M0) * 16.0f));
-    return lev < 0 ? 0 : (int)__ldg(a.lk_key + ((size_t)cell * a.key_rolls + rb) * KEY_LEVELS + lev);
+    return lev < 0 ? 0 : (int)__ldg(a.lk_key + ((size_t)lev * a.lk_cells + cell) * a.key_rolls + rb);
 }
 
 // ------------------------------------------------------------------------------------------------ fallback trial
@@ -1095,8 +1097,9 @@ struct stmpm_handle {
     int lk_bands = 0;
     float lk_cone = -1.0f;
     MathTables* tables = nullptr;
-    uint8_t* lk_key = nullptr;    // footprint work-key table [n_lk_cells][KEY_ROLLS][KEY_LEVELS]
-    uint8_t* lk_key_disc = nullptr;   // disc work-key table [n_lk_cells][KEY_LEVELS]
+    uint8_t* lk_key = nullptr;    // footprint work-key table [KEY_LEVELS][n_lk_cells][KEY_ROLLS]
+    uint8_t* lk_key_disc = nullptr;   // disc work-key table [KEY_LEVELS][n_lk_cells]
+    int lk_cells = 0;
     int tune_key_table = -1;      // -1 = per mode (disc for pre-sampled, footprint for native RNG), 0 = disc, 1 = footprint
     float key_roll_inv = 0.63661977f;
     bool have_catalog = false, have_sensor = false;
@@ -1275,10 +1278,20 @@ static int rebuild_lists(stmpm_handle* h) {
     h->lk_cone = (float)cone;
     cudaFree(h->lk_key); h->lk_key = nullptr;
     cudaFree(h->lk_key_disc); h->lk_key_disc = nullptr;
-    CK(cudaMalloc(&h->lk_key, key_tab.size()));
-    CK(cudaMemcpy(h->lk_key, key_tab.data(), key_tab.size(), cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&h->lk_key_disc, key_disc.size()));
-    CK(cudaMemcpy(h->lk_key_disc, key_disc.data(), key_disc.size(), cudaMemcpyHostToDevice));
+    {   // built cell-major (one pass over each cell's stars in magnitude order), stored level-major (see KArgs::lk_key)
+        std::vector<uint8_t> t_tab(key_tab.size()), t_disc(key_disc.size());
+        for (long long c = 0; c < n_cells; ++c)
+            for (int lev = 0; lev < KEY_LEVELS; ++lev) {
+                for (int k = 0; k < KEY_ROLLS; ++k)
+                    t_tab[((size_t)lev * n_cells + c) * KEY_ROLLS + k] = key_tab[((size_t)c * KEY_ROLLS + k) * KEY_LEVELS + lev];
+                t_disc[(size_t)lev * n_cells + c] = key_disc[(size_t)c * KEY_LEVELS + lev];
+            }
+        CK(cudaMalloc(&h->lk_key, t_tab.size()));
+        CK(cudaMemcpy(h->lk_key, t_tab.data(), t_tab.size(), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&h->lk_key_disc, t_disc.size()));
+        CK(cudaMemcpy(h->lk_key_disc, t_disc.data(), t_disc.size(), cudaMemcpyHostToDevice));
+    }
+    h->lk_cells = (int)n_cells;
     return 0;
 }
 
@@ -1648,7 +1661,7 @@ static int fill_common(stmpm_handle* h, KArgs& a, int precision) {
     a.inv_band_h = (float)((double)h->n_bands / M_PI);
     a.lk_band_tab = h->lk_band_tab; a.lk_off = h->lk_off; a.lk_list = h->lk_list; a.lk_bands = h->lk_bands;
     a.lk_inv_band_h = (float)((double)h->lk_bands / M_PI); a.lk_cone = h->lk_cone; a.tables = h->tables;
-    a.lk_key = h->lk_key; a.key_rolls = KEY_ROLLS; a.key_roll_inv = h->key_roll_inv;   // launch_trials picks the table per mode
+    a.lk_key = h->lk_key; a.lk_cells = h->lk_cells; a.key_rolls = KEY_ROLLS; a.key_roll_inv = h->key_roll_inv;   // launch_trials picks the table per mode
     a.f_ideal = h->cfg.f_ideal; a.f_ideal2 = h->cfg.f_ideal * h->cfg.f_ideal; a.half_u = h->cfg.half_u; a.half_v = h->cfg.half_v; a.n_min = h->cfg.n_min;
     a.hist_shift = 52 - h->cfg.hist_log2_sub; a.n_bins = h->n_bins;
     a.stats_len = STMPM_STATS_HEAD + h->n_bins;
