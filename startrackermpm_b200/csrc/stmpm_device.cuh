@@ -24,7 +24,10 @@
 
 namespace stmpm {
 
-constexpr int TPB = 512;          // threads per CTA (1 CTA / SM: the fp32 catalog lives in shared memory)
+#if !defined(STMPM_TPB)
+#define STMPM_TPB 512
+#endif
+constexpr int TPB = STMPM_TPB;          // threads per CTA (1 CTA / SM: the fp32 catalog lives in shared memory)
 #if !defined(STMPM_LIST_CAP)
 #define STMPM_LIST_CAP 48         // 32 measured -4.4 % (round 2, exp K: more drain rounds); larger does not fit beside the catalog
 #endif
