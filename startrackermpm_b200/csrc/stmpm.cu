@@ -688,6 +688,118 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                         star_step(rb);
                         ++j;
                     }
+#elif defined(STMPM_REBALANCE)
+                    // experiment (round 2, exp N): in-warp work donation.  The 32 trials of a group differ in survivor count (key
+                    // sorting leaves the star loop at ~0.77 lane occupancy with 256-trial windows); once every list is complete,
+                    // the lanes run their own stars up to K = 0.9 x the group's mean count, and at that warp-uniform point each
+                    // lane that has finished takes over the second half of the remaining stars of one lane that has not: the
+                    // m-th finished lane pairs with the lane of m-th largest remainder (rank by bit-sliced ballots, partner by
+                    // match.any).  The helper's plane context, Philox key and thresholds are overwritten by the donor's through
+                    // shuffles (its own are dead after its last star), its own B is parked; afterwards the partial B and count
+                    // go back by shuffle.  Oracle simulation: occupancy 0.77 -> 0.89.  B's summation order then depends on the
+                    // group: records are reproducible for a given launch geometry but no longer bit-identical across geometries.
+                    {
+                        constexpr unsigned FULL = 0xffffffffu;
+                        bool do_rebal = !__any_sync(FULL, scanning);
+                        int end = cnt;
+                        if (do_rebal) {
+                            const int K = ((int)__reduce_add_sync(FULL, (unsigned)cnt) * 29) >> 10;
+                            do_rebal = K >= 6;
+                            if (do_rebal) end = min(cnt, K);
+                        }
+                        int j = 0;
+                        unsigned role = (unsigned)lane;          // partner lane | helper << 8 | donor << 9
+                        volatile double b_park[9];
+                        volatile int nd_park = 0;
+                        volatile float mf_park = 0.0f;
+                        double4 rr = make_double4(0.0, 0.0, 0.0, 0.0);
+                        if (end > 0) rr = ld_rec(a.cat64 + lds_u16(sb_row));
+#pragma unroll 1
+                        for (int ph = 0; ph < 2; ++ph) {
+                            if (ph == 1) {
+                                const int rem = cnt - end;                                   // own stars not done yet
+                                const bool idle = rem == 0 && (use_list || !valid);         // (a fall-back trial keeps its context)
+                                const bool busy = rem >= 2;
+                                const unsigned idle_m = __ballot_sync(FULL, idle), busy_m = __ballot_sync(FULL, busy);
+                                j = end; end = cnt;
+                                if (idle_m != 0u && busy_m != 0u) {
+                                    unsigned eq = busy_m, gt = 0u;
+#pragma unroll
+                                    for (int b = 5; b >= 0; --b) {
+                                        const bool mine = (rem >> b) & 1;
+                                        const unsigned bm = __ballot_sync(FULL, busy && mine);
+                                        if (!mine) gt |= eq & bm;
+                                        eq &= mine ? bm : ~bm;
+                                    }
+                                    const unsigned lt_mask = (1u << lane) - 1u;
+                                    const int rank = __popc(gt) + __popc(eq & ~lt_mask & ~(1u << lane));
+                                    const int v = idle ? __popc(idle_m & lt_mask) : (busy ? rank : 64 + lane);
+                                    const unsigned other = __match_any_sync(FULL, v) & ~(1u << lane);
+                                    const int src = other ? (__ffs(other) - 1) : lane;
+                                    const bool helper = idle && other != 0u, donor = busy && other != 0u;
+                                    role = (unsigned)src | (helper ? 0x100u : 0u) | (donor ? 0x200u : 0u);
+                                    const int p_cnt = __shfl_sync(FULL, cnt, src), p_rem = __shfl_sync(FULL, rem, src);
+                                    const uint32_t p_row = __shfl_sync(FULL, sb_row, src);
+#define STMPM_XCHG(x) { const auto t_ = __shfl_sync(FULL, x, src); if (helper) x = t_; }
+#pragma unroll
+                                    for (int k = 0; k < 3; ++k) { STMPM_XCHG(c.NI[k]) STMPM_XCHG(c.EU[k]) STMPM_XCHG(c.EV[k]) }
+                                    STMPM_XCHG(c.np0) STMPM_XCHG(c.cu) STMPM_XCHG(c.cv) STMPM_XCHG(c.sx) STMPM_XCHG(c.sy)
+                                    STMPM_XCHG(ka) STMPM_XCHG(kb) STMPM_XCHG(cf.magf)
+                                    if (PREC == 32) { STMPM_XCHG(cf.sxf) STMPM_XCHG(cf.syf) STMPM_XCHG(cf.guard_hi) }
+#undef STMPM_XCHG
+                                    if (helper) {
+#pragma unroll
+                                        for (int k = 0; k < 9; ++k) { b_park[k] = B[k]; B[k] = 0.0; }
+                                        nd_park = n_det; n_det = 0;
+                                        if (INSTR == 2) { mf_park = mag_faintest; mag_faintest = -INFINITY; }
+                                        sb_row = p_row; end = p_cnt; j = p_cnt - (p_rem >> 1);
+                                    } else if (donor) {
+                                        end = cnt - (rem >> 1);
+                                    }
+                                }
+                                if (j < end) rr = ld_rec(a.cat64 + lds_u16(sb_row + (uint32_t)j * (TPB * 2u)));
+                            }
+                            for (; j < end; ++j) {
+                                StarRec s;
+                                s.x = rr.x; s.y = rr.y; s.z = rr.z;
+                                s.star_id = (uint32_t)(__double_as_longlong(rr.w) & 0xffffffffll);
+                                if (INSTR == 2) s.mag = __int_as_float((int)(__double_as_longlong(rr.w) >> 32));
+                                const bool mag_ok = __int_as_float(__double2hiint(rr.w)) <= cf.magf;   // see the default loop below
+                                if (j + 1 < end) rr = ld_rec(a.cat64 + lds_u16(sb_row + (uint32_t)(j + 1) * (TPB * 2u)));
+                                uint32_t x0, x1;
+                                philox2x32_10(s.star_id, kb, ka, x0, x1);
+                                bool det;
+                                if (PREC == 64) det = star_exact(c, tabs, s, x0, x1, a.f_ideal, a.f_ideal2, a.half_u, a.half_v, B);
+                                else det = star_f32(c, cf, tabs, s, x0, x1, a.f_ideal, a.f_ideal2, a.half_u, a.half_v, B);
+                                n_det += (det && mag_ok) ? 1 : 0;
+                                if (INSTR == 2 && det) mag_faintest = fmaxf(mag_faintest, s.mag);
+                            }
+                            __syncwarp();
+                            if (!do_rebal) break;
+                        }
+                        if (__any_sync(FULL, (role & 0x300u) != 0u)) {          // partial sums back to their trials
+                            const int src = (int)(role & 31u);
+                            const bool helper = (role & 0x100u) != 0u, donor = (role & 0x200u) != 0u;
+#pragma unroll
+                            for (int k = 0; k < 9; ++k) {
+                                const double t = __shfl_sync(FULL, B[k], src);
+                                if (donor) B[k] += t;
+                            }
+                            const int tn = __shfl_sync(FULL, n_det, src);
+                            if (donor) n_det += tn;
+                            if (INSTR == 2) {
+                                const float tm = __shfl_sync(FULL, mag_faintest, src);
+                                if (donor) mag_faintest = fmaxf(mag_faintest, tm);
+                            }
+                            if (helper) {
+#pragma unroll
+                                for (int k = 0; k < 9; ++k) B[k] = b_park[k];
+                                n_det = nd_park;
+                                if (INSTR == 2) mag_faintest = mf_park;
+                                sb_row = sb + (uint32_t)OFF_LIST + threadIdx.x * 2u;
+                            }
+                        }
+                    }
 #else
                     double4 rr = make_double4(0.0, 0.0, 0.0, 0.0);
                     if (cnt > 0) rr = ld_rec(a.cat64 + lds_u16(sb_row));
