@@ -371,9 +371,20 @@ __device__ STMPM_LIBM_INLINE double atan2_libm(double y, double x) { return atan
 
 __device__ __forceinline__ void setup64(const TrialParams& p, Ctx64& c) {
     double sa, ca, sd, cd, sr, cr;
+#if defined(STMPM_SINCOS_LOOP)
+    {   // ONE copy of libm's sincos (~160 instructions) run three times instead of three inlined copies: the per-trial code is
+        // executed once per group by 16 warps in 16 different places, and its footprint decides whether the hot instruction
+        // stream (~35 KB) fits the 32 KB L1.5 instruction cache (round 2, exp O)
+        double ang[3] = {p.ra, p.dec, p.roll}, sn[3], cs[3];
+#pragma unroll 1
+        for (int i = 0; i < 3; ++i) sincos(ang[i], &sn[i], &cs[i]);
+        sa = sn[0]; ca = cs[0]; sd = sn[1]; cd = cs[1]; sr = sn[2]; cr = cs[2];
+    }
+#else
     sincos_libm(p.ra, &sa, &ca);
     sincos_libm(p.dec, &sd, &cd);
     sincos_libm(p.roll, &sr, &cr);
+#endif
     // C = Rz(ra) Ry(pi/2 - dec) Rz(roll)   (MODEL.md §2; primitives: constants.py:81-94)
     c.C[0] = ca * sd * cr - sa * sr;  c.C[1] = -ca * sd * sr - sa * cr;  c.C[2] = ca * cd;
     c.C[3] = sa * sd * cr + ca * sr;  c.C[4] = -sa * sd * sr + ca * cr;  c.C[5] = sa * cd;
