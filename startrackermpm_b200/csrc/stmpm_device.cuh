@@ -369,6 +369,35 @@ __device__ __forceinline__ void sincos_small(double x, double* s, double* c) {
 __device__ STMPM_LIBM_INLINE void sincos_libm(double x, double* s, double* c) { sincos(x, s, c); }
 __device__ STMPM_LIBM_INLINE double atan2_libm(double y, double x) { return atan2(y, x); }
 
+// sin / cos of an attitude angle, |x| <= 1000: three-term Cody-Waite reduction by pi/2 (exact with FMA for |k| < 2^10), fdlibm's
+// kernel polynomials on |r| <= pi/4, quadrant by the low bits of the rounded quotient.  <= 2.3e-16 absolute error (checked against
+// exact-arithmetic emulation over +-1000): the same 1-ulp class as libm, at ~40 instructions instead of libm's ~76 executed (its
+// fast path carries the hand-over to a Payne-Hanek slow path that attitude angles never reach).  Round 2, exp R.
+__device__ __forceinline__ void sincos_attitude(double x, double* sn, double* cs) {
+    const double t = fma(x, 0.6366197723675814, 6755399441055744.0);             // 2/pi; 1.5 * 2^52: t's low word = rint(x * 2/pi)
+    const double j = t - 6755399441055744.0;
+    const int q = __double2loint(t);
+    double r = fma(-j, 1.5707963267948966, x);
+    r = fma(-j, 6.123233995736766e-17, r);
+    r = fma(-j, -1.4973849048591698e-33, r);
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double s = fma(r * z, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double c = fma(z * z, pc, fma(z, -0.5, 1.0));
+    const double a = (q & 1) ? c : s, b = (q & 1) ? s : c;                        // q = 0: (s, c)  1: (c, -s)  2: (-s, -c)  3: (-c, s)
+    *sn = (q & 2) ? -a : a;
+    *cs = ((q + 1) & 2) ? -b : b;
+}
+
 __device__ __forceinline__ void setup64(const TrialParams& p, Ctx64& c) {
     double sa, ca, sd, cd, sr, cr;
 #if defined(STMPM_SINCOS_LOOP)
@@ -377,6 +406,22 @@ __device__ __forceinline__ void setup64(const TrialParams& p, Ctx64& c) {
         // stream (~35 KB) fits the 32 KB L1.5 instruction cache (round 2, exp O)
         // (through local arrays: no_instruction 0.24 -> 0.12 per issue but long_scoreboard +0.23 and -2.9 %; this form rotates
         // the results through registers instead)
+        double x = p.ra;
+        sa = ca = sd = cd = sr = cr = 0.0;
+#pragma unroll 1
+        for (int i = 0; i < 3; ++i) {
+            double s_, c_;
+            sincos(x, &s_, &c_);
+            sa = sd; ca = cd; sd = sr; cd = cr; sr = s_; cr = c_;
+            x = i == 0 ? p.dec : p.roll;
+        }
+    }
+#elif defined(STMPM_FAST_SINCOS)
+    if (fmax(fabs(p.ra), fmax(fabs(p.dec), fabs(p.roll))) <= 1000.0) {     // practically always, and warp-uniform
+        sincos_attitude(p.ra, &sa, &ca);
+        sincos_attitude(p.dec, &sd, &cd);
+        sincos_attitude(p.roll, &sr, &cr);
+    } else {                                                                // one cold copy of libm's sincos for far-out angles
         double x = p.ra;
         sa = ca = sd = cd = sr = cr = 0.0;
 #pragma unroll 1
