@@ -36,6 +36,7 @@ struct KArgs {
     const uint16_t* lk_list;      // star indices into the sorted catalog; each list ends with index n_stars (the +inf dummy)
     int lk_bands;
     float lk_inv_band_h, lk_cone; // a trial whose scan cone exceeds lk_cone takes the sky-grid scan instead
+    float lk_cone_tan;            // tan(lk_cone - 0.002): what a trial's cone_t is compared with
     const MathTables* tables;
     const uint8_t* lk_key;        // [KEY_LEVELS][n_lk_cells][key_rolls]: stars with mag <= KEY_M0 + (k+1)/16 on the array footprint, saturated at 255
                                   // (level-major: a run's MAX_MAGNITUDE sits in a few levels, whose slices — 41 KB disc, 330 KB footprint — stay cached)
@@ -69,7 +70,7 @@ struct KArgs {
 // last), so ptxas addresses them as [reg + immediate] instead of re-deriving bases from kernel parameters per access.
 // CTA-wide sort window: two permutation buffers (window w uses buffer w & 1: w + 1 is built while w is consumed), the keys
 // and the 256 bin counters (16 bit, two per atomic word) of the window being built, and the scheduler words.
-constexpr size_t WIN_BYTES = 2 * 2 * (size_t)WIN_MAX /*perm u16 x2*/ + WIN_MAX /*keys u8*/ + 2 * KEY_BINS /*counters u16*/ + 32 /*sched*/;
+constexpr size_t WIN_BYTES = 2 * 2 * (size_t)WIN_MAX /*perm u16 x2*/ + WIN_MAX /*keys u8*/ + 2 * KEY_BINS /*counters u16*/ + 32 /*sched*/ + 64 /*window meta x2*/;
 static_assert(WIN_MAX <= 4096 && WIN_MAX % 128 == 0 && KEY_BINS == 256, "16-bit bin counters; the key pass runs 128 trials per round");
 #if !defined(STMPM_KEY_SLOTS)
 #define STMPM_KEY_SLOTS 4
@@ -228,7 +229,8 @@ __device__ __noinline__ void band_walk_trial(const Ctx64* cp, const Ctx32* cfp, 
                                              double half_u, double half_v, uint32_t sb, uint32_t ka, uint32_t kb, double* B_out,
                                              int* n_det_out, float* mag_out, unsigned long long* ins) {
     const Ctx64 c = *cp;
-    const Ctx32 cf = *cfp;
+    Ctx32 cf = *cfp;
+    cf.cone = cone_angle(cf);
     unsigned char* smem = reinterpret_cast<unsigned char*>(__cvta_shared_to_generic((size_t)sb));
     const float4* s_cat = reinterpret_cast<const float4*>(smem + OFF_CAT);
     const int2* s_band = reinterpret_cast<const int2*>(smem + OFF_BAND);
@@ -338,6 +340,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
     unsigned int* w_hist = reinterpret_cast<unsigned int*>(w_key + WIN_MAX);              // 256 16-bit counters, 2 per word
     int* s_sched = reinterpret_cast<int*>(w_hist + KEY_BINS / 2);                         // claim, built, reads[2]
     volatile int* v_sched = s_sched;
+    long long* s_meta = reinterpret_cast<long long*>(s_sched + 8);                        // per window buffer: rec0, seg, nw
 
     // ---- stage the catalog + tables into shared memory (once per CTA; the CTA is persistent).  The 146 KB fp32 catalog
     // goes through the TMA unit: one elected thread issues cp.async.bulk chunks that complete on an mbarrier while the
@@ -375,6 +378,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
     // No CTA barrier: window w + 1 is built by the warp that claims the first group of window w, while the others consume w.
     const int win = a.win;                                 // trials per window, multiple of 32, <= WIN_MAX
     const int gpw = win >> 5;                              // groups per window
+    const int gpw_shift = (gpw & (gpw - 1)) == 0 ? __ffs(gpw) - 1 : -1;
     const long long n_units = a.n_segments * (long long)a.parts_per_segment;
     const long long my_units = (n_units - (long long)blockIdx.x + gridDim.x - 1) / gridDim.x;
     const int n_windows = (int)(my_units * a.windows_per_unit);
@@ -390,6 +394,8 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
     int build_w = (warp == 0 && n_windows > 0) ? 0 : -1;   // pending window to build (warp 0 builds the first one)
     bool have_group = false, aborted = false;
     int grp_w = 0, grp_r = 0, grp_q = 0;
+    long long grp_rec0 = 0, grp_seg = 0;
+    int grp_nw = 0;
     for (;;) {
         if (build_w >= 0) {
             // ================= key pass + counting sort of window build_w into permutation buffer build_w & 1
@@ -418,6 +424,11 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
             const int nw = (int)max(0LL, min((long long)win, t_end - wb));     // valid trials in this window
             const long long rec0 = seg * a.trials_per_segment + wb;
             const DistDev* dist = (MODE == 1) ? ((a.n_segments == 1) ? &a.dist0 : a.dists + seg) : nullptr;
+#if defined(STMPM_WIN_META)
+            // the window's place in the launch, for its groups: they read three words instead of redoing ~100 instructions
+            // of 64-bit index arithmetic (two divisions) per group (exp S)
+            if (lane == 0) { s_meta[(bw & 1) * 4] = rec0; s_meta[(bw & 1) * 4 + 1] = seg; s_meta[(bw & 1) * 4 + 2] = nw; }
+#endif
 #pragma unroll
             for (int q = 0; q < KEY_BINS / 2 / 32; ++q) w_hist[lane + 32 * q] = 0u;
             __syncwarp();
@@ -530,7 +541,11 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
             if (lane == 0) g = atomicAdd(s_sched, 1);
             g = __shfl_sync(0xffffffffu, g, 0);
             if (g >= n_groups) break;
+#if defined(STMPM_WIN_META)
+            grp_w = gpw_shift >= 0 ? (g >> gpw_shift) : g / gpw;   // windows of 2^k groups (the defaults): no division
+#else
             grp_w = g / gpw;
+#endif
             const int gi = g - grp_w * gpw;
             if (v_sched[1] <= grp_w) {
                 const unsigned long long t0 = global_ns();
@@ -543,6 +558,9 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
             __threadfence_block();
             grp_q = gi * 32 + lane;                                   // position in key order
             grp_r = s_perm[(grp_w & 1) * WIN_MAX + grp_q];
+#if defined(STMPM_WIN_META)
+            grp_rec0 = s_meta[(grp_w & 1) * 4]; grp_seg = s_meta[(grp_w & 1) * 4 + 1]; grp_nw = (int)s_meta[(grp_w & 1) * 4 + 2];
+#endif
             __threadfence_block();                        // the entry is in a register before the slot is reported free
             __syncwarp();
             // (with sorted parameter staging the buffer also holds the group's staged columns: it is reported free only
@@ -555,6 +573,10 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
 
         // ================= one group: 32 trials of window grp_w, consecutive in key order
         {
+#if defined(STMPM_WIN_META)
+            const long long seg = grp_seg, rec0 = grp_rec0;
+            const int nw = grp_nw;
+#else
             const long long ku = grp_w / a.windows_per_unit;
             const long long unit = (long long)blockIdx.x + ku * gridDim.x;
             const long long seg = unit / a.parts_per_segment;
@@ -564,6 +586,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
             const long long wb = t_begin + (long long)(grp_w - ku * a.windows_per_unit) * win;
             const int nw = (int)max(0LL, min((long long)win, t_end - wb));
             const long long rec0 = seg * a.trials_per_segment + wb;
+#endif
             const DistDev* dist = (MODE == 1) ? ((a.n_segments == 1) ? &a.dist0 : a.dists + seg) : nullptr;
             if (seg != cur_seg) {
                 if (want_stats && cur_seg >= 0)
@@ -624,7 +647,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                 // from the raw angles (fp32 rounding moves it by < 4e-5 rad; the lists carry a > 3e-3 rad margin).
                 Ctx32 cf;
                 window_and_cone(p, hu32, hv32, cf);
-                const bool use_list = cf.cone <= a.lk_cone;
+                const bool use_list = cf.cone_t <= a.lk_cone_tan;
                 const float ra_f = (float)p.ra, dec_f = (float)p.dec;
                 const bool early = use_list && fabsf(dec_f) <= 1.57079633f && fabsf(ra_f) <= 256.0f;
                 uint32_t l_off = 0;
@@ -1788,6 +1811,7 @@ static int fill_common(stmpm_handle* h, KArgs& a, int precision) {
     a.inv_band_h = (float)((double)h->n_bands / M_PI);
     a.lk_band_tab = h->lk_band_tab; a.lk_off = h->lk_off; a.lk_list = h->lk_list; a.lk_bands = h->lk_bands;
     a.lk_inv_band_h = (float)((double)h->lk_bands / M_PI); a.lk_cone = h->lk_cone; a.tables = h->tables;
+    a.lk_cone_tan = (float)(std::tan(std::min((double)h->lk_cone - 0.002, 1.55)) * (1.0 - 1e-6));
     a.lk_key = h->lk_key; a.lk_cells = h->lk_cells; a.key_rolls = KEY_ROLLS; a.key_roll_inv = h->key_roll_inv;   // launch_trials picks the table per mode
     a.f_ideal = h->cfg.f_ideal; a.f_ideal2 = h->cfg.f_ideal * h->cfg.f_ideal; a.half_u = h->cfg.half_u; a.half_v = h->cfg.half_v; a.n_min = h->cfg.n_min;
     a.hist_shift = 52 - h->cfg.hist_log2_sub; a.n_bins = h->n_bins;

@@ -340,7 +340,8 @@ struct Ctx32 {
     float NI[3], EU[3], EV[3], np0, cu, cv, limu, limv, magf;
     float sxf, syf;               // fp32 mode: |BASE_DEV_X|, |BASE_DEV_Y|
     int guard_hi;                 // fp32 mode: high word of the guard distance around the array edges (see star_f32)
-    float ra0, dec0, cone;        // boresight (lookup-cell key) and scan-cone half angle
+    float ra0, dec0, cone;        // boresight (lookup-cell key) and scan-cone half angle (cone: see cone_angle)
+    float cone_t;                 // tangent of the scan-cone half angle without its 0.002 rad margin; +inf = no usable cone
 };
 
 __device__ __forceinline__ float opaque(float x) {   // stop ptxas re-deriving an fp32 copy from its fp64 source at every
@@ -485,11 +486,24 @@ __device__ __forceinline__ void window_and_cone(const TrialParams& p, float half
     // (double)mag <= maxmag  <=>  mag <= round-down-to-float(maxmag); clamped to a finite value so that the +inf
     // magnitude of the candidate lists' terminator entry never passes
     c.magf = opaque(fminf(__double2float_rd(p.maxmag), 3.0e38f));
+#if defined(STMPM_CONE_ATAN)
     const float reach = 1.41421357f * (fmaxf(half_u, half_v) + noise) + hypotf((float)p.ex, (float)p.ey) + 1.0f;
+#else
+    const float reach = 1.41421357f * (fmaxf(half_u, half_v) + noise) + (fabsf((float)p.ex) + fabsf((float)p.ey)) + 1.0f;   // >= the hypotenuse
+#endif
     const float tilt = fminf((fabsf((float)p.phi) + fabsf((float)p.theta)) * 0.0174532925f, 0.5f);
     const float depth = (float)p.f + (float)p.ez - reach * tilt;
+    // The hot path only asks "is the cone inside the one the candidate lists were built for": it compares tangents
+    // (KArgs::lk_cone_tan, host-computed) and never needs the angle — atanf, a full-precision division and hypotf were ~55
+    // instructions per trial.  The fall-back walks derive the angle themselves (cone_angle).
+    c.cone_t = (depth > 1.0f) ? __fdividef(reach, depth) * 1.000001f : INFINITY;
+#if defined(STMPM_CONE_ATAN)
     c.cone = (depth > 1.0f) ? atanf(reach / depth) + 0.002f : 3.2f;
+#else
+    c.cone = 3.2f;
+#endif
 }
+__device__ __forceinline__ float cone_angle(const Ctx32& c) { return c.cone_t < 1e30f ? atanf(c.cone_t) + 0.002f : 3.2f; }
 
 // fp32 copies of the plane geometry (what prefilter_geom reads).  Cheap enough to redo for the rare re-scan, so the twelve
 // floats need not stay live across the fp64 star loop.

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(TPB_SCAN, 1) split_scan_kernel(const KArgs a, 
                 __stcg(rp + 4, make_double2(p.theta, p.psi));   __stcg(rp + 5, make_double2(p.devx, p.devy));
             }
             Ctx32 cf;
-            const bool ok = setup32(p, hu32, hv32, cf) && cf.cone <= a.lk_cone;
+            const bool ok = setup32(p, hu32, hv32, cf) && cf.cone_t <= a.lk_cone_tan;
             if (ok) {
                 const uint16_t* __restrict__ lp =
                     a.lk_list + __ldg(a.lk_off + lookup_cell(s_lkband, a.lk_bands, a.lk_inv_band_h, cf.ra0, cf.dec0));
@@ -174,7 +174,8 @@ __device__ __noinline__ void slow_trial_global(const KArgs* ap, const Ctx64* cp,
                                                double* B_out, int* n_det_out) {
     const KArgs& a = *ap;
     const Ctx64 c = *cp;
-    const Ctx32 cf = *cfp;
+    Ctx32 cf = *cfp;
+    cf.cone = cone_angle(cf);
     double B[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     int n_det = 0;
     const int b_lo = max(0, (int)floorf((cf.dec0 - cf.cone + 1.57079633f) * a.inv_band_h));
