@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
             const int nw = (int)max(0LL, min((long long)win, t_end - wb));     // valid trials in this window
             const long long rec0 = seg * a.trials_per_segment + wb;
             const DistDev* dist = (MODE == 1) ? ((a.n_segments == 1) ? &a.dist0 : a.dists + seg) : nullptr;
-#if defined(STMPM_WIN_META)
+#if !defined(STMPM_NO_WIN_META)
             // the window's place in the launch, for its groups: they read three words instead of redoing ~100 instructions
             // of 64-bit index arithmetic (two divisions) per group (exp S)
             if (lane == 0) { s_meta[(bw & 1) * 4] = rec0; s_meta[(bw & 1) * 4 + 1] = seg; s_meta[(bw & 1) * 4 + 2] = nw; }
@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
             if (lane == 0) g = atomicAdd(s_sched, 1);
             g = __shfl_sync(0xffffffffu, g, 0);
             if (g >= n_groups) break;
-#if defined(STMPM_WIN_META)
+#if !defined(STMPM_NO_WIN_META)
             grp_w = gpw_shift >= 0 ? (g >> gpw_shift) : g / gpw;   // windows of 2^k groups (the defaults): no division
 #else
             grp_w = g / gpw;
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
             __threadfence_block();
             grp_q = gi * 32 + lane;                                   // position in key order
             grp_r = s_perm[(grp_w & 1) * WIN_MAX + grp_q];
-#if defined(STMPM_WIN_META)
+#if !defined(STMPM_NO_WIN_META)
             grp_rec0 = s_meta[(grp_w & 1) * 4]; grp_seg = s_meta[(grp_w & 1) * 4 + 1]; grp_nw = (int)s_meta[(grp_w & 1) * 4 + 2];
 #endif
             __threadfence_block();                        // the entry is in a register before the slot is reported free
@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
 
         // ================= one group: 32 trials of window grp_w, consecutive in key order
         {
-#if defined(STMPM_WIN_META)
+#if !defined(STMPM_NO_WIN_META)
             const long long seg = grp_seg, rec0 = grp_rec0;
             const int nw = grp_nw;
 #else

@@ -417,7 +417,7 @@ __device__ __forceinline__ void setup64(const TrialParams& p, Ctx64& c) {
             x = i == 0 ? p.dec : p.roll;
         }
     }
-#elif defined(STMPM_FAST_SINCOS)
+#elif !defined(STMPM_LIBM_SINCOS)
     if (fmax(fabs(p.ra), fmax(fabs(p.dec), fabs(p.roll))) <= 1000.0) {     // practically always, and warp-uniform
         sincos_attitude(p.ra, &sa, &ca);
         sincos_attitude(p.dec, &sd, &cd);
