@@ -690,7 +690,7 @@ __device__ __forceinline__ bool star_f32(const Ctx64& c, const Ctx32& cf, const 
 // 2 atan2(|q_v|, |q_w|) of the optimal rotation A_est C (MODEL.md §4).  Returns arcsec.
 __device__ __forceinline__ double quest_error_arcsec(const double* __restrict__ Bi, const double* __restrict__ C,
                                                      int n_det) {
-    const double w = 1.0 / (double)n_det;
+    const double w = fast_div(1.0, (double)n_det);      // a common scale of B (6e-14 relative): the quaternion does not depend on it
     double B[9];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -725,7 +725,11 @@ __device__ __forceinline__ double quest_error_arcsec(const double* __restrict__ 
     const double X0 = alpha * Z0 + beta * SZ0 + (S00 * SZ0 + S01 * SZ1 + S02 * SZ2);
     const double X1 = alpha * Z1 + beta * SZ1 + (S01 * SZ0 + S11 * SZ1 + S12 * SZ2);
     const double X2 = alpha * Z2 + beta * SZ2 + (S02 * SZ0 + S12 * SZ1 + S22 * SZ2);
-    const double vn = sqrt(X0 * X0 + X1 * X1 + X2 * X2);
+    // |X| by a MUFU-seeded reciprocal square root + one Newton step (2^-44 relative: 1e-17 rad on an arcsecond-class error)
+    // instead of libm's correctly rounded sqrt with its special-case branches; an exact zero (or a denormal) stays zero
+    const double n2 = X0 * X0 + X1 * X1 + X2 * X2;
+    const double yr = seed_rsqrt(fmax(n2, 1e-290));
+    const double vn = n2 >= 1e-290 ? n2 * (yr * fma(-0.5 * n2 * yr, yr, 1.5)) : 0.0;
     // theta = 2 atan2(|q_v|, |q_w|).  Attitude errors are arcseconds to a few degrees: for t = |q_v| / |q_w| <= 0.03 the
     // odd series to t^9 is exact to 5e-17 relative (next term t^10 / 11) and replaces libm's ~90-instruction atan2; anything
     // larger (or a zero / non-finite gamma: the comparison is then false) takes libm.
