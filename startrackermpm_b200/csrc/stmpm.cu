@@ -75,6 +75,14 @@ static_assert(WIN_MAX <= 4096 && WIN_MAX % 128 == 0 && KEY_BINS == 256, "16-bit 
 #if !defined(STMPM_KEY_SLOTS)
 #define STMPM_KEY_SLOTS 4
 #endif
+// Which instantiations run two stars per star-loop iteration (exp W, same box): pre-sampled fp64 +4.6 % with it; fp32 mode -5 %
+// (3.08 -> 2.92e9: its loop spills at two stars) and native RNG -0.7 % — those keep the single-star loop.
+#if !defined(STMPM_TWO_STARS_F32)
+#define STMPM_TWO_STARS_F32 0
+#endif
+#if !defined(STMPM_TWO_STARS_RNG)
+#define STMPM_TWO_STARS_RNG 0
+#endif
 constexpr int KS = STMPM_KEY_SLOTS;    // key pass: 32 KS trials per round (the round's loads are issued before their first use)
 constexpr int LK_BANDS = 180;          // 1-degree lookup grid
 constexpr int MAX_BANDS = 256;         // sky-grid declination bands (fallback scan)
@@ -368,6 +376,12 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
 
     const float hu32 = (float)a.half_u, hv32 = (float)a.half_v;
     const bool want_stats = a.stats != nullptr;
+    // star loop: two stars per iteration (exp U) or one; per instantiation, by measurement (exp V, W)
+#if defined(STMPM_ONE_STAR)
+    constexpr bool TWO_STARS = false;
+#else
+    constexpr bool TWO_STARS = (PREC == 64 || STMPM_TWO_STARS_F32) && (MODE == 0 || STMPM_TWO_STARS_RNG);
+#endif
 
     // ---- work distribution.  The CTA owns units blockIdx.x, blockIdx.x + gridDim.x, ... (unit = a contiguous range of
     // one segment's trials); a unit is cut into windows of `win` trials.  Each window is ordered by work key ONCE for the
@@ -835,6 +849,53 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                         }
                     }
 #else
+                    if (TWO_STARS) {
+                    // Two stars per iteration (round 2, exp U): two independent Philox / Box-Muller / projection chains side by
+                    // side supply the instruction-level parallelism that three resident warps per scheduler do not; B is
+                    // accumulated in star order, so every record is what the single-star loop (below, -DSTMPM_ONE_STAR) writes.
+                    // The records of stars j+2, j+3 are in flight while j, j+1 are evaluated.
+                        double4 r0 = make_double4(0.0, 0.0, 0.0, 0.0), r1 = r0;
+                        if (cnt > 0) r0 = ld_rec(a.cat64 + lds_u16(sb_row));
+                        if (cnt > 1) r1 = ld_rec(a.cat64 + lds_u16(sb_row + (uint32_t)(TPB * 2u)));
+                        for (int j = 0; j < cnt; j += 2) {
+                            const bool has1 = j + 1 < cnt;     // odd count: the second slot re-evaluates a stale record, result dropped
+                            StarRec s0, s1;
+                            s0.x = r0.x; s0.y = r0.y; s0.z = r0.z;
+                            s0.star_id = (uint32_t)(__double_as_longlong(r0.w) & 0xffffffffll);
+                            s1.x = r1.x; s1.y = r1.y; s1.z = r1.z;
+                            s1.star_id = (uint32_t)(__double_as_longlong(r1.w) & 0xffffffffll);
+                            if (INSTR == 2) {
+                                s0.mag = __int_as_float((int)(__double_as_longlong(r0.w) >> 32));
+                                s1.mag = __int_as_float((int)(__double_as_longlong(r1.w) >> 32));
+                            }
+                            // the magnitude word takes part in the decision: see the single-star loop (keeps it alive)
+                            const bool ok0 = __int_as_float(__double2hiint(r0.w)) <= cf.magf;
+                            const bool ok1 = __int_as_float(__double2hiint(r1.w)) <= cf.magf;
+                            if (j + 2 < cnt) r0 = ld_rec(a.cat64 + lds_u16(sb_row + (uint32_t)(j + 2) * (TPB * 2u)));
+                            if (j + 3 < cnt) r1 = ld_rec(a.cat64 + lds_u16(sb_row + (uint32_t)(j + 3) * (TPB * 2u)));
+                            uint32_t x00, x01, x10, x11;
+                            philox2x32_10(s0.star_id, kb, ka, x00, x01);
+                            philox2x32_10(s1.star_id, kb, ka, x10, x11);
+                            double b0x, b0y, b0z, b1x, b1y, b1z;
+                            bool d0, d1;
+                            if (PREC == 64) {
+                                d0 = star_eval64(c, tabs, s0, x00, x01, a.f_ideal, a.f_ideal2, a.half_u, a.half_v, b0x, b0y, b0z);
+                                d1 = star_eval64(c, tabs, s1, x10, x11, a.f_ideal, a.f_ideal2, a.half_u, a.half_v, b1x, b1y, b1z);
+                            } else {
+                                bool g0, g1;
+                                d0 = star_eval32(c, cf, tabs, s0, x00, x01, a.f_ideal, a.f_ideal2, a.half_u, a.half_v, b0x, b0y, b0z, g0);
+                                d1 = star_eval32(c, cf, tabs, s1, x10, x11, a.f_ideal, a.f_ideal2, a.half_u, a.half_v, b1x, b1y, b1z, g1);
+                                if (g0) d0 = star_eval64(c, tabs, s0, x00, x01, a.f_ideal, a.f_ideal2, a.half_u, a.half_v, b0x, b0y, b0z);
+                                if (g1) d1 = star_eval64(c, tabs, s1, x10, x11, a.f_ideal, a.f_ideal2, a.half_u, a.half_v, b1x, b1y, b1z);
+                            }
+                            d1 = d1 && has1;
+                            if (d0) star_accumulate(B, s0, b0x, b0y, b0z);
+                            if (d1) star_accumulate(B, s1, b1x, b1y, b1z);
+                            n_det += ((d0 && ok0) ? 1 : 0) + ((d1 && ok1) ? 1 : 0);
+                            if (INSTR == 2 && d0) mag_faintest = fmaxf(mag_faintest, s0.mag);
+                            if (INSTR == 2 && d1) mag_faintest = fmaxf(mag_faintest, s1.mag);
+                        }
+                    } else {
                     double4 rr = make_double4(0.0, 0.0, 0.0, 0.0);
                     if (cnt > 0) rr = ld_rec(a.cat64 + lds_u16(sb_row));
 #if defined(STMPM_IDX_AHEAD)
@@ -861,8 +922,8 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
 #else
                         if (j + 1 < cnt) rr = ld_rec(a.cat64 + lds_u16(sb_row + (uint32_t)(j + 1) * (TPB * 2u)));
 #endif
-                        // (hand-pipelining Philox one star ahead, or two stars per iteration, both measured slower:
-                        // ptxas already overlaps the integer chain with the fp64 one, and extra live state spills)
+                        // (hand-pipelining Philox one star ahead, or two stars per iteration, both measured slower AT 128
+                        // REGISTERS — extra live state spills; with 168 registers the two-star loop above wins)
                         uint32_t x0, x1;
                         philox2x32_10(s.star_id, kb, ka, x0, x1);
                         bool det;
@@ -870,6 +931,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                         else det = star_f32(c, cf, tabs, s, x0, x1, a.f_ideal, a.f_ideal2, a.half_u, a.half_v, B);
                         n_det += (det && mag_ok) ? 1 : 0;
                         if (INSTR == 2 && det) mag_faintest = fmaxf(mag_faintest, s.mag);
+                    }
                     }
 #endif
                     cnt = 0;

@@ -24,12 +24,15 @@
 
 namespace stmpm {
 
+// 384 threads (12 warps, 168 registers: no spills) running TWO stars per star-loop iteration beat 512 threads (16 warps, 128
+// registers) running one: +4.7 % (round 2, exp U) — the loop is bound by dependency latency, and a second independent chain per
+// thread hides more of it than a fourth warp per scheduler.  -DSTMPM_TPB=512 -DSTMPM_ONE_STAR -DSTMPM_LIST_CAP=48 rebuilds v16.
 #if !defined(STMPM_TPB)
-#define STMPM_TPB 512
+#define STMPM_TPB 384
 #endif
 constexpr int TPB = STMPM_TPB;          // threads per CTA (1 CTA / SM: the fp32 catalog lives in shared memory)
 #if !defined(STMPM_LIST_CAP)
-#define STMPM_LIST_CAP 48         // 32 measured -4.4 % (round 2, exp K: more drain rounds); larger does not fit beside the catalog
+#define STMPM_LIST_CAP 64         // 48 KB at 384 threads; 48: -2.4 %, 32: -4.4 % (more drain rounds); larger does not fit beside the catalog
 #endif
 constexpr int LIST_CAP = STMPM_LIST_CAP;   // per-thread survivor list in shared memory (phase A -> phase B hand-off), drained in rounds
 constexpr int WIN_MAX = 2048;     // largest CTA sort window (trials)
@@ -88,7 +91,14 @@ STMPM_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, 
 STMPM_HD void philox2x32_10(uint32_t c0, uint32_t c1, uint32_t k, uint32_t& o0, uint32_t& o1) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
+#if defined(__CUDA_ARCH__) && defined(STMPM_PHILOX_WIDE)
+        // experiment (round 2, exp V): force ONE IMAD.WIDE per round (ptxas splits the second chain of the two-star loop
+        // into IMAD + IMAD.HI)
+        uint32_t hi, lo;
+        asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(c0), "r"(PHILOX2_M));
+#else
         const uint32_t hi = mulhi32(PHILOX2_M, c0), lo = PHILOX2_M * c0;
+#endif
         c0 = hi ^ k ^ c1;
         c1 = lo;
         k += PHILOX_W0;
@@ -627,6 +637,33 @@ __device__ __forceinline__ bool star_exact(const Ctx64& c, const Tab T, const St
     return det;
 }
 
+// Two stars per star-loop iteration (round 2, exp U; -DSTMPM_ONE_STAR restores the single-star loop): the same arithmetic as
+// star_exact, split into an evaluation without side effects (the body vector is computed whether or not the star is detected,
+// so that two evaluations interleave as straight-line code) and the accumulation, which the caller applies in star order —
+// B's summation order, and with it every record, is unchanged.
+template <class Tab>
+__device__ __forceinline__ bool star_eval64(const Ctx64& c, const Tab T, const StarRec& s, uint32_t x0, uint32_t x1, double f_ideal,
+                                            double f_ideal2, double half_u, double half_v, double& bx, double& by, double& bz) {
+    const double dn = c.NI[0] * s.x + c.NI[1] * s.y + c.NI[2] * s.z;
+    const double du = c.EU[0] * s.x + c.EU[1] * s.y + c.EU[2] * s.z;
+    const double dv = c.EV[0] * s.x + c.EV[1] * s.y + c.EV[2] * s.z;
+    const double lam = fast_div(c.np0, dn);
+    double z1, z2;
+    box_muller_t(T, x0, x1, z1, z2);
+    const double um = fma(c.sx, z1, fma(lam, du, -c.cu));
+    const double vm = fma(c.sy, z2, fma(lam, dv, -c.cv));
+    const double n2 = fma(vm, vm, fma(um, um, f_ideal2));
+    const double y = seed_rsqrt(n2);
+    const double w = fma(-0.5 * n2 * y, y, 1.5);
+    bx = (um * y) * w; by = (vm * y) * w; bz = (f_ideal * y) * w;
+    return (dn > 0.0) && (fabs(um) <= half_u) && (fabs(vm) <= half_v);
+}
+__device__ __forceinline__ void star_accumulate(double* __restrict__ B, const StarRec& s, double bx, double by, double bz) {
+    B[0] = fma(bx, s.x, B[0]); B[1] = fma(bx, s.y, B[1]); B[2] = fma(bx, s.z, B[2]);
+    B[3] = fma(by, s.x, B[3]); B[4] = fma(by, s.y, B[4]); B[5] = fma(by, s.z, B[5]);
+    B[6] = fma(bz, s.x, B[6]); B[7] = fma(bz, s.y, B[7]); B[8] = fma(bz, s.z, B[8]);
+}
+
 // the exact evaluation as an out-of-line call, for fp32 mode's rare guard-band fall-back (keeps that loop's code small)
 template <class Tab>
 __device__ STMPM_LIBM_INLINE bool star_exact_rare(const Ctx64* c, const Tab T, const StarRec* s, uint32_t x0, uint32_t x1, double f_ideal,
@@ -684,6 +721,28 @@ __device__ __forceinline__ bool star_f32(const Ctx64& c, const Ctx32& cf, const 
         B[6] = fma(bz, s.x, B[6]); B[7] = fma(bz, s.y, B[7]); B[8] = fma(bz, s.z, B[8]);
     }
     return det;
+}
+
+// star_f32 as a side-effect-free evaluation for the two-star loop: `guard` reports a centroid inside the guard band (the
+// caller then takes star_eval64's decision and body vector for that star instead — rare, ~1e-7 of the stars)
+template <class Tab>
+__device__ __forceinline__ bool star_eval32(const Ctx64& c, const Ctx32& cf, const Tab T, const StarRec& s, uint32_t x0, uint32_t x1,
+                                            double f_ideal, double f_ideal2, double half_u, double half_v, double& bx, double& by,
+                                            double& bz, bool& guard) {
+    const double dn = c.NI[0] * s.x + c.NI[1] * s.y + c.NI[2] * s.z;
+    const double du = c.EU[0] * s.x + c.EU[1] * s.y + c.EU[2] * s.z;
+    const double dv = c.EV[0] * s.x + c.EV[1] * s.y + c.EV[2] * s.z;
+    const double lam = fast_div(c.np0, dn);
+    float z1, z2;
+    box_muller_f32(T, x0, x1, z1, z2);
+    const double um = fma(lam, du, -c.cu) + f2d_bits(cf.sxf * z1);
+    const double vm = fma(lam, dv, -c.cv) + f2d_bits(cf.syf * z2);
+    const double eu = fabs(um) - half_u, ev = fabs(vm) - half_v;
+    const int hu = __double2hiint(eu), hv = __double2hiint(ev);
+    guard = (hu & 0x7fffffff) <= cf.guard_hi || (hv & 0x7fffffff) <= cf.guard_hi;
+    const double y = seed_rsqrt(fma(vm, vm, fma(um, um, f_ideal2)));
+    bx = um * y; by = vm * y; bz = f_ideal * y;
+    return (__double2hiint(dn) > 0) && ((hu & hv) < 0);
 }
 
 // Wahba solve in the body frame: B' = (B / n) C, QUEST Newton from lambda0 = 1 (Shuster & Oh 1981), error angle
