@@ -234,9 +234,12 @@ int stmpm_fma_peak(stmpm_t* h, int precision, double* tflops);
  * returns per-trial means [sky-grid stars visited, magnitude passes, pre-filter survivors, detected stars]. */
 int stmpm_work_counters(stmpm_t* h, int64_t n, uint64_t seed, int64_t trial0, const stmpm_dist* dist_host,
                         double* per_trial4_host);
-/* Diagnostic, host-only (no GPU): the table-based Box-Muller of the star loop (MODEL.md §5), compiled for the host from
- * the same source the kernels use, so its accuracy can be checked against libm without a GPU. */
+/* Diagnostic, host-only (no GPU): the table-based Box-Muller (MODEL.md §5) of the parameter sampler, compiled for the host
+ * from the same source the kernels use, so its accuracy (|dz| < 1e-12) can be checked against libm without a GPU. */
 int stmpm_debug_box_muller(const uint32_t* wa, const uint32_t* wb, int64_t n, double* z1, double* z2);
+/* Same for the star loop's shorter evaluation of that draw (centroid noise, fp64 mode): |dz| < 1e-10, where the 1e-9 rad
+ * bar needs ~3e-7 (exp X). */
+int stmpm_debug_box_muller_star(const uint32_t* wa, const uint32_t* wb, int64_t n, double* z1, double* z2);
 /* Same for fp32 mode's Box-Muller (host build: log2f / sqrtf stand in for the MUFU approximations). */
 int stmpm_debug_box_muller_f32(const uint32_t* wa, const uint32_t* wb, int64_t n, float* z1, float* z2);
 /* Number of kernels this library has launched on this handle (bench.py's gpu_launches claim). */

@@ -24,7 +24,7 @@ NORMAL_PARAMS = ("FOCAL_LENGTH", "F_ARR_EPS_X", "F_ARR_EPS_Y", "F_ARR_EPS_Z", "F
 EXPORTS = ("stmpm_last_error", "stmpm_version", "stmpm_create", "stmpm_destroy", "stmpm_check", "stmpm_device_info",
            "stmpm_set_catalog", "stmpm_set_sensor", "stmpm_set_tuning", "stmpm_set_pipeline", "stmpm_stats_len", "stmpm_stats_finalize",
            "stmpm_trials_presampled", "stmpm_trials_presampled_ex", "stmpm_trials_rng", "stmpm_fill_presampled", "stmpm_run_presampled_host", "stmpm_run_presampled_host_ex",
-           "stmpm_run_rng_host", "stmpm_run_rng_host_compact", "stmpm_run_rng_host_compact32", "stmpm_set_host_pipeline", "stmpm_host_copy_roofline", "stmpm_mc_converge", "stmpm_toolplot_failrate", "stmpm_column_hist", "stmpm_toolplot_reduce", "stmpm_fma_peak", "stmpm_work_counters", "stmpm_debug_box_muller", "stmpm_debug_box_muller_f32", "stmpm_launch_count")
+           "stmpm_run_rng_host", "stmpm_run_rng_host_compact", "stmpm_run_rng_host_compact32", "stmpm_set_host_pipeline", "stmpm_host_copy_roofline", "stmpm_mc_converge", "stmpm_toolplot_failrate", "stmpm_column_hist", "stmpm_toolplot_reduce", "stmpm_fma_peak", "stmpm_work_counters", "stmpm_debug_box_muller", "stmpm_debug_box_muller_star", "stmpm_debug_box_muller_f32", "stmpm_launch_count")
 
 
 class SensorCfg(C.Structure):
@@ -104,6 +104,7 @@ def load():
     lib.stmpm_fma_peak.argtypes = [vp, C.c_int, P(dbl)]
     lib.stmpm_work_counters.argtypes = [vp, i64, u64, i64, P(Dist), P(dbl)]
     lib.stmpm_debug_box_muller.argtypes = [vp, vp, i64, vp, vp]
+    lib.stmpm_debug_box_muller_star.argtypes = [vp, vp, i64, vp, vp]
     lib.stmpm_debug_box_muller_f32.argtypes = [vp, vp, i64, vp, vp]
     lib.stmpm_launch_count.argtypes = [vp, P(i64)]
     for name in EXPORTS:

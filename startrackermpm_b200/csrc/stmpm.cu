@@ -2221,6 +2221,14 @@ extern "C" int stmpm_debug_box_muller(const uint32_t* wa, const uint32_t* wb, in
     return 0;
 }
 
+extern "C" int stmpm_debug_box_muller_star(const uint32_t* wa, const uint32_t* wb, int64_t n, double* z1, double* z2) {
+    if (!wa || !wb || !z1 || !z2 || n < 0) return fail(STMPM_E_ARG, "stmpm_debug_box_muller_star: bad arguments");
+    MathTables mt;
+    stmpm_host_tables(&mt);
+    for (int64_t i = 0; i < n; ++i) box_muller_star_tab(&mt, wa[i], wb[i], z1[i], z2[i]);
+    return 0;
+}
+
 extern "C" int stmpm_toolplot_reduce(stmpm_t* h, const double* err_dev, int64_t n, int32_t bins, stmpm_toolplot* out,
                                      double* density_host, void* stream) {
     if (!h || !err_dev || !out || n <= 0 || bins < 1 || bins > 4096)

@@ -209,8 +209,20 @@ static_assert(offsetof(MathTables, sc32) == 4096 + 16384 + 272, "TabSmem::sc32 o
 #endif
 STMPM_HD void box_muller_tab(const MathTables* __restrict__ T, uint32_t wa, uint32_t wb, double& z1, double& z2);
 
-template <class Tab>
+// STAR = false: the full-accuracy draw (|dz| < 2e-13) — the parameter sampler (MODEL.md §6: columns reproduce the oracle's to
+//   1e-11) and the debug entry.
+// STAR = true: the per-star centroid-noise draw of the star loop, three FP64-pipe instructions shorter (round 2, exp X:
+//   +1.2 %): the r^5/5 term of log1p (< 5.6e-15) and the d^4/24 term of cos d (< 3.7e-12) dropped, the angle scale folded
+//   into the remainder's coefficients.  |dz| < 2.5e-11, i.e. a centroid moved by < 2.5e-11 sigma_c px — the 1e-9 rad bar
+//   needs |dz| <~ 3e-7 (sigma_c * dz over a roll lever arm of ~100 px); measured at 2e6 trials x 3 configs: 1e-11 rad.
+//   -DSTMPM_NO_TRIM64 gives the star loop the full draw again.
+template <bool STAR, class Tab>
 STMPM_HD void box_muller_t(const Tab T, uint32_t wa, uint32_t wb, double& z1, double& z2) {
+#if defined(STMPM_NO_TRIM64)
+    constexpr bool TRIM = false;
+#else
+    constexpr bool TRIM = STAR;
+#endif
     // ---- L = -2 ln u1,  u1 = (2 wa + 1) 2^-33.  Exact int -> double through the 2^52 magic number (one DADD, no
     // conversion instruction, no clz / shift normalisation); exponent and mantissa then come from the bit pattern.
     const unsigned long long v = 2ull * wa + 1ull;                         // 33-bit odd integer
@@ -224,12 +236,14 @@ STMPM_HD void box_muller_t(const Tab T, uint32_t wa, uint32_t wb, double& z1, do
     const double r = fma(m, inv_c, -1.0);
     // log1p(r) = r - r^2/2 + r^3/3 - r^4/4 + r^5/5, |r| <= 2^-9 (truncation r^6/6 < 1e-17), Estrin form: depth 3
     const double r2 = r * r;
+    double p;
 #if defined(STMPM_HI_COEF)
     // experiment (round 2, exp J): 1/3 and 1/5 truncated to their high words (relative 2.4e-7 on terms below 2.5e-9), so that
     // they encode as DFMA immediates instead of two register moves each
-    const double p = fma(r2, fma(r2, fma(r, 0.19999992847442627, -0.25), fma(r, 0.33333325386047363, -0.5)), r);
+    p = fma(r2, fma(r2, fma(r, 0.19999992847442627, -0.25), fma(r, 0.33333325386047363, -0.5)), r);
 #else
-    const double p = fma(r2, fma(r2, fma(r, 0.2, -0.25), fma(r, 1.0 / 3.0, -0.5)), r);
+    if (TRIM) p = fma(r2, fma(r2, -0.25, fma(r, 1.0 / 3.0, -0.5)), r);
+    else p = fma(r2, fma(r2, fma(r, 0.2, -0.25), fma(r, 1.0 / 3.0, -0.5)), r);
 #endif
 #if !defined(STMPM_K2_TABLE)
     // -2 ln m + 2 k ln 2, the second term by arithmetic (k exact through the 2^52 magic number): the table read it replaces
@@ -248,15 +262,26 @@ STMPM_HD void box_muller_t(const Tab T, uint32_t wa, uint32_t wb, double& z1, do
     const uint32_t rem = wb & 0x3FFFFFu;
     // d = (pi/512) ((rem + 0.5) / 2^22 - 0.5), |d| <= pi/1024, via the 2^52 magic number (exact, no conversion instruction)
     const double t = bits_to_double(0x4330000000000000ull | (unsigned long long)(2u * rem + 1u));
-    const double d = (t - 4503599631564800.0) * 7.314590396335798e-10;   // (2^52 + 2^22);  pi / 512 / 2^23
-    const double d2 = d * d;
+    constexpr double kc = 7.314590396335798e-10;                         // pi / 512 / 2^23
+    double sd, cd;
+    if (TRIM) {
+        // e = t - (2^52 + 2^22), d = c e:  sin d = e (c - c^3 e^2 / 6),  cos d = 1 - c^2 e^2 / 2 — five instead of seven
+        // FP64-pipe instructions, and cos d does not wait for d
+        const double e = t - 4503599631564800.0;
+        const double q = e * e;
+        sd = e * fma(q, -(kc * kc * kc) / 6.0, kc);
+        cd = fma(q, -(kc * kc) / 2.0, 1.0);
+    } else {
+        const double d = (t - 4503599631564800.0) * kc;
+        const double d2 = d * d;
 #if defined(STMPM_HI_COEF)
-    const double sd = fma(d * d2, -0.16666662693023682, d);              // high-word-only 1/6: 1.2e-15 on top of the truncation
-    const double cd = fma(d2, fma(d2, 0.041666656732559204, -0.5), 1.0);
+        sd = fma(d * d2, -0.16666662693023682, d);                       // high-word-only 1/6: 1.2e-15 on top of the truncation
+        cd = fma(d2, fma(d2, 0.041666656732559204, -0.5), 1.0);
 #else
-    const double sd = fma(d * d2, -1.0 / 6.0, d);                        // truncation d^5/120 < 2.3e-15
-    const double cd = fma(d2, fma(d2, 1.0 / 24.0, -0.5), 1.0);           // truncation d^6/720 < 1.2e-18
+        sd = fma(d * d2, -1.0 / 6.0, d);                                 // truncation d^5/120 < 2.3e-15
+        cd = fma(d2, fma(d2, 1.0 / 24.0, -0.5), 1.0);                    // truncation d^6/720 < 1.2e-18
 #endif
+    }
     double S, C;
     T.sc(j2, S, C);
     const double sq = fma(S, cd, C * sd);
@@ -265,7 +290,10 @@ STMPM_HD void box_muller_t(const Tab T, uint32_t wa, uint32_t wb, double& z1, do
     z2 = R * sq;
 }
 STMPM_HD void box_muller_tab(const MathTables* __restrict__ T, uint32_t wa, uint32_t wb, double& z1, double& z2) {
-    box_muller_t(TabPtr{T}, wa, wb, z1, z2);
+    box_muller_t<false>(TabPtr{T}, wa, wb, z1, z2);
+}
+STMPM_HD void box_muller_star_tab(const MathTables* __restrict__ T, uint32_t wa, uint32_t wb, double& z1, double& z2) {
+    box_muller_t<true>(TabPtr{T}, wa, wb, z1, z2);
 }
 
 // ------------------------------------------------------------------------------------------------ fp32-mode Box-Muller
@@ -603,6 +631,28 @@ __device__ __forceinline__ bool prefilter_geom(const Ctx32& c, const float4 s) {
     return dn > 0.02f && fabsf(u) <= c.limu && fabsf(v) <= c.limv;
 }
 
+// b = (um, vm, f) / |(um, vm, f)|: seed y ~ 1/|.|, one Newton factor w (2^-44 relative, a common scale of one star's b)
+__device__ __forceinline__ void body_vector(double um, double vm, double f_ideal, double f_ideal2, double& bx, double& by, double& bz) {
+    const double n2 = fma(vm, vm, fma(um, um, f_ideal2));
+    const double y = seed_rsqrt(n2);
+#if !defined(STMPM_NO_TRIM64)
+    const double yw = y * fma(-0.5 * n2 * y, y, 1.5);     // exp X: 9 instead of 11 FP64-pipe instructions, one deeper
+    bx = um * yw; by = vm * yw; bz = f_ideal * yw;
+#else
+    const double w = fma(-0.5 * n2 * y, y, 1.5);           // (um y), (vm y), (f y) run beside the Newton chain
+    bx = (um * y) * w; by = (vm * y) * w; bz = (f_ideal * y) * w;
+#endif
+}
+// n.r > 0 (MODEL.md §3).  exp X: on the high word, integer pipe — exact for every dn but a positive denormal below 2^-1022 * 2^-20
+// (survivors of the pre-filter have dn > 0.02; in the band walk and the fall-backs dn is a dot product of unit vectors)
+__device__ __forceinline__ bool dn_positive(double dn) {
+#if !defined(STMPM_NO_TRIM64)
+    return __double2hiint(dn) > 0;
+#else
+    return dn > 0.0;
+#endif
+}
+
 // Exact (fp64) star evaluation: MODEL.md §2-§4. Returns detected?; on detection adds b s^T into B.
 // (x0, x1) = the star's Philox2x32-10 words (MODEL.md §5), computed by the caller.
 template <class Tab>
@@ -620,16 +670,13 @@ __device__ __forceinline__ bool star_exact(const Ctx64& c, const Tab T, const St
     const double lam = fast_div(c.np0, dn);      // dn <= 0 gives a negative / infinite / NaN scale: every comparison below is then false
 #endif
     double z1, z2;
-    box_muller_t(T, x0, x1, z1, z2);
+    box_muller_t<true>(T, x0, x1, z1, z2);
     const double um = fma(c.sx, z1, fma(lam, du, -c.cu));
     const double vm = fma(c.sy, z2, fma(lam, dv, -c.cv));
-    const bool det = (dn > 0.0) && (fabs(um) <= half_u) && (fabs(vm) <= half_v);
+    const bool det = dn_positive(dn) && (fabs(um) <= half_u) && (fabs(vm) <= half_v);
     if (det) {
-        // b = (um, vm, f) / |.|: seed y ~ 1/|.|, one Newton factor w; (um y), (vm y), (f y) run beside the Newton chain
-        const double n2 = fma(vm, vm, fma(um, um, f_ideal2));
-        const double y = seed_rsqrt(n2);
-        const double w = fma(-0.5 * n2 * y, y, 1.5);
-        const double bx = (um * y) * w, by = (vm * y) * w, bz = (f_ideal * y) * w;
+        double bx, by, bz;
+        body_vector(um, vm, f_ideal, f_ideal2, bx, by, bz);
         B[0] = fma(bx, s.x, B[0]); B[1] = fma(bx, s.y, B[1]); B[2] = fma(bx, s.z, B[2]);
         B[3] = fma(by, s.x, B[3]); B[4] = fma(by, s.y, B[4]); B[5] = fma(by, s.z, B[5]);
         B[6] = fma(bz, s.x, B[6]); B[7] = fma(bz, s.y, B[7]); B[8] = fma(bz, s.z, B[8]);
@@ -649,14 +696,11 @@ __device__ __forceinline__ bool star_eval64(const Ctx64& c, const Tab T, const S
     const double dv = c.EV[0] * s.x + c.EV[1] * s.y + c.EV[2] * s.z;
     const double lam = fast_div(c.np0, dn);
     double z1, z2;
-    box_muller_t(T, x0, x1, z1, z2);
+    box_muller_t<true>(T, x0, x1, z1, z2);
     const double um = fma(c.sx, z1, fma(lam, du, -c.cu));
     const double vm = fma(c.sy, z2, fma(lam, dv, -c.cv));
-    const double n2 = fma(vm, vm, fma(um, um, f_ideal2));
-    const double y = seed_rsqrt(n2);
-    const double w = fma(-0.5 * n2 * y, y, 1.5);
-    bx = (um * y) * w; by = (vm * y) * w; bz = (f_ideal * y) * w;
-    return (dn > 0.0) && (fabs(um) <= half_u) && (fabs(vm) <= half_v);
+    body_vector(um, vm, f_ideal, f_ideal2, bx, by, bz);
+    return dn_positive(dn) && (fabs(um) <= half_u) && (fabs(vm) <= half_v);
 }
 __device__ __forceinline__ void star_accumulate(double* __restrict__ B, const StarRec& s, double bx, double by, double bz) {
     B[0] = fma(bx, s.x, B[0]); B[1] = fma(bx, s.y, B[1]); B[2] = fma(bx, s.z, B[2]);

@@ -321,12 +321,14 @@ class TrialEngine:
         return summarize(stats, self.hist_log2_sub)
 
 
-def debug_box_muller(wa: np.ndarray, wb: np.ndarray):
-    """Host build of the kernels' table-based Box-Muller (diagnostic; no GPU needed)."""
+def debug_box_muller(wa: np.ndarray, wb: np.ndarray, star: bool = False):
+    """Host build of the kernels' table-based Box-Muller (diagnostic; no GPU needed): the parameter sampler's full-accuracy
+    draw, or (star=True) the star loop's shorter evaluation of the same draw."""
     wa = np.ascontiguousarray(wa, dtype=np.uint32)
     wb = np.ascontiguousarray(wb, dtype=np.uint32)
     z1, z2 = np.empty(wa.size), np.empty(wa.size)
-    _abi.check(_abi.load().stmpm_debug_box_muller(_ptr(wa), _ptr(wb), wa.size, _ptr(z1), _ptr(z2)))
+    fn = _abi.load().stmpm_debug_box_muller_star if star else _abi.load().stmpm_debug_box_muller
+    _abi.check(fn(_ptr(wa), _ptr(wb), wa.size, _ptr(z1), _ptr(z2)))
     return z1, z2
 
 

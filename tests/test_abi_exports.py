@@ -70,6 +70,11 @@ def test_table_box_muller_matches_libm(lib_built):
     z1, z2 = engine.debug_box_muller(wa, wb)
     r1, r2 = philox.box_muller(wa, wb)
     assert np.abs(z1 - r1).max() < 1e-12 and np.abs(z2 - r2).max() < 1e-12
+    # the star loop's shorter evaluation of the same draw (three FP64-pipe instructions fewer per star): two truncations worth
+    # < 2.5e-11 in z.  The 1e-9 rad bar tolerates |dz| ~ 3e-7 (a centroid moved by sigma_c * dz over a ~100 px roll lever arm).
+    s1, s2 = engine.debug_box_muller(wa, wb, star=True)
+    assert np.abs(s1 - r1).max() < 1e-10 and np.abs(s2 - r2).max() < 1e-10
+    assert np.abs(s1 - z1).max() > 0                                        # it IS the other code path
 
 
 def test_engine_rejects_mis_sized_host_buffers(lib_built):
