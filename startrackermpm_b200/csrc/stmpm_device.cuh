@@ -214,7 +214,8 @@ STMPM_HD void box_muller_tab(const MathTables* __restrict__ T, uint32_t wa, uint
 // STAR = true: the per-star centroid-noise draw of the star loop, three FP64-pipe instructions shorter (round 2, exp X:
 //   +1.2 %): the r^5/5 term of log1p (< 5.6e-15) and the d^4/24 term of cos d (< 3.7e-12) dropped, the angle scale folded
 //   into the remainder's coefficients.  |dz| < 2.5e-11, i.e. a centroid moved by < 2.5e-11 sigma_c px — the 1e-9 rad bar
-//   needs |dz| <~ 3e-7 (sigma_c * dz over a roll lever arm of ~100 px); measured at 2e6 trials x 3 configs: 1e-11 rad.
+//   needs |dz| <~ 3e-7 (sigma_c * dz over a roll lever arm of ~100 px); parity at 2e6 trials x 3 configs is unchanged by it
+//   (max |d error| 6.9e-13 / 1.3e-12 / 9e-14 rad, tests/test_gpu_scale.py: the Wahba solve's rounding dominates).
 //   -DSTMPM_NO_TRIM64 gives the star loop the full draw again.
 template <bool STAR, class Tab>
 STMPM_HD void box_muller_t(const Tab T, uint32_t wa, uint32_t wb, double& z1, double& z2) {
