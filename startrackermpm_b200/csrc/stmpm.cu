@@ -1,7 +1,7 @@
 // stmpm.cu — kernels + C ABI (include/stmpm.h) of the B200-native StarTrackerMPM Monte Carlo trial loop.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC  (see build.py)
 //
-// Kernel design: persistent CTAs, one per SM, 512 threads, one trial per thread.  The fp32 copy of the
+// Kernel design: persistent CTAs, one per SM, 384 threads, one trial per thread.  The fp32 copy of the
 // sky-grid-sorted catalog (16 B/star), the Box-Muller tables, the per-thread survivor lists and the CTA's sort window +
 // group scheduler live in shared memory; the exact fp64 star records (one 32 B sector each) are gathered from L2 only for
 // pre-filter survivors; the error histogram is accumulated with fire-and-forget REDs in L2.
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
     // ---- work distribution.  The CTA owns units blockIdx.x, blockIdx.x + gridDim.x, ... (unit = a contiguous range of
     // one segment's trials); a unit is cut into windows of `win` trials.  Each window is ordered by work key ONCE for the
     // whole CTA (counting sort by one warp, into the permutation buffer the previous-but-one window has vacated), and the
-    // 16 warps then claim its groups of 32 consecutive sorted trials from a shared counter.  The wider the window, the
+    // 12 warps then claim its groups of 32 consecutive sorted trials from a shared counter.  The wider the window, the
     // more alike the 32 trials a warp runs in lock-step (2 048 instead of 128 trials: ~8 % of the issue slots, lanes idle in
     // the star loop) — but the wider the 32 lanes' column gathers scatter (launch_trials picks the window per mode).
     // No CTA barrier: window w + 1 is built by the warp that claims the first group of window w, while the others consume w.
@@ -683,9 +683,10 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                 }
 
                 // The truth attitude C (18 registers) is needed again only by the solve: park it in local memory (L1) for the
-                // duration of the candidate scan and the star loop.  At the 128-register cap ptxas otherwise spills values of
-                // its own choosing inside the loops and sinks the next star record's load to just before its use (round 2,
-                // fp32 instantiation: 19 % of all stall samples on the first instruction that reuses the load's registers).
+                // duration of the candidate scan and the star loop.  At the register cap (128 with 512 threads, 168 with 384 and
+                // two stars per iteration) ptxas otherwise spills values of its own choosing inside the loops and sinks the next
+                // star record's load to just before its use (round 2, fp32 instantiation: 19 % of all stall samples on the first
+                // instruction that reuses the load's registers; two stars without parking: -6.5 %, exp U).
 #if !defined(STMPM_NO_PARK)
                 volatile double c_park[9];
 #pragma unroll
