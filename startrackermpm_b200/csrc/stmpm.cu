@@ -858,6 +858,9 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                         double4 r0 = make_double4(0.0, 0.0, 0.0, 0.0), r1 = r0;
                         if (cnt > 0) r0 = ld_rec(a.cat64 + lds_u16(sb_row));
                         if (cnt > 1) r1 = ld_rec(a.cat64 + lds_u16(sb_row + (uint32_t)(TPB * 2u)));
+#if defined(STMPM_STAR_UNROLL)
+#pragma unroll 2
+#endif
                         for (int j = 0; j < cnt; j += 2) {
                             const bool has1 = j + 1 < cnt;     // odd count: the second slot re-evaluates a stale record, result dropped
                             StarRec s0, s1;
@@ -872,8 +875,16 @@ __global__ void __launch_bounds__(TPB, 1) trials_kernel(const KArgs a) {
                             // the magnitude word takes part in the decision: see the single-star loop (keeps it alive)
                             const bool ok0 = __int_as_float(__double2hiint(r0.w)) <= cf.magf;
                             const bool ok1 = __int_as_float(__double2hiint(r1.w)) <= cf.magf;
+#if defined(STMPM_UNCOND_PREFETCH)
+                            // experiment (round 2, exp Y): unconditional prefetch of clamped list entries.  A predicated load has
+                            // to preserve its destination when the predicate is false, and slot 1's predicate (j + 3 < cnt) is not
+                            // the loop's: ptxas copies the record out and back around the load (16 moves per iteration)
+                            r0 = ld_rec(a.cat64 + lds_u16(sb_row + (uint32_t)min(j + 2, cnt - 1) * (TPB * 2u)));
+                            r1 = ld_rec(a.cat64 + lds_u16(sb_row + (uint32_t)min(j + 3, cnt - 1) * (TPB * 2u)));
+#else
                             if (j + 2 < cnt) r0 = ld_rec(a.cat64 + lds_u16(sb_row + (uint32_t)(j + 2) * (TPB * 2u)));
                             if (j + 3 < cnt) r1 = ld_rec(a.cat64 + lds_u16(sb_row + (uint32_t)(j + 3) * (TPB * 2u)));
+#endif
                             uint32_t x00, x01, x10, x11;
                             philox2x32_10(s0.star_id, kb, ka, x00, x01);
                             philox2x32_10(s1.star_id, kb, ka, x10, x11);
